@@ -1,0 +1,159 @@
+// TEST INFRASTRUCTURE ONLY (oracle/).  Host (CPU) definitions of the synthetic
+// log-density targets named in SURVEY.md §8(d).  They play the role of the
+// user's `target_log_kernel(vals_inp, grad_out, target_data)` callback
+// (contract: /root/reference/examples/eigen/hmc_normal.cpp:44-76 — grad_out may
+// be null, the return value is log pi(x)).  Both the unmodified-reference
+// driver (ref_driver.cpp) and the restated oracle (oracle.cpp) call these, so
+// the two CPU paths see bit-identical callbacks.
+//
+// `sum_mode` selects the order of the d-term reductions:
+//   SUM_SEQ  : plain index order (what the stand-in Eigen does),
+//   SUM_WARP : the order the CUDA kernels use — element j lives on lane
+//              (j % 64) / 2 of a 32-lane warp (128-bit lane-pair striping), each
+//              lane adds its elements in increasing j, then a 5-stage xor
+//              butterfly (offsets 16,8,4,2,1) combines the lanes.
+// Element-wise results never depend on sum_mode.
+#ifndef MCMC_B200_ORACLE_HOST_TARGETS_HPP
+#define MCMC_B200_ORACLE_HOST_TARGETS_HPP
+
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#include <vector>
+
+namespace otgt
+{
+
+enum { SUM_SEQ = 0, SUM_WARP = 1 };
+
+enum {
+    TGT_ISO_GAUSS    = 0,  // log pi = -1/2 |x|^2                              (C1, C2)
+    TGT_DIAG_GAUSS   = 1,  // log pi = -1/2 sum_i w_i x_i^2, data = w[d]
+    TGT_DENSE_GAUSS  = 2,  // log pi = -1/2 x' P x, data = P[d*d] row-major     (C4)
+    TGT_LINREG       = 3,  // log pi = -1/2 t' A t + b' t, data = A[d*d], b[d]  (C3)
+    TGT_NORMAL_MODEL = 4   // 2-parameter Normal(mu, sigma) likelihood on sufficient statistics
+                           // data = {n, xbar, M2 = sum (x - xbar)^2}  (examples/eigen/*_normal.cpp)
+};
+
+inline int lane_of(int j) { return (j % 64) / 2; }
+
+// sum of t[0..n) in the requested order
+inline double reduce_sum(const double* t, int n, int sum_mode)
+{
+    if (sum_mode == SUM_SEQ) {
+        double s = 0.0;
+        for (int j = 0; j < n; ++j) s = s + t[j];
+        return s;
+    }
+    double lane[32];
+    bool has[32];
+    for (int l = 0; l < 32; ++l) { lane[l] = 0.0; has[l] = false; }
+    for (int j = 0; j < n; ++j) {
+        const int l = lane_of(j);
+        // first term initialises the lane partial (the kernel starts from 0.0 + t,
+        // which is exact, so both conventions agree bit-for-bit)
+        lane[l] = has[l] ? lane[l] + t[j] : 0.0 + t[j];
+        has[l] = true;
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        double nxt[32];
+        for (int l = 0; l < 32; ++l) nxt[l] = lane[l] + lane[l ^ off];
+        for (int l = 0; l < 32; ++l) lane[l] = nxt[l];
+    }
+    return lane[0];
+}
+
+inline double dot(const double* a, const double* b, int n, int sum_mode)
+{
+    std::vector<double> t(static_cast<size_t>(n));
+    for (int j = 0; j < n; ++j) t[size_t(j)] = a[j] * b[j];
+    return reduce_sum(t.data(), n, sum_mode);
+}
+
+// y = A x for row-major A (n x n); each y_i accumulates in increasing j
+inline void gemv_rowmajor(const double* A, const double* x, double* y, int n)
+{
+    for (int i = 0; i < n; ++i) {
+        double s = 0.0;
+        const double* row = A + size_t(i) * size_t(n);
+        for (int j = 0; j < n; ++j) s = s + row[j] * x[j];
+        y[i] = s;
+    }
+}
+
+// log pi(x); if grad != nullptr also d log pi / dx.
+inline double value_and_grad(int target_id, const double* data, const double* x, double* grad, int d, int sum_mode)
+{
+    std::vector<double> t(static_cast<size_t>(d));
+    switch (target_id) {
+    case TGT_ISO_GAUSS: {
+        for (int j = 0; j < d; ++j) t[size_t(j)] = x[j] * x[j];
+        const double s = reduce_sum(t.data(), d, sum_mode);
+        if (grad)
+            for (int j = 0; j < d; ++j) grad[j] = -x[j];
+        return -(0.5 * s);
+    }
+    case TGT_DIAG_GAUSS: {
+        for (int j = 0; j < d; ++j) t[size_t(j)] = (data[j] * x[j]) * x[j];
+        const double s = reduce_sum(t.data(), d, sum_mode);
+        if (grad)
+            for (int j = 0; j < d; ++j) grad[j] = -(data[j] * x[j]);
+        return -(0.5 * s);
+    }
+    case TGT_DENSE_GAUSS: {
+        std::vector<double> y(static_cast<size_t>(d));
+        gemv_rowmajor(data, x, y.data(), d);
+        for (int j = 0; j < d; ++j) t[size_t(j)] = x[j] * y[size_t(j)];
+        const double s = reduce_sum(t.data(), d, sum_mode);
+        if (grad)
+            for (int j = 0; j < d; ++j) grad[j] = -y[size_t(j)];
+        return -(0.5 * s);
+    }
+    case TGT_LINREG: {
+        const double* A = data;
+        const double* b = data + size_t(d) * size_t(d);
+        std::vector<double> y(static_cast<size_t>(d));
+        gemv_rowmajor(A, x, y.data(), d);
+        // log pi = sum_j x_j (b_j - y_j / 2)
+        for (int j = 0; j < d; ++j) t[size_t(j)] = x[j] * (b[j] - 0.5 * y[size_t(j)]);
+        const double s = reduce_sum(t.data(), d, sum_mode);
+        if (grad)
+            for (int j = 0; j < d; ++j) grad[j] = b[j] - y[size_t(j)];
+        return s;
+    }
+    case TGT_NORMAL_MODEL: {
+        const double n = data[0], xbar = data[1], M2 = data[2];
+        const double mu = x[0], sigma = x[1];
+        const double dm = xbar - mu;
+        const double ss = M2 + n * (dm * dm);  // sum (x_k - mu)^2
+        const double s2 = sigma * sigma;
+        const double ret = -n * (0.91893853320467274178 + std::log(sigma)) - ss / (2.0 * s2);
+        if (grad) {
+            grad[0] = (n * dm) / s2;
+            grad[1] = ss / (s2 * sigma) - n / sigma;
+        }
+        return ret;
+    }
+    default:
+        return std::nan("");
+    }
+}
+
+// Fisher-information metric for TGT_NORMAL_MODEL (examples/eigen/rmhmc_normal.cpp:82-111):
+// G = diag(n/sigma^2, 2n/sigma^2); dG/dmu = 0; dG/dsigma = -2 G / sigma.
+// G: d*d column-major; dG: d blocks of d*d column-major (may be null).
+inline void metric_normal_model(const double* data, const double* x, double* G, double* dG)
+{
+    const double n = data[0];
+    const double sigma = x[1];
+    const double s2 = sigma * sigma;
+    G[0] = n / s2; G[1] = 0.0; G[2] = 0.0; G[3] = 2.0 * n / s2;
+    if (dG) {
+        for (int k = 0; k < 8; ++k) dG[k] = 0.0;
+        for (int k = 0; k < 4; ++k) dG[4 + k] = (-2.0 * G[k]) / sigma;
+    }
+}
+
+}  // namespace otgt
+
+#endif
