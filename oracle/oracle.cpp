@@ -1,0 +1,792 @@
+// TEST INFRASTRUCTURE ONLY (oracle/) — never linked, imported or executed by the
+// product path (mcmc_b200/, include/).  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load liboracle.so.
+//
+// A plain-C++ CPU restatement of the reference's four samplers with a pluggable
+// RNG source and a pluggable reduction order, written from SURVEY.md Appendices
+// C/D/E and checked bit-for-bit against the UNMODIFIED reference sources
+// (oracle/_ref, built by oracle/Makefile) in tests/test_oracle_vs_reference.py.
+// Each function cites the reference lines it follows.
+//
+// PARITY PINNING: the reference ships no tests, golden vectors or KATs for this
+// path, so the oracle is pinned against outputs of the
+// reference itself run here (oracle/_ref) and against tests/golden/*.json, which
+// tests/golden/make_golden.py generated from oracle/_ref.
+//
+// RNG sources
+//   RNG_MT     std::mt19937_64 consumed exactly like BaseMatrixOps does
+//              (include/BaseMatrixOps/include/stats/rnorm.hpp:46-60,120-128: a FRESH
+//               std::normal_distribution per variate; runif.hpp:46-64: nextafter(0,1)
+//               then uniform_real_distribution) — SURVEY Q1, Q2.
+//   RNG_TAPE   a flat per-chain stream of doubles consumed in order (what the CUDA
+//              kernels read in tape mode).
+//   RNG_PHILOX Philox4x32-10, key = (seed_lo, seed_hi), counter =
+//              (index, draw+1, chain, stream); stream 0 = normals by Box-Muller
+//              pair q -> elements (2q, 2q+1), stream 1 = uniforms.  This is the
+//              engine's own production RNG (not in the reference); the oracle
+//              restates it independently from the spec in DESIGN.md.
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <random>
+#include <vector>
+
+#include "host_targets.hpp"
+
+namespace
+{
+
+typedef std::vector<double> vec;
+
+enum { RNG_MT = 0, RNG_TAPE = 1, RNG_PHILOX = 2 };
+enum { S_HMC = 0, S_MALA = 1, S_NUTS = 2, S_RMHMC = 3 };
+
+// ---------------------------------------------------------------- Philox4x32-10
+
+inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4])
+{
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = uint64_t(M0) * c0;
+        const uint64_t p1 = uint64_t(M1) * c2;
+        const uint32_t n0 = uint32_t(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = uint32_t(p1);
+        const uint32_t n2 = uint32_t(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = uint32_t(p0);
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+inline double u53_open(uint32_t hi, uint32_t lo)
+{
+    const uint64_t k = ((uint64_t(hi) << 32) | lo) >> 11;  // 53 bits
+    return (double(k) + 0.5) * 1.1102230246251565404e-16;  // 2^-53, result in (0,1)
+}
+
+// sin(pi t), cos(pi t) for t in [0,2) with exact octant reduction
+inline void sincospi_host(double t, double* s, double* c)
+{
+    // t = q/2 + r, q in {0,1,2,3}, r in [-1/4, 1/4]
+    const double q = std::floor(t * 2.0 + 0.5);
+    const double r = t - q * 0.5;
+    const double a = 3.14159265358979323846 * r;
+    const double sr = std::sin(a), cr = std::cos(a);
+    switch (int(q) & 3) {
+    case 0: *s = sr; *c = cr; break;
+    case 1: *s = cr; *c = -sr; break;
+    case 2: *s = -sr; *c = -cr; break;
+    default: *s = -cr; *c = sr; break;
+    }
+}
+
+// ---------------------------------------------------------------- RNG sources
+
+struct Rng {
+    int mode;
+    std::mt19937_64 eng;
+    const double* tape; long tape_len; long cursor;
+    uint32_t k0, k1; uint32_t chain;
+    double* rec; long rec_cap; long rec_n;  // optional recording of every variate returned
+
+    void record(double v) { if (rec && rec_n < rec_cap) rec[rec_n] = v; ++rec_n; }
+
+    // d normals for draw `draw` (draw = -1: the pre-loop draw of NUTS / RM-HMC)
+    void normals(long draw, int d, double* z)
+    {
+        if (mode == RNG_MT) {
+            for (int i = 0; i < d; ++i) {
+                std::normal_distribution<double> nd(0.0, 1.0);  // fresh per variate (rnorm.hpp:57)
+                z[i] = 0.0 + 1.0 * nd(eng);                     // mu_par + sigma_par*norm_dist(engine) (:59)
+            }
+        } else if (mode == RNG_TAPE) {
+            for (int i = 0; i < d; ++i) z[i] = (cursor < tape_len) ? tape[cursor++] : std::nan("");
+        } else {
+            for (int q = 0; 2 * q < d; ++q) {
+                uint32_t r[4];
+                philox4x32_10(uint32_t(q), uint32_t(draw + 1), chain, 0u, k0, k1, r);
+                const double u1 = u53_open(r[0], r[1]), u2 = u53_open(r[2], r[3]);
+                const double rad = std::sqrt(-2.0 * std::log(u1));
+                double s, c;
+                sincospi_host(2.0 * u2, &s, &c);
+                z[2 * q] = rad * c;
+                if (2 * q + 1 < d) z[2 * q + 1] = rad * s;
+            }
+        }
+        for (int i = 0; i < d; ++i) record(z[i]);
+    }
+
+    // k-th uniform of draw `draw`
+    double uniform(long draw, int k)
+    {
+        double u;
+        if (mode == RNG_MT) {
+            const double a_adj = std::nextafter(0.0, 1.0);  // runif.hpp:60
+            std::uniform_real_distribution<double> ud(a_adj, 1.0);
+            u = ud(eng);
+        } else if (mode == RNG_TAPE) {
+            u = (cursor < tape_len) ? tape[cursor++] : std::nan("");
+        } else {
+            uint32_t r[4];
+            philox4x32_10(uint32_t(k), uint32_t(draw + 1), chain, 1u, k0, k1, r);
+            u = u53_open(r[0], r[1]);
+        }
+        record(u);
+        return u;
+    }
+};
+
+// ---------------------------------------------------------------- small dense linear algebra
+// column-major d x d, mirroring the stand-in Eigen's operation order (oracle/standin/Eigen/Dense)
+
+struct Ctx {
+    int target_id; const double* tdata; int d; int sum_mode;
+    bool identity;            // precond empty -> M = I (src/hmc.cpp:57)
+    vec M, Minv, S;           // precond, inverse, "sqrt" factor (CHOL_LOWER semantics per chol_mode)
+};
+
+void mat_inverse(const vec& A, int n, vec& inv)
+{
+    vec lu(A);
+    std::vector<int> piv(n);
+    for (int i = 0; i < n; ++i) piv[i] = i;
+    auto at = [&](vec& m, int i, int j) -> double& { return m[size_t(j) * n + i]; };
+    for (int k = 0; k < n; ++k) {
+        int p = k; double best = std::abs(at(lu, k, k));
+        for (int i = k + 1; i < n; ++i)
+            if (std::abs(at(lu, i, k)) > best) { best = std::abs(at(lu, i, k)); p = i; }
+        if (p != k) {
+            for (int j = 0; j < n; ++j) std::swap(at(lu, k, j), at(lu, p, j));
+            std::swap(piv[k], piv[p]);
+        }
+        const double dd = at(lu, k, k);
+        for (int i = k + 1; i < n; ++i) at(lu, i, k) /= dd;
+        for (int j = k + 1; j < n; ++j) {
+            const double t = at(lu, k, j);
+            for (int i = k + 1; i < n; ++i) at(lu, i, j) -= at(lu, i, k) * t;
+        }
+    }
+    inv.assign(size_t(n) * n, 0.0);
+    vec y(n);
+    for (int c = 0; c < n; ++c) {
+        for (int i = 0; i < n; ++i) y[i] = (piv[i] == c) ? 1.0 : 0.0;
+        for (int i = 0; i < n; ++i) { double s = y[i]; for (int j = 0; j < i; ++j) s -= at(lu, i, j) * y[j]; y[i] = s; }
+        for (int i = n - 1; i >= 0; --i) { double s = y[i]; for (int j = i + 1; j < n; ++j) s -= at(lu, i, j) * y[j]; y[i] = s / at(lu, i, i); }
+        for (int i = 0; i < n; ++i) at(inv, i, c) = y[i];
+    }
+}
+
+// in-place lower Cholesky; chol_mode 1 keeps A's strict upper triangle (Eigen matrixLLT storage),
+// chol_mode 0 zeroes it (Armadillo chol(A,"lower"), core/cholesky.hpp:31)
+void mat_chol(const vec& A, int n, int chol_mode, vec& L)
+{
+    L = A;
+    auto at = [&](int i, int j) -> double& { return L[size_t(j) * n + i]; };
+    for (int j = 0; j < n; ++j) {
+        double s = at(j, j);
+        for (int k = 0; k < j; ++k) s -= at(j, k) * at(j, k);
+        const double dd = std::sqrt(s);
+        at(j, j) = dd;
+        for (int i = j + 1; i < n; ++i) {
+            double t = at(i, j);
+            for (int k = 0; k < j; ++k) t -= at(i, k) * at(j, k);
+            at(i, j) = t / dd;
+        }
+    }
+    if (chol_mode == 0)
+        for (int j = 1; j < n; ++j)
+            for (int i = 0; i < j; ++i) at(i, j) = 0.0;
+}
+
+// y_i = sum_j A_ij * (alpha * v_j), j increasing (ScaledMat * vector in the stand-in)
+void gemv_scaled(const vec& A, int n, double alpha, const double* v, double* y)
+{
+    for (int i = 0; i < n; ++i) y[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double t = alpha * v[j];
+        const double* col = &A[size_t(j) * n];
+        for (int i = 0; i < n; ++i) y[i] += col[i] * t;
+    }
+}
+void gemv_plain(const vec& A, int n, const double* v, double* y)
+{
+    for (int i = 0; i < n; ++i) y[i] = 0.0;
+    for (int j = 0; j < n; ++j) {
+        const double t = v[j];
+        const double* col = &A[size_t(j) * n];
+        for (int i = 0; i < n; ++i) y[i] += col[i] * t;
+    }
+}
+void matmul(const vec& A, const vec& B, int n, vec& C)
+{
+    C.assign(size_t(n) * n, 0.0);
+    for (int j = 0; j < n; ++j)
+        for (int l = 0; l < n; ++l) {
+            const double t = B[size_t(j) * n + l];
+            for (int i = 0; i < n; ++i) C[size_t(j) * n + i] += A[size_t(l) * n + i] * t;
+        }
+}
+
+double logdet_llt(const vec& A, int n)
+{
+    vec L; mat_chol(A, n, 1, L);
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += std::log(L[size_t(i) * n + i]) * 2;  // (diag.log()*2).sum(), core/log_det.hpp:35
+    return s;
+}
+
+// x = A^-1 b by Householder QR with column pivoting (stand-in's colPivHouseholderQr().solve)
+void qr_solve(const vec& A, int n, const double* b, double* x)
+{
+    vec q(A), rhs(b, b + n);
+    std::vector<int> perm(n);
+    for (int j = 0; j < n; ++j) perm[j] = j;
+    auto at = [&](int i, int j) -> double& { return q[size_t(j) * n + i]; };
+    for (int k = 0; k < n; ++k) {
+        int p = k; double best = -1.0;
+        for (int j = k; j < n; ++j) {
+            double s = 0.0;
+            for (int i = k; i < n; ++i) s += at(i, j) * at(i, j);
+            if (s > best) { best = s; p = j; }
+        }
+        if (p != k) { for (int i = 0; i < n; ++i) std::swap(at(i, k), at(i, p)); std::swap(perm[k], perm[p]); }
+        double nrm = 0.0;
+        for (int i = k; i < n; ++i) nrm += at(i, k) * at(i, k);
+        nrm = std::sqrt(nrm);
+        if (nrm == 0.0) continue;
+        const double alpha = (at(k, k) > 0.0) ? -nrm : nrm;
+        vec v(n - k);
+        for (int i = k; i < n; ++i) v[i - k] = at(i, k);
+        v[0] -= alpha;
+        double vn2 = 0.0;
+        for (size_t i = 0; i < v.size(); ++i) vn2 += v[i] * v[i];
+        if (vn2 == 0.0) continue;
+        for (int j = k; j < n; ++j) {
+            double s = 0.0;
+            for (int i = k; i < n; ++i) s += v[i - k] * at(i, j);
+            const double f = 2.0 * s / vn2;
+            for (int i = k; i < n; ++i) at(i, j) -= f * v[i - k];
+        }
+        double s = 0.0;
+        for (int i = k; i < n; ++i) s += v[i - k] * rhs[i];
+        const double f = 2.0 * s / vn2;
+        for (int i = k; i < n; ++i) rhs[i] -= f * v[i - k];
+    }
+    vec z(n);
+    for (int i = n - 1; i >= 0; --i) {
+        double s = rhs[i];
+        for (int j = i + 1; j < n; ++j) s -= at(i, j) * z[j];
+        z[i] = s / at(i, i);
+    }
+    for (int j = 0; j < n; ++j) x[perm[j]] = z[j];
+}
+
+// ---------------------------------------------------------------- shared pieces
+
+double logp(const Ctx& c, const double* x, double* grad)
+{
+    return otgt::value_and_grad(c.target_id, c.tdata, x, grad, c.d, c.sum_mode);
+}
+
+// p = sqrt_precond * z   (src/hmc.cpp:158)
+void momentum_from_normals(const Ctx& c, const double* z, double* p)
+{
+    if (c.identity) { for (int i = 0; i < c.d; ++i) p[i] = z[i]; return; }
+    gemv_plain(c.S, c.d, z, p);
+}
+
+// K = p.(M^-1 p)/2   (src/hmc.cpp:160,184)
+double kinetic(const Ctx& c, const double* p)
+{
+    if (c.identity) return otgt::dot(p, p, c.d, c.sum_mode) / 2.0;
+    vec t(c.d);
+    gemv_plain(c.Minv, c.d, p, t.data());
+    return otgt::dot(p, t.data(), c.d, c.sum_mode) / 2.0;
+}
+
+// one leapfrog step of size eps, the reference's operation order (src/hmc.cpp:164-176, src/nuts.cpp:139-154):
+//   p <- p + (eps*grad(x))/2 ; x <- x + (eps*M^-1) p ; p <- p + (eps*grad(x))/2       
+void leapfrog(const Ctx& c, double eps, double* x, double* p)
+{
+    const int d = c.d;
+    vec g(d), t(d);
+    logp(c, x, g.data());
+    for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
+    if (c.identity) {
+        for (int i = 0; i < d; ++i) x[i] = x[i] + eps * p[i];
+    } else {
+        gemv_scaled(c.Minv, d, eps, p, t.data());
+        for (int i = 0; i < d; ++i) x[i] = x[i] + t[i];
+    }
+    logp(c, x, g.data());
+    for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
+}
+
+void setup_precond(Ctx& c, const double* precond, int chol_mode)
+{
+    const int d = c.d;
+    c.identity = (precond == nullptr);
+    if (!c.identity) {
+        c.M.assign(precond, precond + size_t(d) * d);
+        mat_inverse(c.M, d, c.Minv);
+        mat_chol(c.M, d, chol_mode, c.S);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+struct oracle_cfg_t {
+    int sampler, target_id;
+    const double* tdata;
+    int d;
+    long n_burnin, n_keep, n_leap_steps;
+    double step_size;
+    const double* precond;  // d*d column-major or null
+    int chol_mode;          // 1 = Eigen matrixLLT storage (Q8), 0 = true lower factor
+    long n_fp_steps;
+    long n_adapt_draws;
+    double target_accept_rate, gamma_val, t0_val, kappa_val;
+    long max_tree_depth;
+    int rng_mode;
+    unsigned long seed;
+    const double* tape; long tape_len;
+    long chain_id;
+    int sum_mode;
+    int mala_exact_dmvnorm;  // 1: two dmvnorm() with LLT log-det + QR solve (mala.ipp:63-64); 0: cancelled form
+    double* tape_out; long tape_out_cap;  // optional: every variate consumed, in order
+};
+
+struct oracle_res_t {
+    long n_accept;
+    long tape_used;      // variates consumed
+    double final_step;   // nuts: step size after the last draw
+    long n_leapfrog;     // reference-order leapfrog count (nuts: with multiplicity)
+};
+
+static void init_rng(Rng& r, const oracle_cfg_t* cfg)
+{
+    r.mode = cfg->rng_mode;
+    r.eng.seed(cfg->seed);
+    r.tape = cfg->tape; r.tape_len = cfg->tape_len; r.cursor = 0;
+    r.k0 = uint32_t(cfg->seed); r.k1 = uint32_t(uint64_t(cfg->seed) >> 32);
+    r.chain = uint32_t(cfg->chain_id);
+    r.rec = cfg->tape_out; r.rec_cap = cfg->tape_out_cap; r.rec_n = 0;
+}
+
+// ------------------------------------------------------------------ HMC (src/hmc.cpp:30-227, Appendix E)
+static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
+{
+    Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
+    setup_precond(c, cfg->precond, cfg->chol_mode);
+    Rng rng; init_rng(rng, cfg);
+    const int d = c.d;
+    const long n_total = cfg->n_burnin + cfg->n_keep;
+    const double eps = cfg->step_size;
+    const unsigned n_leap = unsigned(cfg->n_leap_steps);  // Q22
+
+    vec prev(x0, x0 + d), cur(d), p(d), z(d);
+    double prev_U = -logp(c, prev.data(), nullptr);   // :140
+    long n_accept = 0, n_lf = 0;
+
+    for (long t = 0; t < n_total; ++t) {
+        rng.normals(t, d, z.data());                 // :156
+        momentum_from_normals(c, z.data(), p.data()); // :158
+        const double prev_K = kinetic(c, p.data());   // :160
+        cur = prev;                                   // :162
+        for (unsigned k = 0; k < n_leap; ++k) { leapfrog(c, eps, cur.data(), p.data()); ++n_lf; }  // :164-176
+        double prop_U = -logp(c, cur.data(), nullptr);  // :178
+        if (!std::isfinite(prop_U)) prop_U = std::numeric_limits<double>::infinity();  // :180-182
+        const double prop_K = kinetic(c, p.data());     // :184
+        const double comp = std::min(0.01, -(prop_U + prop_K) + (prev_U + prev_K));  // :188 (Q6)
+        const double u = rng.uniform(t, 0);             // :189
+        const bool acc = u < std::exp(comp);            // :191
+        if (acc) { prev = cur; prev_U = prop_U; }
+        if (t >= cfg->n_burnin) {
+            const long row = t - cfg->n_burnin;
+            for (int j = 0; j < d; ++j) draws[row * d + j] = prev[j];
+            if (logp_out) logp_out[row] = -prev_U;
+            if (acc) ++n_accept;                        // :198 (Q7)
+        }
+    }
+    res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = n_lf;
+    return 0;
+}
+
+// ------------------------------------------------------------------ MALA (src/mala.cpp:30-208, mala.ipp:30-70, dmvnorm.hpp:28-54)
+static void mala_mean(const Ctx& c, double eps, const double* v, double* out)
+{
+    // v + (((eps*eps)*M)*grad)/2   (src/mala.cpp:123)
+    const int d = c.d;
+    vec g(d), t(d);
+    logp(c, v, g.data());
+    const double e2 = eps * eps;
+    if (c.identity) {
+        for (int i = 0; i < d; ++i) out[i] = v[i] + (e2 * g[i]) / 2.0;
+    } else {
+        gemv_scaled(c.M, d, e2, g.data(), t.data());
+        for (int i = 0; i < d; ++i) out[i] = v[i] + t[i] / 2.0;
+    }
+}
+
+static double dmvnorm_log(const double* X, const double* mu, const vec& Sigma, int d, int sum_mode)
+{
+    const double cons_term = -0.5 * double(size_t(d)) * double(1.83787706640934548356L);  // dmvnorm.hpp:36
+    vec xc(d), sol(d);
+    for (int i = 0; i < d; ++i) xc[i] = X[i] - mu[i];
+    qr_solve(Sigma, d, xc.data(), sol.data());
+    const double quad = otgt::dot(xc.data(), sol.data(), d, sum_mode);
+    return cons_term - 0.5 * (logdet_llt(Sigma, d) + quad);  // :41
+}
+
+static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
+{
+    Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
+    setup_precond(c, cfg->precond, cfg->chol_mode);
+    Rng rng; init_rng(rng, cfg);
+    const int d = c.d;
+    const long n_total = cfg->n_burnin + cfg->n_keep;
+    const double eps = cfg->step_size;
+    const double e2 = eps * eps;
+
+    // Sigma = eps^2 M (materialised like ScaledMat -> Mat_t) and, for the cancelled form, its inverse
+    vec Sigma(size_t(d) * d, 0.0), SigInv;
+    if (c.identity) for (int i = 0; i < d; ++i) Sigma[size_t(i) * d + i] = 1.0 * e2;
+    else for (size_t k = 0; k < Sigma.size(); ++k) Sigma[k] = c.M[k] * e2;
+    if (!cfg->mala_exact_dmvnorm && !c.identity) mat_inverse(Sigma, d, SigInv);
+
+    vec prev(x0, x0 + d), cur(d), z(d), mean_prev(d), mean_prop(d), t(d), r(d);
+    double prev_LP = logp(c, prev.data(), nullptr);   // src/mala.cpp:138
+    long n_accept = 0;
+
+    for (long it = 0; it < n_total; ++it) {
+        rng.normals(it, d, z.data());                 // :150
+        mala_mean(c, eps, prev.data(), mean_prev.data());
+        if (c.identity) for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + eps * z[i];   // :159
+        else { gemv_scaled(c.S, d, eps, z.data(), t.data()); for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + t[i]; }
+        double prop_LP = logp(c, cur.data(), nullptr);  // :162
+        if (!std::isfinite(prop_LP)) prop_LP = -std::numeric_limits<double>::infinity();  // :164-166
+        mala_mean(c, eps, cur.data(), mean_prop.data());   // mala.ipp:60 (mean at prev is recomputed identically, :61)
+        double adj;
+        if (cfg->mala_exact_dmvnorm) {
+            adj = dmvnorm_log(prev.data(), mean_prop.data(), Sigma, d, c.sum_mode)
+                - dmvnorm_log(cur.data(), mean_prev.data(), Sigma, d, c.sum_mode);   // mala.ipp:63-64
+        } else {
+            // constants and log-dets cancel: adj = -1/2 (q(prev - mean_prop) - q(cur - mean_prev)), q(r) = r' Sigma^-1 r
+            double q1, q2;
+            for (int i = 0; i < d; ++i) r[i] = prev[i] - mean_prop[i];
+            if (c.identity) q1 = otgt::dot(r.data(), r.data(), d, c.sum_mode) / e2;
+            else { gemv_plain(SigInv, d, r.data(), t.data()); q1 = otgt::dot(r.data(), t.data(), d, c.sum_mode); }
+            for (int i = 0; i < d; ++i) r[i] = cur[i] - mean_prev[i];
+            if (c.identity) q2 = otgt::dot(r.data(), r.data(), d, c.sum_mode) / e2;
+            else { gemv_plain(SigInv, d, r.data(), t.data()); q2 = otgt::dot(r.data(), t.data(), d, c.sum_mode); }
+            adj = -0.5 * (q1 - q2);
+        }
+        const double comp = std::min(0.01, prop_LP - prev_LP + adj);   // src/mala.cpp:170
+        const double u = rng.uniform(it, 0);                            // :171
+        const bool acc = u < std::exp(comp);                            // :173
+        if (acc) { prev = cur; prev_LP = prop_LP; }
+        if (it >= cfg->n_burnin) {
+            const long row = it - cfg->n_burnin;
+            for (int j = 0; j < d; ++j) draws[row * d + j] = prev[j];
+            if (logp_out) logp_out[row] = prev_LP;
+            if (acc) ++n_accept;
+        }
+    }
+    res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = 0;
+    return 0;
+}
+
+// ------------------------------------------------------------------ NUTS (src/nuts.cpp:30-332, nuts.ipp:30-241, Appendix C)
+struct NutsEnv {
+    const Ctx* c; Rng* rng; long draw; int* ucount; long* n_lf;
+    double log_u, prev_U, prev_K;
+};
+
+// literal restatement of nuts_build_tree (nuts.ipp:97-241): same slot aliasing (Q13)
+static void build_tree(NutsEnv& e, int dir, double eps, const vec& draw_vec, const vec& mntm_vec, long depth,
+                       vec& new_draw, vec& pos, vec& neg, vec& mpos, vec& mneg,
+                       long& n_val, long& s_val, double& alpha, long& n_alpha)
+{
+    const Ctx& c = *e.c;
+    const int d = c.d;
+    if (depth == 0) {
+        new_draw = draw_vec;                       // :127
+        vec new_mntm(mntm_vec);                    // :128
+        leapfrog(c, dir * eps, new_draw.data(), new_mntm.data()); ++*e.n_lf;   // :132
+        double prop_U = -logp(c, new_draw.data(), nullptr);                    // :134
+        if (!std::isfinite(prop_U)) prop_U = std::numeric_limits<double>::infinity();
+        const double prop_K = kinetic(c, new_mntm.data());                     // :140
+        n_val = (e.log_u <= -prop_U - prop_K);                                 // :146
+        s_val = (e.log_u < 1000.0 - prop_U - prop_K);                          // :147
+        pos = new_draw; neg = new_draw; mpos = new_mntm; mneg = new_mntm;      // :151-155
+        alpha = std::exp(std::min(0.0, -(prop_U + prop_K) + (e.prev_U + e.prev_K)));  // :157
+        n_alpha = 1;
+        return;
+    }
+    long n_p, s_p, n_alpha_p; double alpha_p; vec new_draw_p;
+    build_tree(e, dir, eps, draw_vec, mntm_vec, depth - 1, new_draw_p, pos, neg, mpos, mneg, n_p, s_p, alpha_p, n_alpha_p);  // :166-171
+    if (s_p == 1) {
+        long n_pp, s_pp, n_alpha_pp; double alpha_pp; vec new_draw_pp;
+        if (dir == -1) {
+            vec dummy_draw(pos), dummy_mntm(mpos), start_x(neg), start_p(mneg);   // :186-189
+            // callee's pos slots alias OUR neg slots (:195)
+            build_tree(e, dir, eps, start_x, start_p, depth - 1, new_draw_pp, neg, dummy_draw, mneg, dummy_mntm,
+                       n_pp, s_pp, alpha_pp, n_alpha_pp);
+        } else {
+            vec dummy_draw(neg), dummy_mntm(mneg), start_x(pos), start_p(mpos);   // :198-201
+            build_tree(e, dir, eps, start_x, start_p, depth - 1, new_draw_pp, dummy_draw, pos, dummy_mntm, mpos,
+                       n_pp, s_pp, alpha_pp, n_alpha_pp);                          // :203-208
+        }
+        const double prob = double(n_pp) / double(n_p + n_pp);   // :213
+        const double zz = e.rng->uniform(e.draw, (*e.ucount)++);  // :214
+        if (zz < prob) new_draw_p = new_draw_pp;                  // :216-218
+        n_p += n_pp; alpha_p += alpha_pp; n_alpha_p += n_alpha_pp;  // :220-222
+        vec diff(d);
+        for (int i = 0; i < d; ++i) diff[i] = pos[i] - neg[i];
+        const int chk1 = otgt::dot(diff.data(), mneg.data(), d, c.sum_mode) >= 0.0;   // :226
+        const int chk2 = otgt::dot(diff.data(), mpos.data(), d, c.sum_mode) >= 0.0;   // :227
+        s_p = s_pp * chk1 * chk2;                                                     // :229
+    }
+    n_val = n_p; s_val = s_p; alpha = alpha_p; n_alpha = n_alpha_p; new_draw = new_draw_p;   // :234-239
+}
+
+static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
+{
+    Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
+    setup_precond(c, cfg->precond, cfg->chol_mode);
+    Rng rng; init_rng(rng, cfg);
+    const int d = c.d;
+    const long n_total = cfg->n_burnin + cfg->n_keep;
+    const long n_adapt = (cfg->n_adapt_draws <= n_total) ? cfg->n_adapt_draws : n_total;   // src/nuts.cpp:54
+    const double delta = cfg->target_accept_rate;
+    const long max_depth = cfg->max_tree_depth;
+    double eps_bar = cfg->step_size;                                                        // :59
+    const double gamma = cfg->gamma_val, t0 = cfg->t0_val, kappa = cfg->kappa_val;
+    long n_lf = 0;
+    const double inf = std::numeric_limits<double>::infinity();
+
+    vec first(x0, x0 + d), z(d), mntm(d);
+    rng.normals(-1, d, z.data());                       // :166 (Q3)
+    momentum_from_normals(c, z.data(), mntm.data());    // :168
+
+    // nuts_find_initial_step_size (nuts.ipp:30-93, Q14)
+    double eps = 1.0;
+    {
+        double pU = -logp(c, first.data(), nullptr);
+        if (!std::isfinite(pU)) pU = inf;
+        const double pK = kinetic(c, mntm.data());
+        vec nx(first), np(mntm);
+        leapfrog(c, eps, nx.data(), np.data()); ++n_lf;
+        double qU = -logp(c, nx.data(), nullptr);
+        if (!std::isfinite(qU)) qU = inf;
+        double qK = kinetic(c, np.data());
+        int a_val = 2 * (-(qU + qK) + (pU + pK) > std::log(0.5)) - 1;
+        bool cond = (-(qU + qK) + (pU + pK)) > -std::log(2);
+        while (cond) {
+            eps *= std::pow(2, a_val);
+            leapfrog(c, eps, nx.data(), np.data()); ++n_lf;
+            qU = -logp(c, nx.data(), nullptr);
+            if (!std::isfinite(qU)) qU = inf;
+            qK = kinetic(c, np.data());
+            a_val = 2 * ((-(qU + qK) + (pU + pK)) > std::log(0.5)) - 1;
+            cond = (-(qU + qK) + (pU + pK)) > -std::log(2);
+        }
+    }
+    const double mu = std::log(10 * eps);   // src/nuts.cpp:174
+    double h = 0.0;
+
+    double prev_U = -logp(c, first.data(), nullptr);   // :181
+    vec prev(first), new_draw(first), dpos(first), dneg(first), mpos(mntm), mneg(mntm);
+    long n_accept = 0;
+
+    for (long t = 0; t < n_total; ++t) {
+        int ucount = 0;
+        rng.normals(t, d, z.data());                         // :200
+        momentum_from_normals(c, z.data(), mntm.data());     // :202
+        const double prev_K = kinetic(c, mntm.data());       // :204
+        const double log_u = std::log(rng.uniform(t, ucount++)) - prev_U - prev_K;   // :206
+        new_draw = prev; dpos = prev; dneg = prev; mpos = mntm; mneg = mntm;          // :210-215
+        long depth = 0, n_val = 1, s_val = 1;
+        double alpha = 0.0; long n_alpha = 0; int good_round = 0;
+
+        while (s_val == 1 && depth < max_depth) {            // :227
+            long n_p = 0, s_p = 0;
+            const double zz = rng.uniform(t, ucount++);      // :233
+            const int dir = (zz <= 0.5) ? -1 : 1;            // :235
+            NutsEnv e; e.c = &c; e.rng = &rng; e.draw = t; e.ucount = &ucount; e.n_lf = &n_lf;
+            e.log_u = log_u; e.prev_U = prev_U; e.prev_K = prev_K;
+            if (dir == -1) {
+                vec dummy_draw(dpos), dummy_mntm(mpos);
+                build_tree(e, dir, eps, prev, mntm, depth, new_draw, dummy_draw, dneg, dummy_mntm, mneg, n_p, s_p, alpha, n_alpha);  // :241-246 (Q12)
+            } else {
+                vec dummy_draw(dneg), dummy_mntm(mneg);
+                build_tree(e, dir, eps, prev, mntm, depth, new_draw, dpos, dummy_draw, mpos, dummy_mntm, n_p, s_p, alpha, n_alpha);  // :251-255
+            }
+            if (s_p == 1) {
+                const double z2 = rng.uniform(t, ucount++);   // :261
+                if (z2 < double(n_p) / double(n_val)) {       // :263
+                    double prop_U = -logp(c, new_draw.data(), nullptr);   // :264
+                    if (!std::isfinite(prop_U)) prop_U = inf;
+                    prev = new_draw; prev_U = prop_U; good_round = 1;     // :272-277
+                }
+            }
+            n_val += n_p; depth += 1;                                      // :283-284
+            vec diff(d);
+            for (int i = 0; i < d; ++i) diff[i] = dpos[i] - dneg[i];
+            const int chk1 = otgt::dot(diff.data(), mneg.data(), d, c.sum_mode) >= 0.0;   // :286
+            const int chk2 = otgt::dot(diff.data(), mpos.data(), d, c.sum_mode) >= 0.0;   // :287
+            s_val = s_p * chk1 * chk2;                                                    // :289
+        }
+
+        if (t < n_adapt) {   // :294-299 (Q15)
+            h += (1 / double(double(t + 1) + t0)) * (delta - (double(alpha) / double(n_alpha)) - h);
+            eps = std::exp(mu - h * std::sqrt(double(t + 1)) / gamma);
+            eps_bar *= std::exp(std::pow(double(t + 1), -kappa) * (std::log(eps) - std::log(eps_bar)));
+        } else {
+            eps = eps_bar;   // :301
+        }
+        if (t >= cfg->n_burnin) {
+            const long row = t - cfg->n_burnin;
+            for (int j = 0; j < d; ++j) draws[row * d + j] = prev[j];
+            if (logp_out) logp_out[row] = -prev_U;
+            n_accept += good_round;   // :308
+        }
+    }
+    res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = n_lf;
+    return 0;
+}
+
+// ------------------------------------------------------------------ RM-HMC (src/rmhmc.cpp:30-294, Appendix E)
+// only TGT_NORMAL_MODEL carries a metric in this oracle (examples/eigen/rmhmc_normal.cpp)
+static void metric(const Ctx& c, const double* x, vec& G, vec* dG)
+{
+    const int d = c.d;
+    G.assign(size_t(d) * d, 0.0);
+    if (dG) dG->assign(size_t(d) * d * d, 0.0);
+    otgt::metric_normal_model(c.tdata, x, G.data(), dG ? dG->data() : nullptr);
+}
+
+// returns (eps * F)/2 with F_i = -grad_i + 1/2 (tr(A D_i) - ((A D_i)' q).(A q))   (src/rmhmc.cpp:132-146; Q16 sign)
+static void rm_mntm_update(const Ctx& c, double eps, const double* y, const double* q, const vec& A, const vec& dG, double* out)
+{
+    const int d = c.d;
+    vec g(d), Aq(d), tq(d), T, Tt(size_t(d) * d);
+    logp(c, y, g.data());
+    for (int i = 0; i < d; ++i) {
+        vec Di(dG.begin() + size_t(i) * d * d, dG.begin() + size_t(i + 1) * d * d);
+        matmul(A, Di, d, T);                      // tmp_mat = inv_tensor * deriv.mat(i)
+        double tr = 0.0;
+        for (int k = 0; k < d; ++k) tr += T[size_t(k) * d + k];
+        for (int a = 0; a < d; ++a)
+            for (int b = 0; b < d; ++b) Tt[size_t(b) * d + a] = T[size_t(a) * d + b];   // transpose (materialised)
+        gemv_plain(Tt, d, q, tq.data());
+        gemv_plain(A, d, q, Aq.data());
+        const double dp = otgt::dot(tq.data(), Aq.data(), d, c.sum_mode);
+        g[i] = -g[i] + 0.5 * (tr - dp);
+    }
+    for (int i = 0; i < d; ++i) out[i] = (eps * g[i]) / 2.0;
+}
+
+static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
+{
+    Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
+    c.identity = true;   // precond_mat is never read (Q18)
+    Rng rng; init_rng(rng, cfg);
+    const int d = c.d;
+    const long n_total = cfg->n_burnin + cfg->n_keep;
+    const double eps = cfg->step_size;
+    const unsigned n_leap = unsigned(cfg->n_leap_steps), n_fp = unsigned(cfg->n_fp_steps);
+    const double inf = std::numeric_limits<double>::infinity();
+
+    vec prev(x0, x0 + d), cur(d), z(d), p(d), q(d), upd(d), w(d), t(d);
+    rng.normals(-1, d, z.data());   // :176 (Q3: value unused)
+
+    vec newG, newdG, prevG, invNew, invPrev, prevdG, L, Gw, invW, sumM(size_t(d) * d);
+    cur = prev;
+    metric(c, cur.data(), newG, &newdG);   // :179
+    prevG = newG; mat_inverse(newG, d, invNew); invPrev = invNew; prevdG = newdG;   // :181-186
+    const double cons_term = double(0.5 * double(size_t(d)) * 1.83787706640934548356L);   // :188 (Q19)
+    double prev_U = cons_term - logp(c, prev.data(), nullptr) + 0.5 * logdet_llt(newG, d);  // :190
+    long n_accept = 0, n_lf = 0;
+
+    for (long it = 0; it < n_total; ++it) {
+        rng.normals(it, d, z.data());               // :200
+        mat_chol(prevG, d, cfg->chol_mode, L);      // :202 (Q8)
+        gemv_plain(L, d, z.data(), p.data());
+        gemv_plain(invPrev, d, p.data(), t.data());
+        const double prev_K = otgt::dot(p.data(), t.data(), d, c.sum_mode) / 2.0;   // :204
+        cur = prev;                                 // :206
+        for (unsigned k = 0; k < n_leap; ++k) {
+            q = p;                                  // :211
+            for (unsigned kk = 0; kk < n_fp; ++kk) {   // :213-215 (Q17: start-of-trajectory metric)
+                rm_mntm_update(c, eps, cur.data(), q.data(), invPrev, prevdG, upd.data());
+                for (int i = 0; i < d; ++i) q[i] = p[i] + upd[i];
+            }
+            p = q;                                  // :217
+            w = cur;                                // :221
+            for (unsigned kk = 0; kk < n_fp; ++kk) {   // :224-228
+                metric(c, w.data(), Gw, nullptr);
+                mat_inverse(Gw, d, invW);
+                invNew = invW;
+                for (size_t m = 0; m < sumM.size(); ++m) sumM[m] = invPrev[m] + invW[m];
+                gemv_scaled(sumM, d, 0.5 * eps, p.data(), t.data());
+                for (int i = 0; i < d; ++i) w[i] = cur[i] + t[i];
+            }
+            cur = w;                                // :230
+            metric(c, cur.data(), newG, &newdG);    // :232
+            mat_inverse(newG, d, invNew);           // :233
+            rm_mntm_update(c, eps, cur.data(), p.data(), invNew, newdG, upd.data());   // :237
+            for (int i = 0; i < d; ++i) p[i] += upd[i];
+            ++n_lf;
+        }
+        double prop_U = cons_term - logp(c, cur.data(), nullptr) + 0.5 * logdet_llt(newG, d);   // :240
+        if (!std::isfinite(prop_U)) prop_U = inf;
+        gemv_plain(invNew, d, p.data(), t.data());
+        const double prop_K = otgt::dot(p.data(), t.data(), d, c.sum_mode) / 2.0;               // :246
+        const double comp = std::min(0.01, -(prop_U + prop_K) + (prev_U + prev_K));             // :250
+        const double u = rng.uniform(it, 0);
+        const bool acc = u < std::exp(comp);
+        if (acc) { prev = cur; prev_U = prop_U; prevG = newG; invPrev = invNew; prevdG = newdG; }   // :254-261
+        if (it >= cfg->n_burnin) {
+            const long row = it - cfg->n_burnin;
+            for (int j = 0; j < d; ++j) draws[row * d + j] = prev[j];
+            if (logp_out) logp_out[row] = -(prev_U - cons_term);   // includes the +1/2 logdet G term
+            if (acc) ++n_accept;
+        }
+    }
+    res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = n_lf;
+    return 0;
+}
+
+int oracle_run_chain(const oracle_cfg_t* cfg, const double* x0, double* draws_out, double* logp_out, oracle_res_t* res)
+{
+    switch (cfg->sampler) {
+    case S_HMC: return run_hmc(cfg, x0, draws_out, logp_out, res);
+    case S_MALA: return run_mala(cfg, x0, draws_out, logp_out, res);
+    case S_NUTS: return run_nuts(cfg, x0, draws_out, logp_out, res);
+    case S_RMHMC: return run_rmhmc(cfg, x0, draws_out, logp_out, res);
+    default: return -1;
+    }
+}
+
+// target value / gradient as the samplers see it (used by tests to check the CUDA functors)
+double oracle_target(int target_id, const double* tdata, int d, const double* x, double* grad, int sum_mode)
+{
+    return otgt::value_and_grad(target_id, tdata, x, grad, d, sum_mode);
+}
+
+// raw RNG streams, for checking the engine's host-side tape generator and device Philox
+void oracle_rng_stream(int rng_mode, unsigned long seed, long chain_id, long draw, int d, int n_unif, double* out)
+{
+    oracle_cfg_t cfg; std::memset(&cfg, 0, sizeof(cfg));
+    cfg.rng_mode = rng_mode; cfg.seed = seed; cfg.chain_id = chain_id;
+    Rng r; init_rng(r, &cfg);
+    r.normals(draw, d, out);
+    for (int k = 0; k < n_unif; ++k) out[d + k] = r.uniform(draw, k);
+}
+
+}  // extern "C"
