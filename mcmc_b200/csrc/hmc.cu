@@ -1,0 +1,188 @@
+// Many-chain HMC: one persistent kernel, one warp per chain, all draws of a chain in one launch.
+//
+// Replaces internal::hmc_impl (/root/reference/src/hmc.cpp:30-227) run once per chain.  Per draw
+// (SURVEY Appendix E):
+//   z ~ N(0,I)                       src/hmc.cpp:156   (Philox in-kernel, or the reference's tape)
+//   p = sqrtM z ; K0 = p.(M^-1 p)/2  :158-160
+//   L leapfrog steps                 :164-176  p += (eps grad)/2 ; x += (eps M^-1) p ; p += (eps grad)/2
+//   U1 = -log pi(x) (non-finite -> +inf), K1                         :178-184
+//   accept iff u < exp(min(0.01, -(U1+K1) + (U0+K0)))                :188-191
+//   kept draws written to draws_out, post-burn-in accepts counted    :196-203
+// State (x, p, grad) never leaves registers during a trajectory; HBM traffic is the initial x
+// (d*8 B per chain, once) and the draws_out row (d*8 B per kept draw): <= 2*d*8 B per transition,
+// the contract figure of SURVEY §8(d).  The gradient at the end of leapfrog step k is the gradient
+// at the start of step k+1, so it is evaluated L+1 times per draw instead of the reference's 2L
+// calls + 1 value call; in STRICT mode the two half-kicks are still applied as two
+// separately rounded updates, so element-wise results are bit-identical to the reference order.
+#include "engine.h"
+#include "rng.cuh"
+#include "targets.cuh"
+#include <math_constants.h>
+
+namespace mcmcb200
+{
+
+template <class T, int EPL, bool DENSE_M, bool STRICT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaunch a)
+{
+    extern __shared__ double smem[];
+    typedef Ar<STRICT> A;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long chain = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (chain >= a.n_chains) return;  // whole warp exits together; no block-level barriers below
+    const int d = a.d;
+    const int dpad = (d + 1) & ~1;
+    double* tscr = smem + (size_t)warp * 2 * dpad;  // target functor scratch
+    double* mscr = tscr + dpad;                      // mass-matrix scratch
+    const WarpCtx w{lane, d, tscr};
+
+    double x[EPL], p[EPL], g[EPL], xs[EPL];
+    load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
+
+    ChainRng rng;
+    rng.init(a.rng, chain, a.chain_offset + chain);
+
+    double U = -T::template eval<EPL, STRICT, true, false>(a.tdata, w, x, g);  // src/hmc.cpp:140
+    long long n_acc = 0;
+    const long long n_total = a.n_burnin + a.n_keep;
+    const double eps = a.eps;
+    const double heps = 0.5 * eps;
+    const int L = a.n_leap;
+    double* out_row = a.draws + chain * a.n_keep * d;
+    double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
+
+    for (long long t = 0; t < n_total; ++t) {
+        // ---- momentum refresh ----
+        rng.normals<EPL>(a.rng, t, d, lane, p);
+        double K0;
+        if (DENSE_M) {
+            double tmp[EPL];
+            stage_vec<EPL>(mscr, d, lane, p);
+            gemv_cm<EPL, STRICT>(a.S_cm, d, lane, mscr, 1.0, tmp);  // p = sqrtM z
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) p[k] = tmp[k];
+            stage_vec<EPL>(mscr, d, lane, p);
+            gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, 1.0, tmp);
+            K0 = A::mul(0.5, warp_dot<EPL, STRICT>(p, tmp));
+        } else {
+            K0 = A::mul(0.5, warp_dot<EPL, STRICT>(p, p));
+        }
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) xs[k] = x[k];
+
+        // ---- trajectory ----
+        double U1 = U;
+        if (L > 0) {
+            T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) p[k] = STRICT ? A::add(p[k], A::mul(A::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
+            for (int s = 0; s < L; ++s) {
+                if (DENSE_M) {
+                    double tmp[EPL];
+                    stage_vec<EPL>(mscr, d, lane, p);
+                    gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);  // (eps M^-1) p
+#pragma unroll
+                    for (int k = 0; k < EPL; ++k) x[k] = A::add(x[k], tmp[k]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < EPL; ++k) x[k] = A::mad(eps, p[k], x[k]);
+                }
+                if (s + 1 < L) {
+                    T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
+#pragma unroll
+                    for (int k = 0; k < EPL; ++k) {
+                        if (STRICT) {
+                            const double hk = A::mul(A::mul(eps, g[k]), 0.5);
+                            p[k] = A::add(A::add(p[k], hk), hk);  // end of step s, start of step s+1
+                        } else {
+                            p[k] = fma(eps, g[k], p[k]);
+                        }
+                    }
+                } else {
+                    U1 = -T::template eval<EPL, STRICT, true, true>(a.tdata, w, x, g);
+#pragma unroll
+                    for (int k = 0; k < EPL; ++k)
+                        p[k] = STRICT ? A::add(p[k], A::mul(A::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
+                }
+            }
+        } else {
+            U1 = -T::template eval<EPL, STRICT, true, false>(a.tdata, w, x, g);
+        }
+        if (!isfinite(U1)) U1 = CUDART_INF;
+
+        double K1;
+        if (DENSE_M) {
+            double tmp[EPL];
+            stage_vec<EPL>(mscr, d, lane, p);
+            gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, 1.0, tmp);
+            K1 = A::mul(0.5, warp_dot<EPL, STRICT>(p, tmp));
+        } else {
+            K1 = A::mul(0.5, warp_dot<EPL, STRICT>(p, p));
+        }
+
+        // ---- Metropolis test (Q6) ----
+        const double comp = fmin(0.01, A::add(-A::add(U1, K1), A::add(U, K0)));
+        const double u = rng.uniform(a.rng, t, 0);
+        const bool acc = u < exp(comp);
+        if (acc) {
+            U = U1;
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) x[k] = xs[k];
+        }
+        if (t >= a.n_burnin) {
+            const long long row = t - a.n_burnin;
+            store_vec<EPL>(out_row + row * d, d, lane, x);
+            if (out_lp && lane == 0) out_lp[row] = -U;
+            n_acc += acc ? 1 : 0;
+        }
+    }
+    if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
+}
+
+template <class T, int EPL, bool DENSE_M, bool STRICT> static int launch_one(const HmcLaunch& a)
+{
+    const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int dpad = (a.d + 1) & ~1;
+    const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dpad * sizeof(double) : 0;
+    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT>;
+    if (smem > 48 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
+    MCMCB200_CUDA_TRY(cudaGetLastError());
+    return MCMCB200_OK;
+}
+
+template <class T, int EPL> static int launch_epl(const HmcLaunch& a)
+{
+    const bool dense = a.S_cm != nullptr;
+    if (dense) return a.strict ? launch_one<T, EPL, true, true>(a) : launch_one<T, EPL, true, false>(a);
+    return a.strict ? launch_one<T, EPL, false, true>(a) : launch_one<T, EPL, false, false>(a);
+}
+
+template <class T> static int launch_target(const HmcLaunch& a)
+{
+    switch (epl_for_dim(a.d)) {
+    case 2: return launch_epl<T, 2>(a);
+    case 4: return launch_epl<T, 4>(a);
+    case 8: return launch_epl<T, 8>(a);
+    case 16: return launch_epl<T, 16>(a);
+    default:
+        set_error("hmc: n_dim=%d exceeds the register-resident kernels (max %d)", a.d, 32 * MAX_EPL);
+        return MCMCB200_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_hmc(const HmcLaunch& a)
+{
+    switch (a.target_id) {
+#define X(ID, TYPE) \
+    case ID: return launch_target<TYPE>(a);
+        MCMCB200_FOREACH_TARGET(X)
+#undef X
+    default:
+        set_error("hmc: unknown target id %d", a.target_id);
+        return MCMCB200_ERR_UNKNOWN_TARGET;
+    }
+}
+
+}  // namespace mcmcb200

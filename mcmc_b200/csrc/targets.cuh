@@ -1,0 +1,154 @@
+// Registered __device__ log-density functors.
+//
+// These replace the reference's host callback
+//   std::function<fp_t(const ColVec_t& vals_inp, ColVec_t* grad_out, void* target_data)>
+// (include/mcmc/hmc.hpp:46, contract shown by examples/eigen/hmc_normal.cpp:44-76: grad_out
+// may be null = "value only"; the return value is log pi).  A functor is warp-cooperative:
+// x and grad are lane-striped (warp.cuh), `data` is the target's blob in global memory, and
+//   eval<EPL, STRICT, WANT_VALUE, WANT_GRAD>(data, ctx, x, g)
+// returns log pi(x) (warp-uniform) when WANT_VALUE, writes d log pi/dx into g when
+// WANT_GRAD.  One fused evaluation may serve several reference calls.
+// To add a target: write a struct with the same eval<> signature, give it an id in
+// include/mcmc_b200.h and add it to MCMCB200_FOREACH_TARGET below.
+#pragma once
+
+#include "warp.cuh"
+
+namespace mcmcb200
+{
+
+// log pi = -1/2 |x|^2                       (SURVEY §8d C1/C2 target)
+struct IsoGauss {
+    static constexpr bool needs_scratch = false;
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    static __device__ __forceinline__ double eval(const double*, const WarpCtx&, const double (&x)[EPL], double (&g)[EPL])
+    {
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) g[k] = -x[k];
+        }
+        if (WANT_VALUE) {
+            const double s = warp_dot<EPL, STRICT>(x, x);
+            return -Ar<STRICT>::mul(0.5, s);
+        }
+        return 0.0;
+    }
+};
+
+// log pi = -1/2 sum_i w_i x_i^2, data = w[d]
+struct DiagGauss {
+    static constexpr bool needs_scratch = false;
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+                                                  double (&g)[EPL])
+    {
+        double t[EPL];
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int j = elem_index(w.lane, k);
+            const double wj = (j < w.d) ? __ldg(data + j) : 0.0;
+            t[k] = Ar<STRICT>::mul(wj, x[k]);
+        }
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) g[k] = -t[k];
+        }
+        if (WANT_VALUE) {
+            const double s = warp_dot<EPL, STRICT>(t, x);
+            return -Ar<STRICT>::mul(0.5, s);
+        }
+        return 0.0;
+    }
+};
+
+// log pi = -1/2 x' P x, data = P[d*d] symmetric          (SURVEY §8d C4 target; functor data = Sigma^-1)
+struct DenseGauss {
+    static constexpr bool needs_scratch = true;
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+                                                  double (&g)[EPL])
+    {
+        double y[EPL];
+        stage_vec<EPL>(w.scr, w.d, w.lane, x);
+        gemv_cm<EPL, STRICT>(data, w.d, w.lane, w.scr, 1.0, y);
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) g[k] = -y[k];
+        }
+        if (WANT_VALUE) {
+            const double s = warp_dot<EPL, STRICT>(x, y);
+            return -Ar<STRICT>::mul(0.5, s);
+        }
+        return 0.0;
+    }
+};
+
+// Bayesian linear regression on sufficient statistics: log pi = -1/2 t'At + b't, data = A[d*d] (sym), b[d]
+// (SURVEY §8d C3 target; grad = b - A t)
+struct LinReg {
+    static constexpr bool needs_scratch = true;
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+                                                  double (&g)[EPL])
+    {
+        double y[EPL], b[EPL];
+        stage_vec<EPL>(w.scr, w.d, w.lane, x);
+        gemv_cm<EPL, STRICT>(data, w.d, w.lane, w.scr, 1.0, y);
+        const double* __restrict__ bp = data + (size_t)w.d * (size_t)w.d;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int j = elem_index(w.lane, k);
+            b[k] = (j < w.d) ? __ldg(bp + j) : 0.0;
+        }
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) g[k] = Ar<STRICT>::sub(b[k], y[k]);
+        }
+        if (WANT_VALUE) {
+            double t[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) t[k] = Ar<STRICT>::sub(b[k], Ar<STRICT>::mul(0.5, y[k]));
+            return warp_dot<EPL, STRICT>(x, t);
+        }
+        return 0.0;
+    }
+};
+
+// 2-parameter Normal(mu, sigma) likelihood (examples/eigen/hmc_normal.cpp:44-76) on the sufficient
+// statistics data = {n, xbar, M2 = sum (x_k - xbar)^2}:  sum (x_k - mu)^2 = M2 + n (xbar - mu)^2.
+struct NormalModel {
+    static constexpr bool needs_scratch = false;
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+                                                  double (&g)[EPL])
+    {
+        const double n = __ldg(data), xbar = __ldg(data + 1), M2 = __ldg(data + 2);
+        const double mu = __shfl_sync(FULL, x[0], 0), sigma = __shfl_sync(FULL, x[1], 0);
+        const double dm = Ar<STRICT>::sub(xbar, mu);
+        const double ss = Ar<STRICT>::mad(n, Ar<STRICT>::mul(dm, dm), M2);
+        const double s2 = Ar<STRICT>::mul(sigma, sigma);
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) g[k] = 0.0;
+            if (w.lane == 0) {
+                g[0] = Ar<STRICT>::mul(n, dm) / s2;
+                g[1] = Ar<STRICT>::sub(ss / Ar<STRICT>::mul(s2, sigma), n / sigma);
+            }
+        }
+        if (WANT_VALUE) {
+            const double a = Ar<STRICT>::mul(-n, Ar<STRICT>::add(0.91893853320467274178, log(sigma)));
+            return Ar<STRICT>::sub(a, ss / Ar<STRICT>::mul(2.0, s2));
+        }
+        return 0.0;
+    }
+};
+
+}  // namespace mcmcb200
+
+// X-macro: (enum id, functor type)
+#define MCMCB200_FOREACH_TARGET(X)          \
+    X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)   \
+    X(MCMCB200_TARGET_DIAG_GAUSS, DiagGauss) \
+    X(MCMCB200_TARGET_DENSE_GAUSS, DenseGauss) \
+    X(MCMCB200_TARGET_LINREG, LinReg)        \
+    X(MCMCB200_TARGET_NORMAL_MODEL, NormalModel)
