@@ -133,7 +133,7 @@ static int stage_common(Staged& s, const mcmcb200_problem_t* pr, const mcmcb200_
 {
     if (!pr || !rng || !out) { set_error("null argument"); return MCMCB200_ERR_INVALID_ARG; }
     if (pr->n_chains <= 0 || pr->n_dim <= 0) { set_error("n_chains and n_dim must be positive"); return MCMCB200_ERR_INVALID_ARG; }
-    if (n_burnin < 0 || n_keep < 0) { set_error("negative draw counts"); return MCMCB200_ERR_INVALID_ARG; }
+    if (n_burnin < 0 || n_keep < 0 || n_burnin + n_keep > 0x7ffffff0ll) { set_error("draw counts out of range"); return MCMCB200_ERR_INVALID_ARG; }
     if (!pr->initial_vals) { set_error("initial_vals is null"); return MCMCB200_ERR_INVALID_ARG; }
     if (n_keep > 0 && !out->draws_out) { set_error("draws_out is null"); return MCMCB200_ERR_INVALID_ARG; }
     const int d = pr->n_dim;

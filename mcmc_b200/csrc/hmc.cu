@@ -22,11 +22,37 @@
 namespace mcmcb200
 {
 
-template <class T, int EPL, bool DENSE_M, bool STRICT>
+// Half / full momentum kicks.  STRICT keeps the reference's rounding sequence p + (eps*g)/2 (a full kick is two
+// separately rounded half kicks, src/hmc.cpp:167,175); FAST fuses them.
+template <int EPL, bool STRICT> __device__ __forceinline__ void kick_half(double (&p)[EPL], const double (&g)[EPL], double eps, double heps)
+{
+#pragma unroll
+    for (int k = 0; k < EPL; ++k)
+        p[k] = STRICT ? Ar<STRICT>::add(p[k], Ar<STRICT>::mul(Ar<STRICT>::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
+}
+template <int EPL, bool STRICT> __device__ __forceinline__ void kick_full(double (&p)[EPL], const double (&g)[EPL], double eps)
+{
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        if (STRICT) {
+            const double hk = Ar<STRICT>::mul(Ar<STRICT>::mul(eps, g[k]), 0.5);
+            p[k] = Ar<STRICT>::add(Ar<STRICT>::add(p[k], hk), hk);
+        } else {
+            p[k] = fma(eps, g[k], p[k]);
+        }
+    }
+}
+
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaunch a)
 {
     extern __shared__ double smem[];
+    __shared__ double2 log_tab[RNGM == RNG_PHILOX ? LOG_TAB_SIZE : 1];
     typedef Ar<STRICT> A;
+    if (RNGM == RNG_PHILOX) {
+        build_log_table(log_tab);
+        __syncthreads();
+    }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long chain = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
     if (chain >= a.n_chains) return;  // whole warp exits together; no block-level barriers below
@@ -36,127 +62,144 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaun
     double* mscr = tscr + dpad;                      // mass-matrix scratch
     const WarpCtx w{lane, d, tscr};
 
-    double x[EPL], p[EPL], g[EPL], xs[EPL];
+    double x[EPL], y[EPL], p[EPL], g[EPL];
     load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
 
-    ChainRng rng;
+    ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
 
-    double U = -T::template eval<EPL, STRICT, true, false>(a.tdata, w, x, g);  // src/hmc.cpp:140
-    long long n_acc = 0;
-    const long long n_total = a.n_burnin + a.n_keep;
+    // U = -log pi(x): STRICT carries the reduced scalar (src/hmc.cpp:140); FAST carries this lane's partial sum,
+    // so that one butterfly per draw reduces (U0 + K0) - (U1 + K1) directly.
+    double U = -T::template eval<EPL, STRICT, true, false, STRICT>(a.tdata, w, x, g);
+    int n_acc = 0;
+    const int n_total = (int)(a.n_burnin + a.n_keep);
+    const int n_burnin = (int)a.n_burnin;
     const double eps = a.eps;
     const double heps = 0.5 * eps;
     const int L = a.n_leap;
     double* out_row = a.draws + chain * a.n_keep * d;
     double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
 
-    for (long long t = 0; t < n_total; ++t) {
-        // ---- momentum refresh ----
-        rng.normals<EPL>(a.rng, t, d, lane, p);
+    for (int t = 0; t < n_total; ++t) {
+        // ---- momentum refresh: p = sqrtM z, K0 = p.(M^-1 p)/2 (lane partial in FAST) ----
+        rng.template normals<EPL>(a.rng, t, d, lane, log_tab, p);
         double K0;
         if (DENSE_M) {
             double tmp[EPL];
             stage_vec<EPL>(mscr, d, lane, p);
-            gemv_cm<EPL, STRICT>(a.S_cm, d, lane, mscr, 1.0, tmp);  // p = sqrtM z
+            gemv_cm<EPL, STRICT>(a.S_cm, d, lane, mscr, 1.0, tmp);
 #pragma unroll
             for (int k = 0; k < EPL; ++k) p[k] = tmp[k];
             stage_vec<EPL>(mscr, d, lane, p);
             gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, 1.0, tmp);
-            K0 = A::mul(0.5, warp_dot<EPL, STRICT>(p, tmp));
+            K0 = A::mul(0.5, STRICT ? warp_dot<EPL, STRICT>(p, tmp) : lane_dot<EPL, STRICT>(p, tmp));
         } else {
-            K0 = A::mul(0.5, warp_dot<EPL, STRICT>(p, p));
+            K0 = A::mul(0.5, STRICT ? warp_dot<EPL, STRICT>(p, p) : lane_dot<EPL, STRICT>(p, p));
         }
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) xs[k] = x[k];
 
-        // ---- trajectory ----
-        double U1 = U;
+        // ---- trajectory on y; x stays untouched until the proposal is accepted ----
+        double U1;
         if (L > 0) {
             T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
+            kick_half<EPL, STRICT>(p, g, eps, heps);
+            if (DENSE_M) {
+                double tmp[EPL];
+                stage_vec<EPL>(mscr, d, lane, p);
+                gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);  // (eps M^-1) p
 #pragma unroll
-            for (int k = 0; k < EPL; ++k) p[k] = STRICT ? A::add(p[k], A::mul(A::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
-            for (int s = 0; s < L; ++s) {
+                for (int k = 0; k < EPL; ++k) y[k] = A::add(x[k], tmp[k]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) y[k] = A::mad(eps, p[k], x[k]);
+            }
+            for (int s = 1; s < L; ++s) {
+                T::template eval<EPL, STRICT, false, true>(a.tdata, w, y, g);
+                kick_full<EPL, STRICT>(p, g, eps);  // end of step s-1 and start of step s share this gradient
                 if (DENSE_M) {
                     double tmp[EPL];
                     stage_vec<EPL>(mscr, d, lane, p);
-                    gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);  // (eps M^-1) p
+                    gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);
 #pragma unroll
-                    for (int k = 0; k < EPL; ++k) x[k] = A::add(x[k], tmp[k]);
+                    for (int k = 0; k < EPL; ++k) y[k] = A::add(y[k], tmp[k]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < EPL; ++k) x[k] = A::mad(eps, p[k], x[k]);
-                }
-                if (s + 1 < L) {
-                    T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
-#pragma unroll
-                    for (int k = 0; k < EPL; ++k) {
-                        if (STRICT) {
-                            const double hk = A::mul(A::mul(eps, g[k]), 0.5);
-                            p[k] = A::add(A::add(p[k], hk), hk);  // end of step s, start of step s+1
-                        } else {
-                            p[k] = fma(eps, g[k], p[k]);
-                        }
-                    }
-                } else {
-                    U1 = -T::template eval<EPL, STRICT, true, true>(a.tdata, w, x, g);
-#pragma unroll
-                    for (int k = 0; k < EPL; ++k)
-                        p[k] = STRICT ? A::add(p[k], A::mul(A::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
+                    for (int k = 0; k < EPL; ++k) y[k] = A::mad(eps, p[k], y[k]);
                 }
             }
+            U1 = -T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, y, g);  // value-only call of :178 fused in
+            kick_half<EPL, STRICT>(p, g, eps, heps);
         } else {
-            U1 = -T::template eval<EPL, STRICT, true, false>(a.tdata, w, x, g);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) y[k] = x[k];
+            U1 = U;
         }
-        if (!isfinite(U1)) U1 = CUDART_INF;
 
         double K1;
         if (DENSE_M) {
             double tmp[EPL];
             stage_vec<EPL>(mscr, d, lane, p);
             gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, 1.0, tmp);
-            K1 = A::mul(0.5, warp_dot<EPL, STRICT>(p, tmp));
+            K1 = A::mul(0.5, STRICT ? warp_dot<EPL, STRICT>(p, tmp) : lane_dot<EPL, STRICT>(p, tmp));
         } else {
-            K1 = A::mul(0.5, warp_dot<EPL, STRICT>(p, p));
+            K1 = A::mul(0.5, STRICT ? warp_dot<EPL, STRICT>(p, p) : lane_dot<EPL, STRICT>(p, p));
         }
 
-        // ---- Metropolis test (Q6) ----
-        const double comp = fmin(0.01, A::add(-A::add(U1, K1), A::add(U, K0)));
+        // ---- Metropolis test ----
         const double u = rng.uniform(a.rng, t, 0);
-        const bool acc = u < exp(comp);
+        bool acc;
+        if (STRICT) {
+            // the reference's expression, evaluated literally (src/hmc.cpp:180-191)
+            if (!isfinite(U1)) U1 = CUDART_INF;
+            const double comp = fmin(0.01, A::add(-A::add(U1, K1), A::add(U, K0)));
+            acc = u < exp(comp);
+        } else {
+            // dH = (U0 + K0) - (U1 + K1) in one butterfly; u < exp(min(0.01, dH)) holds trivially for dH >= 0 (u < 1),
+            // so exp() is only evaluated for dH < 0.  A non-finite energy rejects (src/hmc.cpp:180-182).
+            const double dH = warp_sum<false>((U + K0) - (U1 + K1));
+            acc = false;
+            if (fabs(dH) <= 1.7976931348623157e308) acc = (dH >= 0.0) ? true : (u < exp(dH));
+        }
         if (acc) {
             U = U1;
-        } else {
 #pragma unroll
-            for (int k = 0; k < EPL; ++k) x[k] = xs[k];
+            for (int k = 0; k < EPL; ++k) x[k] = y[k];
         }
-        if (t >= a.n_burnin) {
-            const long long row = t - a.n_burnin;
-            store_vec<EPL>(out_row + row * d, d, lane, x);
-            if (out_lp && lane == 0) out_lp[row] = -U;
+        if (t >= n_burnin) {
+            store_vec<EPL>(out_row, d, lane, x);
+            out_row += d;
+            if (out_lp) {
+                const double Ur = STRICT ? U : warp_sum<false>(U);
+                if (lane == 0) *out_lp = -Ur;
+                ++out_lp;
+            }
             n_acc += acc ? 1 : 0;
         }
     }
     if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT> static int launch_one(const HmcLaunch& a)
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int launch_one(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dpad * sizeof(double) : 0;
-    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT>;
-    if (smem > 48 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM>;
+    if (smem > 40 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
     return MCMCB200_OK;
 }
 
+template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch& a)
+{
+    if (a.rng.mode == RNG_PHILOX)
+        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
+    return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE>(a);
+}
+
 template <class T, int EPL> static int launch_epl(const HmcLaunch& a)
 {
-    const bool dense = a.S_cm != nullptr;
-    if (dense) return a.strict ? launch_one<T, EPL, true, true>(a) : launch_one<T, EPL, true, false>(a);
-    return a.strict ? launch_one<T, EPL, false, true>(a) : launch_one<T, EPL, false, false>(a);
+    return (a.S_cm != nullptr) ? launch_mass<T, EPL, true>(a) : launch_mass<T, EPL, false>(a);
 }
 
 template <class T> static int launch_target(const HmcLaunch& a)

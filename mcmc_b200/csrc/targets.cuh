@@ -5,9 +5,11 @@
 // (include/mcmc/hmc.hpp:46, contract shown by examples/eigen/hmc_normal.cpp:44-76: grad_out
 // may be null = "value only"; the return value is log pi).  A functor is warp-cooperative:
 // x and grad are lane-striped (warp.cuh), `data` is the target's blob in global memory, and
-//   eval<EPL, STRICT, WANT_VALUE, WANT_GRAD>(data, ctx, x, g)
+//   eval<EPL, STRICT, WANT_VALUE, WANT_GRAD, REDUCE>(data, ctx, x, g)
 // returns log pi(x) (warp-uniform) when WANT_VALUE, writes d log pi/dx into g when
-// WANT_GRAD.  One fused evaluation may serve several reference calls.
+// WANT_GRAD.  With REDUCE = false the return value is this lane's partial sum (the warp
+// total is log pi), so a caller can fold it into one butterfly with its other terms.
+// One fused evaluation may serve several reference calls.
 // To add a target: write a struct with the same eval<> signature, give it an id in
 // include/mcmc_b200.h and add it to MCMCB200_FOREACH_TARGET below.
 #pragma once
@@ -20,7 +22,7 @@ namespace mcmcb200
 // log pi = -1/2 |x|^2                       (SURVEY §8d C1/C2 target)
 struct IsoGauss {
     static constexpr bool needs_scratch = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double*, const WarpCtx&, const double (&x)[EPL], double (&g)[EPL])
     {
         if (WANT_GRAD) {
@@ -28,7 +30,7 @@ struct IsoGauss {
             for (int k = 0; k < EPL; ++k) g[k] = -x[k];
         }
         if (WANT_VALUE) {
-            const double s = warp_dot<EPL, STRICT>(x, x);
+            const double s = REDUCE ? warp_dot<EPL, STRICT>(x, x) : lane_dot<EPL, STRICT>(x, x);
             return -Ar<STRICT>::mul(0.5, s);
         }
         return 0.0;
@@ -38,7 +40,7 @@ struct IsoGauss {
 // log pi = -1/2 sum_i w_i x_i^2, data = w[d]
 struct DiagGauss {
     static constexpr bool needs_scratch = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
@@ -54,7 +56,7 @@ struct DiagGauss {
             for (int k = 0; k < EPL; ++k) g[k] = -t[k];
         }
         if (WANT_VALUE) {
-            const double s = warp_dot<EPL, STRICT>(t, x);
+            const double s = REDUCE ? warp_dot<EPL, STRICT>(t, x) : lane_dot<EPL, STRICT>(t, x);
             return -Ar<STRICT>::mul(0.5, s);
         }
         return 0.0;
@@ -64,7 +66,7 @@ struct DiagGauss {
 // log pi = -1/2 x' P x, data = P[d*d] symmetric          (SURVEY §8d C4 target; functor data = Sigma^-1)
 struct DenseGauss {
     static constexpr bool needs_scratch = true;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
@@ -76,7 +78,7 @@ struct DenseGauss {
             for (int k = 0; k < EPL; ++k) g[k] = -y[k];
         }
         if (WANT_VALUE) {
-            const double s = warp_dot<EPL, STRICT>(x, y);
+            const double s = REDUCE ? warp_dot<EPL, STRICT>(x, y) : lane_dot<EPL, STRICT>(x, y);
             return -Ar<STRICT>::mul(0.5, s);
         }
         return 0.0;
@@ -87,7 +89,7 @@ struct DenseGauss {
 // (SURVEY §8d C3 target; grad = b - A t)
 struct LinReg {
     static constexpr bool needs_scratch = true;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
@@ -108,7 +110,7 @@ struct LinReg {
             double t[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) t[k] = Ar<STRICT>::sub(b[k], Ar<STRICT>::mul(0.5, y[k]));
-            return warp_dot<EPL, STRICT>(x, t);
+            return REDUCE ? warp_dot<EPL, STRICT>(x, t) : lane_dot<EPL, STRICT>(x, t);
         }
         return 0.0;
     }
@@ -118,7 +120,7 @@ struct LinReg {
 // statistics data = {n, xbar, M2 = sum (x_k - xbar)^2}:  sum (x_k - mu)^2 = M2 + n (xbar - mu)^2.
 struct NormalModel {
     static constexpr bool needs_scratch = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD>
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
@@ -137,7 +139,8 @@ struct NormalModel {
         }
         if (WANT_VALUE) {
             const double a = Ar<STRICT>::mul(-n, Ar<STRICT>::add(0.91893853320467274178, log(sigma)));
-            return Ar<STRICT>::sub(a, ss / Ar<STRICT>::mul(2.0, s2));
+            const double v = Ar<STRICT>::sub(a, ss / Ar<STRICT>::mul(2.0, s2));
+            return (REDUCE || w.lane == 0) ? v : 0.0;
         }
         return 0.0;
     }

@@ -63,11 +63,14 @@ int launch_target_eval(const EvalLaunch& a)
 
 template <int EPL> __global__ void philox_stream_kernel(RngArgs r, long long chain, long long draw, int d, int n_unif, double* out)
 {
+    __shared__ double2 log_tab[LOG_TAB_SIZE];
+    build_log_table(log_tab);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
-    ChainRng rng;
+    ChainRng<RNG_PHILOX> rng;
     rng.init(r, 0, chain);
     double z[EPL];
-    rng.normals<EPL>(r, draw, d, lane, z);
+    rng.template normals<EPL>(r, draw, d, lane, log_tab, z);
     store_vec<EPL>(out, d, lane, z);
     for (int k = 0; k < n_unif; ++k) {
         const double u = rng.uniform(r, draw, k);

@@ -22,9 +22,11 @@
 //              kernels read in tape mode).
 //   RNG_PHILOX Philox4x32-10, key = (seed_lo, seed_hi), counter =
 //              (index, draw+1, chain, stream); stream 0 = normals by Box-Muller
-//              pair q -> elements (2q, 2q+1), stream 1 = uniforms.  This is the
-//              engine's own production RNG (not in the reference); the oracle
-//              restates it independently from the spec in DESIGN.md.
+//              pair q -> elements (2q, 2q+1) (uniform #0 of a draw comes from the
+//              unused bits of blocks 0 and 1), stream 1 = uniforms #1.. .  This is
+//              the engine's own production RNG (not in the reference); the oracle
+//              restates its definition (mcmc_b200/csrc/rng.cuh header)
+//              independently with libm log / sin / cos.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -60,11 +62,9 @@ inline void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, ui
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-inline double u53_open(uint32_t hi, uint32_t lo)
-{
-    const uint64_t k = ((uint64_t(hi) << 32) | lo) >> 11;  // 53 bits
-    return (double(k) + 0.5) * 1.1102230246251565404e-16;  // 2^-53, result in (0,1)
-}
+// 52 random bits k -> (k + 1/2) 2^-52 in the open interval (0,1); exact in double
+inline uint64_t top52(uint32_t hi, uint32_t lo) { return ((uint64_t(hi) << 32) | lo) >> 12; }
+inline double u52_open(uint64_t k) { return (double(k) + 0.5) * 2.220446049250313080847e-16; }
 
 // sin(pi t), cos(pi t) for t in [0,2) with exact octant reduction
 inline void sincospi_host(double t, double* s, double* c)
@@ -104,15 +104,19 @@ struct Rng {
         } else if (mode == RNG_TAPE) {
             for (int i = 0; i < d; ++i) z[i] = (cursor < tape_len) ? tape[cursor++] : std::nan("");
         } else {
+            // Box-Muller pair q -> elements (2q, 2q+1); definition in mcmc_b200/csrc/rng.cuh / DESIGN.md
             for (int q = 0; 2 * q < d; ++q) {
                 uint32_t r[4];
                 philox4x32_10(uint32_t(q), uint32_t(draw + 1), chain, 0u, k0, k1, r);
-                const double u1 = u53_open(r[0], r[1]), u2 = u53_open(r[2], r[3]);
+                const double u1 = u52_open(top52(r[0], r[1]));
+                const uint64_t k2 = top52(r[2], r[3]);
+                const uint64_t f = k2 & ((uint64_t(1) << 50) - 1);
+                const int b0 = int((k2 >> 50) & 1), b1 = int((k2 >> 51) & 1);
                 const double rad = std::sqrt(-2.0 * std::log(u1));
                 double s, c;
-                sincospi_host(2.0 * u2, &s, &c);
-                z[2 * q] = rad * c;
-                if (2 * q + 1 < d) z[2 * q + 1] = rad * s;
+                sincospi_host(0.5 * ((double(f) + 0.5) * 8.8817841970012523234e-16), &s, &c);  // phi/pi = (f+1/2) 2^-51
+                z[2 * q] = (b0 ? -rad : rad) * c;
+                if (2 * q + 1 < d) z[2 * q + 1] = (b1 ? -rad : rad) * s;
             }
         }
         for (int i = 0; i < d; ++i) record(z[i]);
@@ -129,9 +133,19 @@ struct Rng {
         } else if (mode == RNG_TAPE) {
             u = (cursor < tape_len) ? tape[cursor++] : std::nan("");
         } else {
-            uint32_t r[4];
-            philox4x32_10(uint32_t(k), uint32_t(draw + 1), chain, 1u, k0, k1, r);
-            u = u53_open(r[0], r[1]);
+            if (k == 0) {
+                // uniform #0 of a draw: the 24 unused bits of normal blocks q = 0 and q = 1
+                uint32_t a[4], b[4];
+                philox4x32_10(0u, uint32_t(draw + 1), chain, 0u, k0, k1, a);
+                philox4x32_10(1u, uint32_t(draw + 1), chain, 0u, k0, k1, b);
+                const uint64_t sbits = (uint64_t(a[1] & 0xfffu) << 36) | (uint64_t(a[3] & 0xfffu) << 24) |
+                                       (uint64_t(b[1] & 0xfffu) << 12) | uint64_t(b[3] & 0xfffu);
+                u = (double(sbits) + 0.5) * 3.5527136788005009294e-15;  // 2^-48
+            } else {
+                uint32_t r[4];
+                philox4x32_10(uint32_t(k), uint32_t(draw + 1), chain, 1u, k0, k1, r);
+                u = u52_open(top52(r[0], r[1]));
+            }
         }
         record(u);
         return u;
