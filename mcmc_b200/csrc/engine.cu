@@ -173,8 +173,7 @@ static int stage_common(Staged& s, const mcmcb200_problem_t* pr, const mcmcb200_
 
     // RNG
     const long long n_total = n_burnin + n_keep;
-    c.rng.k0 = (unsigned)(rng->seed & 0xffffffffull);
-    c.rng.k1 = (unsigned)(rng->seed >> 32);
+    rng_set_key(c.rng, rng->seed);
     c.rng.tape = nullptr;
     c.rng.tape_stride = 0;
     if (rng->mode == MCMCB200_RNG_PHILOX) {
@@ -533,8 +532,7 @@ int mcmcb200_philox_stream(uint64_t seed, int64_t chain, int64_t draw, int32_t n
     if (rc) return rc;
     void* p = nullptr;
     if ((rc = pool_get(sc.dev, SLOT_EVAL_V, (size_t)(n_dim + n_unif) * sizeof(double), &p))) return rc;
-    if ((rc = launch_philox_stream((unsigned)(seed & 0xffffffffull), (unsigned)(seed >> 32), chain, draw, n_dim, n_unif,
-                                   static_cast<double*>(p), nullptr)))
+    if ((rc = launch_philox_stream(seed, chain, draw, n_dim, n_unif, static_cast<double*>(p), nullptr)))
         return rc;
     MCMCB200_CUDA_TRY(cudaMemcpy(out, p, (size_t)(n_dim + n_unif) * sizeof(double), cudaMemcpyDeviceToHost));
     return MCMCB200_OK;

@@ -84,7 +84,7 @@ int launch_mala(const MalaLaunch& a);
 int launch_nuts(const NutsLaunch& a);
 int launch_rmhmc(const RmhmcLaunch& a);
 int launch_target_eval(const EvalLaunch& a);
-int launch_philox_stream(unsigned k0, unsigned k1, long long chain, long long draw, int d, int n_unif, double* out_dev,
+int launch_philox_stream(unsigned long long seed, long long chain, long long draw, int d, int n_unif, double* out_dev,
                          cudaStream_t stream);
 long long nuts_work_doubles_per_chain(int d, int max_depth);
 

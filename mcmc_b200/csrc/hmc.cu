@@ -43,14 +43,18 @@ template <int EPL, bool STRICT> __device__ __forceinline__ void kick_full(double
     }
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaunch a)
+// resident CTAs per SM the register allocator should aim for (4096 chains = 1024 CTAs = 6.9 per SM at EPL <= 4)
+constexpr int hmc_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 4 : 2); }
+
+// FT ("full tile"): n_dim == 32*EPL and 16-byte aligned rows, so no padding predicates anywhere.
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_kernel(const __grid_constant__ HmcLaunch a)
 {
     extern __shared__ double smem[];
-    __shared__ double2 log_tab[RNGM == RNG_PHILOX ? LOG_TAB_SIZE : 1];
+    __shared__ double2 log_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
     typedef Ar<STRICT> A;
     if (RNGM == RNG_PHILOX) {
-        build_log_table(log_tab);
+        build_rng_tables(log_tab);
         __syncthreads();
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -63,7 +67,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaun
     const WarpCtx w{lane, d, tscr};
 
     double x[EPL], y[EPL], p[EPL], g[EPL];
-    load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
+    if (FT) load_vec_full<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), lane, x);
+    else load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
 
     ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
@@ -82,7 +87,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaun
 
     for (int t = 0; t < n_total; ++t) {
         // ---- momentum refresh: p = sqrtM z, K0 = p.(M^-1 p)/2 (lane partial in FAST) ----
-        rng.template normals<EPL>(a.rng, t, d, lane, log_tab, p);
+        rng.template normals<EPL, FT>(a.rng, t, d, lane, log_tab, p);
         double K0;
         if (DENSE_M) {
             double tmp[EPL];
@@ -153,11 +158,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaun
             const double comp = fmin(0.01, A::add(-A::add(U1, K1), A::add(U, K0)));
             acc = u < exp(comp);
         } else {
-            // dH = (U0 + K0) - (U1 + K1) in one butterfly; u < exp(min(0.01, dH)) holds trivially for dH >= 0 (u < 1),
-            // so exp() is only evaluated for dH < 0.  A non-finite energy rejects (src/hmc.cpp:180-182).
+            // dH = (U0 + K0) - (U1 + K1) in one butterfly.  u < exp(min(0.01, dH)) holds trivially for dH >= 0 (u < 1)
+            // and whenever u < 1 + dH (<= exp(dH)), so exp() is evaluated only in the thin band 1 + dH <= u: the
+            // decision is always that of the exact test.  A non-finite energy rejects (src/hmc.cpp:180-182).
             const double dH = warp_sum<false>((U + K0) - (U1 + K1));
             acc = false;
-            if (fabs(dH) <= 1.7976931348623157e308) acc = (dH >= 0.0) ? true : (u < exp(dH));
+            if (fabs(dH) <= 1.7976931348623157e308) acc = (u < 1.0 + dH) ? true : (u < exp(dH));
         }
         if (acc) {
             U = U1;
@@ -165,7 +171,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaun
             for (int k = 0; k < EPL; ++k) x[k] = y[k];
         }
         if (t >= n_burnin) {
-            store_vec<EPL>(out_row, d, lane, x);
+            if (FT) store_vec_full<EPL>(out_row, lane, x);
+            else store_vec<EPL>(out_row, d, lane, x);
             out_row += d;
             if (out_lp) {
                 const double Ur = STRICT ? U : warp_sum<false>(U);
@@ -178,12 +185,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32) hmc_kernel(const HmcLaun
     if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int launch_one(const HmcLaunch& a)
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT> static int launch_one(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dpad * sizeof(double) : 0;
-    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM>;
+    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT>;
     if (smem > 40 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -192,9 +199,14 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int laun
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch& a)
 {
-    if (a.rng.mode == RNG_PHILOX)
-        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
-    return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE>(a);
+    if (a.rng.mode == RNG_PHILOX) {
+        // the unpredicated full-tile kernels exist for the production configuration: Philox, identity mass
+        const bool ft = !DENSE_M && a.d == 32 * EPL && ((reinterpret_cast<uintptr_t>(a.x0) | reinterpret_cast<uintptr_t>(a.draws)) & 15) == 0;
+        if (!DENSE_M && ft)
+            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
+        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, false>(a);
+    }
+    return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE, false>(a);
 }
 
 template <class T, int EPL> static int launch_epl(const HmcLaunch& a)

@@ -61,16 +61,16 @@ int launch_target_eval(const EvalLaunch& a)
     }
 }
 
-template <int EPL> __global__ void philox_stream_kernel(RngArgs r, long long chain, long long draw, int d, int n_unif, double* out)
+template <int EPL> __global__ void philox_stream_kernel(const RngArgs r, long long chain, long long draw, int d, int n_unif, double* out)
 {
-    __shared__ double2 log_tab[LOG_TAB_SIZE];
-    build_log_table(log_tab);
+    __shared__ double2 log_tab[RNG_TAB_DOUBLE2];
+    build_rng_tables(log_tab);
     __syncthreads();
     const int lane = threadIdx.x & 31;
     ChainRng<RNG_PHILOX> rng;
     rng.init(r, 0, chain);
     double z[EPL];
-    rng.template normals<EPL>(r, draw, d, lane, log_tab, z);
+    rng.template normals<EPL, false>(r, draw, d, lane, log_tab, z);
     store_vec<EPL>(out, d, lane, z);
     for (int k = 0; k < n_unif; ++k) {
         const double u = rng.uniform(r, draw, k);
@@ -78,13 +78,12 @@ template <int EPL> __global__ void philox_stream_kernel(RngArgs r, long long cha
     }
 }
 
-int launch_philox_stream(unsigned k0, unsigned k1, long long chain, long long draw, int d, int n_unif, double* out_dev,
+int launch_philox_stream(unsigned long long seed, long long chain, long long draw, int d, int n_unif, double* out_dev,
                          cudaStream_t stream)
 {
     RngArgs r;
     r.mode = RNG_PHILOX;
-    r.k0 = k0;
-    r.k1 = k1;
+    rng_set_key(r, seed);
     r.tape = nullptr;
     r.tape_stride = 0;
     switch (epl_for_dim(d)) {

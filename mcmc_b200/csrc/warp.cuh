@@ -96,6 +96,22 @@ template <int EPL> __device__ __forceinline__ void load_vec(const double* __rest
     }
 }
 
+// full-tile variants: d == 32*EPL and 16-byte aligned rows (checked on the host), no predicates
+template <int EPL> __device__ __forceinline__ void load_vec_full(const double* __restrict__ src, int lane, double (&x)[EPL])
+{
+#pragma unroll
+    for (int m = 0; m < EPL / 2; ++m) {
+        const double2 v = *reinterpret_cast<const double2*>(src + m * 64 + 2 * lane);
+        x[2 * m] = v.x;
+        x[2 * m + 1] = v.y;
+    }
+}
+template <int EPL> __device__ __forceinline__ void store_vec_full(double* __restrict__ dst, int lane, const double (&x)[EPL])
+{
+#pragma unroll
+    for (int m = 0; m < EPL / 2; ++m) *reinterpret_cast<double2*>(dst + m * 64 + 2 * lane) = make_double2(x[2 * m], x[2 * m + 1]);
+}
+
 template <int EPL> __device__ __forceinline__ void store_vec(double* __restrict__ dst, int d, int lane, const double (&x)[EPL])
 {
     const bool vec_ok = ((d & 1) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);

@@ -110,13 +110,11 @@ struct Rng {
                 philox4x32_10(uint32_t(q), uint32_t(draw + 1), chain, 0u, k0, k1, r);
                 const double u1 = u52_open(top52(r[0], r[1]));
                 const uint64_t k2 = top52(r[2], r[3]);
-                const uint64_t f = k2 & ((uint64_t(1) << 50) - 1);
-                const int b0 = int((k2 >> 50) & 1), b1 = int((k2 >> 51) & 1);
                 const double rad = std::sqrt(-2.0 * std::log(u1));
                 double s, c;
-                sincospi_host(0.5 * ((double(f) + 0.5) * 8.8817841970012523234e-16), &s, &c);  // phi/pi = (f+1/2) 2^-51
-                z[2 * q] = (b0 ? -rad : rad) * c;
-                if (2 * q + 1 < d) z[2 * q + 1] = (b1 ? -rad : rad) * s;
+                sincospi_host((double(k2) + 0.5) * 4.4408920985006261617e-16, &s, &c);  // phi/pi = (k2+1/2) 2^-51
+                z[2 * q] = rad * c;
+                if (2 * q + 1 < d) z[2 * q + 1] = rad * s;
             }
         }
         for (int i = 0; i < d; ++i) record(z[i]);
