@@ -1,5 +1,386 @@
+// Many-chain NUTS with dual averaging: one persistent kernel, one warp per chain.
+//
+// Replaces internal::nuts_impl (/root/reference/src/nuts.cpp:30-332), nuts_find_initial_step_size and the
+// recursive nuts_build_tree (include/mcmc/nuts.ipp:30-93, 97-241), bug-compatibly.
+//
+// The recursion is restated per SURVEY Appendix C: a doubling of depth j in direction v starts from
+// S = (prev_draw, initial momentum of the draw) and only ever visits the states LF^k S (k leapfrog steps of size
+// v*eps): the leaf list of T(j, a) is o_j = o_{j-1} ++ (j + o_{j-1}) offset by a, its "near" slot is offset a+1 and
+// its "far" slot is a+j+1 when the first half did not stop (else the first half's far slot).  So instead of the
+// reference's 2^j leapfrogs per doubling the kernel computes each distinct state once (at most 1 + j(j+1)/2),
+// keeps (x_k, r_k, U_k, K_k) in a per-chain work area and replays the merge logic — slice counts, the uniform
+// draws in post-order, the theta' selection, alpha statistics and U-turn tests — on scalars and on dot products of
+// stored states, with an explicit stack instead of recursion.  Results are those of the literal recursion
+// (oracle.cpp build_tree restates it literally; tests compare the two).
+//
+// Per-chain work area (doubles, dp = n_dim rounded up to even):
+//   [0,dp) prev_draw  [dp,2dp) draw momentum  [2dp,3dp) theta+  [3dp,4dp) theta-  [4dp,5dp) r+  [5dp,6dp) r-
+//   then for k = 1..m_max: x_k, r_k (2 dp each), then U_k[m_max], K_k[m_max].
 #include "engine.h"
-namespace mcmcb200 {
-int launch_nuts(const NutsLaunch&) { set_error("nuts kernel not built yet"); return MCMCB200_ERR_UNSUPPORTED; }
+#include "rng.cuh"
+#include "targets.cuh"
+#include <math_constants.h>
+
+namespace mcmcb200
+{
+
+static __host__ __device__ int nuts_m_max(int max_depth)
+{
+    const int j = max_depth > 0 ? max_depth - 1 : 0;  // deepest tree built is depth max_depth-1
+    return 1 + j * (j + 1) / 2;
 }
-namespace mcmcb200 { long long nuts_work_doubles_per_chain(int, int) { return 1; } }
+
+long long nuts_work_doubles_per_chain(int d, int max_depth)
+{
+    const long long dp = (d + 1) & ~1;
+    const long long m = nuts_m_max(max_depth);
+    return 6 * dp + 2 * dp * m + 2 * m + 2;
+}
+
+constexpr int NUTS_MAX_LEVELS = 22;
+
+struct NutsStack {  // per-warp recursion stack (shared memory)
+    int j[NUTS_MAX_LEVELS], a[NUTS_MAX_LEVELS], phase[NUTS_MAX_LEVELS], sel[NUTS_MAX_LEVELS], nalpha[NUTS_MAX_LEVELS];
+    long long n[NUTS_MAX_LEVELS];
+    double alpha[NUTS_MAX_LEVELS];
+};
+
+constexpr int nuts_min_blocks(int epl) { return epl <= 4 ? 4 : (epl == 8 ? 2 : 1); }
+
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nuts_kernel(const __grid_constant__ NutsLaunch a)
+{
+    extern __shared__ double smem[];
+    __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
+    __shared__ NutsStack stacks[WARPS_PER_BLOCK];
+    typedef Ar<STRICT> A;
+    if (RNGM == RNG_PHILOX) {
+        build_rng_tables(rng_tab);
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long chain = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (chain >= a.n_chains) return;
+    const int d = a.d;
+    const int dp = (d + 1) & ~1;
+    double* tscr = smem + (size_t)warp * 2 * dp;
+    double* mscr = tscr + dp;
+    const WarpCtx w{lane, d, tscr};
+    NutsStack& st = stacks[warp];
+    const int m_max = nuts_m_max(a.max_depth);
+
+    double* W = a.work + chain * a.work_stride;
+    double* Wprev = W;
+    double* Wm = W + dp;
+    double* Wxp = W + 2 * dp;
+    double* Wxn = W + 3 * dp;
+    double* Wrp = W + 4 * dp;
+    double* Wrn = W + 5 * dp;
+    double* Wst = W + 6 * dp;  // state k (1-based): x at Wst + (k-1)*2dp, r at + dp
+    double* Us = Wst + (size_t)2 * dp * m_max;
+    double* Ks = Us + m_max;
+
+    // K = p.(M^-1 p)/2  (src/nuts.cpp:204, nuts.ipp:140)
+    auto kinetic = [&](const double (&p)[EPL]) -> double {
+        if (DENSE_M) {
+            double t[EPL];
+            stage_vec<EPL>(mscr, d, lane, p);
+            gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, 1.0, t);
+            return A::mul(0.5, warp_dot<EPL, STRICT>(p, t));
+        }
+        return A::mul(0.5, warp_dot<EPL, STRICT>(p, p));
+    };
+    // p = sqrtM z
+    auto momentum = [&](double (&p)[EPL]) {
+        if (DENSE_M) {
+            double t[EPL];
+            stage_vec<EPL>(mscr, d, lane, p);
+            gemv_cm<EPL, STRICT>(a.S_cm, d, lane, mscr, 1.0, t);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) p[k] = t[k];
+        }
+    };
+    // one leapfrog step of (signed) size e; g holds grad log pi(x) on entry and on exit; returns log pi(new x)
+    // (src/nuts.cpp:139-154: half kick, drift with (e M^-1) p, half kick — two gradient calls of which the first
+    //  repeats the previous step's last one)
+    auto leapfrog = [&](double e, double (&x)[EPL], double (&p)[EPL], double (&g)[EPL]) -> double {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) p[k] = STRICT ? A::add(p[k], A::mul(A::mul(e, g[k]), 0.5)) : fma(0.5 * e, g[k], p[k]);
+        if (DENSE_M) {
+            double t[EPL];
+            stage_vec<EPL>(mscr, d, lane, p);
+            gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, e, t);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) x[k] = A::add(x[k], t[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) x[k] = A::mad(e, p[k], x[k]);
+        }
+        const double lp = T::template eval<EPL, STRICT, true, true>(a.tdata, w, x, g);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) p[k] = STRICT ? A::add(p[k], A::mul(A::mul(e, g[k]), 0.5)) : fma(0.5 * e, g[k], p[k]);
+        return lp;
+    };
+    auto neg_logp_finite = [](double lp) -> double {
+        const double U = -lp;
+        return isfinite(U) ? U : CUDART_INF;  // "if (!std::isfinite(prop_U)) prop_U = posinf"
+    };
+
+    double x[EPL], xt[EPL], rt[EPL], gt[EPL];
+    load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
+    ChainRng<RNGM> rng;
+    rng.init(a.rng, chain, a.chain_offset + chain);
+    long long n_lf = 0;
+
+    // ---- pre-loop momentum draw (src/nuts.cpp:166-168) and nuts_find_initial_step_size (nuts.ipp:30-93) ----
+    rng.template normals<EPL, false>(a.rng, -1, d, lane, rng_tab, rt);
+    momentum(rt);
+    double eps = 1.0;
+    {
+        const double pU = neg_logp_finite(T::template eval<EPL, STRICT, true, true>(a.tdata, w, x, gt));
+        const double pK = kinetic(rt);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) xt[k] = x[k];
+        double qU = neg_logp_finite(leapfrog(eps, xt, rt, gt));
+        ++n_lf;
+        double qK = kinetic(rt);
+        double dH = A::add(-A::add(qU, qK), A::add(pU, pK));
+        int a_val = 2 * (dH > -0.69314718055994530942) - 1;   // > std::log(0.5)
+        bool cond = dH > -0.69314718055994530942;            // > -std::log(2)
+        while (cond) {
+            eps *= (a_val == 1) ? 2.0 : 0.5;                  // step_size *= std::pow(2, a_val)
+            qU = neg_logp_finite(leapfrog(eps, xt, rt, gt));   // state is NOT reset between doublings (Q14)
+            ++n_lf;
+            qK = kinetic(rt);
+            dH = A::add(-A::add(qU, qK), A::add(pU, pK));
+            a_val = 2 * (dH > -0.69314718055994530942) - 1;
+            cond = dH > -0.69314718055994530942;
+        }
+    }
+    const double mu = log(10.0 * eps);  // src/nuts.cpp:174
+    double h = 0.0;
+    double eps_bar = a.eps_bar0;
+    double prev_U = -T::template eval<EPL, STRICT, true, false>(a.tdata, w, x, gt);  // :181 (no finite clamp here)
+    store_vec<EPL>(Wprev, d, lane, x);
+
+    int n_acc = 0;
+    const int n_total = (int)(a.n_burnin + a.n_keep);
+    const int n_burnin = (int)a.n_burnin;
+    double* out_row = a.draws + chain * a.n_keep * d;
+    double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
+
+    for (int t = 0; t < n_total; ++t) {
+        int ucount = 0;
+        rng.template normals<EPL, false>(a.rng, t, d, lane, rng_tab, rt);   // :200
+        momentum(rt);                                                       // :202
+        const double prev_K = kinetic(rt);                                  // :204
+        store_vec<EPL>(Wm, d, lane, rt);
+        const double log_u = A::sub(A::sub(log(rng.uniform(a.rng, t, ucount++)), prev_U), prev_K);   // :206
+        store_vec<EPL>(Wxp, d, lane, x);   // :212-215
+        store_vec<EPL>(Wxn, d, lane, x);
+        store_vec<EPL>(Wrp, d, lane, rt);
+        store_vec<EPL>(Wrn, d, lane, rt);
+        __syncwarp();
+
+        int depth = 0, s_val = 1, n_alpha = 0, good_round = 0;
+        long long n_val = 1;
+        double alpha = 0.0;
+
+        while (s_val == 1 && depth < a.max_depth) {   // :227
+            const double zz = rng.uniform(a.rng, t, ucount++);   // :233
+            const int dir = (zz <= 0.5) ? -1 : 1;
+            const double e_signed = (dir == 1) ? eps : -eps;
+            const double H0 = A::add(prev_U, prev_K);
+
+            // tip of the lazily extended trajectory LF^k (prev_draw, draw momentum): always restarts here (Q12)
+            int computed = 0;
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) xt[k] = x[k];
+            load_vec<EPL>(Wm, d, lane, rt);
+            T::template eval<EPL, STRICT, false, true>(a.tdata, w, xt, gt);
+
+            // ---- T(depth, 0) with an explicit stack ----
+            int R_sel = 0, R_s = 0, R_nalpha = 0, R_far = 0;
+            long long R_n = 0;
+            double R_alpha = 0.0;
+            int level = 0;
+            st.j[0] = depth; st.a[0] = 0; st.phase[0] = 0;
+            while (level >= 0) {
+                const int j = st.j[level], ao = st.a[level], ph = st.phase[level];
+                if (ph == 0) {
+                    if (j == 0) {
+                        const int k_need = ao + 1;
+                        while (computed < k_need) {   // extend the trajectory by one leapfrog (nuts.ipp:132)
+                            const double lp = leapfrog(e_signed, xt, rt, gt);
+                            ++computed; ++n_lf;
+                            const double Uk = neg_logp_finite(lp);   // :134-138
+                            const double Kk = kinetic(rt);           // :140
+                            store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp, d, lane, xt);
+                            store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp + dp, d, lane, rt);
+                            if (lane == 0) { Us[computed - 1] = Uk; Ks[computed - 1] = Kk; }
+                            __syncwarp();
+                        }
+                        const double Uk = reinterpret_cast<volatile double*>(Us)[k_need - 1], Kk = reinterpret_cast<volatile double*>(Ks)[k_need - 1];
+                        R_n = (log_u <= A::sub(-Uk, Kk)) ? 1 : 0;                    // :146
+                        R_s = (log_u < A::sub(A::sub(1000.0, Uk), Kk)) ? 1 : 0;      // :147
+                        R_alpha = exp(fmin(0.0, A::add(-A::add(Uk, Kk), H0)));        // :157
+                        R_nalpha = 1;
+                        R_sel = k_need;
+                        R_far = k_need;
+                        --level;
+                    } else {
+                        if (lane == 0) { st.phase[level] = 1; st.j[level + 1] = j - 1; st.a[level + 1] = ao; st.phase[level + 1] = 0; }
+                        __syncwarp();
+                        ++level;
+                    }
+                } else if (ph == 1) {   // first half returned in R_*
+                    if (R_s == 1) {
+                        if (lane == 0) {
+                            st.sel[level] = R_sel; st.n[level] = R_n; st.alpha[level] = R_alpha; st.nalpha[level] = R_nalpha;
+                            st.phase[level] = 2;
+                            st.j[level + 1] = j - 1; st.a[level + 1] = ao + j; st.phase[level + 1] = 0;   // second half from far(A)
+                        }
+                        __syncwarp();
+                        ++level;
+                    } else {
+                        --level;   // result = first half's (nuts.ipp:234-239)
+                    }
+                } else {   // second half returned in R_*
+                    const long long nA = st.n[level];
+                    const double prob = (double)R_n / (double)(nA + R_n);        // :213
+                    const double z2 = rng.uniform(a.rng, t, ucount++);           // :214
+                    const int sel = (z2 < prob) ? R_sel : st.sel[level];
+                    // U-turn test on the updated slots: near = ao+1, far = ao+j+1 (Appendix C)
+                    double xn_[EPL], xf_[EPL], rn_[EPL], rf_[EPL];
+                    const int near = ao + 1, far = ao + j + 1;
+                    load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp, d, lane, xn_);
+                    load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp + dp, d, lane, rn_);
+                    load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp, d, lane, xf_);
+                    load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp + dp, d, lane, rf_);
+                    double diff[EPL];
+#pragma unroll
+                    for (int k = 0; k < EPL; ++k) diff[k] = (dir == 1) ? A::sub(xf_[k], xn_[k]) : A::sub(xn_[k], xf_[k]);   // pos - neg
+                    // dir=+1: pos=far, neg=near; dir=-1: pos=near, neg=far
+                    const double d_neg = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rn_) : warp_dot<EPL, STRICT>(diff, rf_);   // :226
+                    const double d_pos = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rf_) : warp_dot<EPL, STRICT>(diff, rn_);   // :227
+                    R_s = R_s * ((d_neg >= 0.0) ? 1 : 0) * ((d_pos >= 0.0) ? 1 : 0);                                           // :229
+                    R_sel = sel;
+                    R_n = nA + R_n;
+                    R_alpha = st.alpha[level] + R_alpha;
+                    R_nalpha = st.nalpha[level] + R_nalpha;
+                    R_far = far;
+                    --level;
+                }
+            }
+            alpha = R_alpha;   // overwritten by every doubling (Q12)
+            n_alpha = R_nalpha;
+
+            // the far slot of T lands in theta^v / r^v (src/nuts.cpp:241-256)
+            {
+                double xf_[EPL], rf_[EPL];
+                load_vec<EPL>(Wst + (size_t)(R_far - 1) * 2 * dp, d, lane, xf_);
+                load_vec<EPL>(Wst + (size_t)(R_far - 1) * 2 * dp + dp, d, lane, rf_);
+                store_vec<EPL>(dir == 1 ? Wxp : Wxn, d, lane, xf_);
+                store_vec<EPL>(dir == 1 ? Wrp : Wrn, d, lane, rf_);
+                __syncwarp();
+            }
+            if (R_s == 1) {
+                const double z3 = rng.uniform(a.rng, t, ucount++);   // :261
+                if (z3 < (double)R_n / (double)n_val) {              // :263
+                    load_vec<EPL>(Wst + (size_t)(R_sel - 1) * 2 * dp, d, lane, x);   // prev_draw = theta'
+                    prev_U = reinterpret_cast<volatile double*>(Us)[R_sel - 1];                                         // = -log pi(theta'), non-finite -> +inf
+                    store_vec<EPL>(Wprev, d, lane, x);
+                    good_round = 1;
+                }
+            }
+            n_val += R_n;   // :283
+            depth += 1;
+            {
+                double xp_[EPL], xn_[EPL], rp_[EPL], rn_[EPL], diff[EPL];
+                load_vec<EPL>(Wxp, d, lane, xp_);
+                load_vec<EPL>(Wxn, d, lane, xn_);
+                load_vec<EPL>(Wrp, d, lane, rp_);
+                load_vec<EPL>(Wrn, d, lane, rn_);
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) diff[k] = A::sub(xp_[k], xn_[k]);
+                const int c1 = warp_dot<EPL, STRICT>(diff, rn_) >= 0.0;   // :286
+                const int c2 = warp_dot<EPL, STRICT>(diff, rp_) >= 0.0;   // :287
+                s_val = R_s * c1 * c2;                                     // :289
+            }
+        }
+
+        // ---- dual averaging (src/nuts.cpp:294-302) ----
+        if (t < a.n_adapt) {
+            h += (1.0 / ((double)(t + 1) + a.t0)) * (a.delta - (alpha / (double)n_alpha) - h);
+            eps = exp(mu - h * sqrt((double)(t + 1)) / a.gamma);
+            eps_bar *= exp(pow((double)(t + 1), -a.kappa) * (log(eps) - log(eps_bar)));
+        } else {
+            eps = eps_bar;
+        }
+        if (t >= n_burnin) {
+            store_vec<EPL>(out_row, d, lane, x);
+            out_row += d;
+            if (out_lp) {
+                if (lane == 0) *out_lp = -prev_U;
+                ++out_lp;
+            }
+            n_acc += good_round;   // :308
+        }
+    }
+    if (lane == 0) {
+        if (a.n_accept) a.n_accept[chain] = n_acc;
+        if (a.step_out) a.step_out[chain] = eps;
+        if (a.n_leapfrog) a.n_leapfrog[chain] = n_lf;
+    }
+}
+
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int launch_one(const NutsLaunch& a)
+{
+    if (a.max_depth + 1 > NUTS_MAX_LEVELS) {
+        set_error("nuts: max_tree_depth %d exceeds %d", a.max_depth, NUTS_MAX_LEVELS - 1);
+        return MCMCB200_ERR_UNSUPPORTED;
+    }
+    const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const int dp = (a.d + 1) & ~1;
+    const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dp * sizeof(double) : 0;
+    auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM>;
+    if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
+    MCMCB200_CUDA_TRY(cudaGetLastError());
+    return MCMCB200_OK;
+}
+
+template <class T, int EPL, bool DENSE_M> static int launch_mass(const NutsLaunch& a)
+{
+    if (a.rng.mode == RNG_PHILOX)
+        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
+    return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE>(a);
+}
+
+template <class T> static int launch_target(const NutsLaunch& a)
+{
+    const bool dense = a.S_cm != nullptr;
+    switch (epl_for_dim(a.d)) {
+    case 2: return dense ? launch_mass<T, 2, true>(a) : launch_mass<T, 2, false>(a);
+    case 4: return dense ? launch_mass<T, 4, true>(a) : launch_mass<T, 4, false>(a);
+    case 8: return dense ? launch_mass<T, 8, true>(a) : launch_mass<T, 8, false>(a);
+    default:
+        set_error("nuts: n_dim=%d exceeds the register-resident kernels (max %d)", a.d, 256);
+        return MCMCB200_ERR_UNSUPPORTED;
+    }
+}
+
+int launch_nuts(const NutsLaunch& a)
+{
+    switch (a.target_id) {
+#define X(ID, TYPE) \
+    case ID: return launch_target<TYPE>(a);
+        MCMCB200_FOREACH_TARGET(X)
+#undef X
+    default:
+        set_error("nuts: unknown target id %d", a.target_id);
+        return MCMCB200_ERR_UNKNOWN_TARGET;
+    }
+}
+
+}  // namespace mcmcb200

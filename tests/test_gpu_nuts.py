@@ -1,0 +1,139 @@
+"""GPU parity tests for the NUTS path (src/nuts.cpp + nuts.ipp) through the C ABI.
+
+NUTS consumes a data-dependent number of uniforms per draw, so the reference-stream parity protocol is: the oracle
+(bit-equal to the unmodified reference, tests/test_oracle_vs_reference.py) runs on std::mt19937_64 and records every
+variate it consumes; the kernel replays that tape (USER_TAPE) with its memoised, stack-based tree and must
+reproduce the literal recursion's draws.
+
+Tolerances: with adaptation OFF the contract tolerance 1e-10 applies.  With dual averaging ON the reference
+algorithm itself amplifies last-bit differences (the step size feeds back on the energy errors of the previous tree):
+the CPU oracle run twice with nothing but its summation order changed drifts by up to ~3e-7 over 120 draws
+(tests/test_oracle_vs_reference.py::test_nuts_adaptation_amplifies_rounding), so adaptive runs are held to identical
+accept counts / decisions and an L-inf of ADAPT_TOL."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from test_gpu_hmc import _sym_pd, TOL
+
+ADAPT_TOL = 2e-5
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(engine, oracle, tid, tname, tdata, x0s, st, seed, arith, precond=None, chol_mode=1, tol=TOL):
+    C, d = x0s.shape
+    tapes, od, oa, ostep, onlf = [], [], [], [], []
+    for c in range(C):
+        o = oracle.run_chain(ol.NUTS, tid, tdata, x0s[c], st, seed=seed + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP,
+                             chol_mode=chol_mode, record_tape=4_000_000)
+        assert o["tape_used"] <= 4_000_000
+        tapes.append(o["tape"]); od.append(o["draws"]); oa.append(o["n_accept"]); ostep.append(o["final_step"])
+        onlf.append(o["n_leapfrog"])
+    L = max(len(t) for t in tapes) + 8
+    tape = np.zeros((C, L))
+    for c in range(C):
+        tape[c, :len(tapes[c])] = tapes[c]
+    r = engine.nuts(x0s, tname, target_data=tdata, step_size=st["step_size"], n_adapt_draws=st["n_adapt_draws"],
+                    target_accept_rate=st["target_accept_rate"], max_tree_depth=st["max_tree_depth"], gamma_val=st["gamma_val"],
+                    t0_val=st["t0_val"], kappa_val=st["kappa_val"], precond_mat=precond, chol_mode=chol_mode,
+                    n_burnin=st["n_burnin"], n_keep=st["n_keep"], rng_mode=engine.api.RNG_USER_TAPE, tape=tape, arith=arith)
+    od = np.stack(od)
+    assert np.abs(r["draws"] - od).max() <= tol, np.abs(r["draws"] - od).max()
+    assert np.array_equal(r["n_accept"], np.array(oa))
+    assert np.allclose(r["step_size"], ostep, rtol=1e3 * tol, atol=0)
+    # memoisation: never more leapfrogs than the literal recursion
+    assert (r["n_leapfrog"] <= np.array(onlf)).all()
+    return r, od, np.array(onlf)
+
+
+def test_g5_1d(engine, oracle, reference):
+    """1-D N(0,1), x0=0.3, seed 3, no adaptation, eps_bar=0.05."""
+    st = ol.Settings(n_burnin=0, n_keep=3, step_size=0.05, n_adapt_draws=0)
+    ref, acc = reference.run_chain(ol.NUTS, ol.TGT_ISO_GAUSS, None, [0.3], st, 3)
+    r, od, _ = _run_pair(engine, oracle, ol.TGT_ISO_GAUSS, "iso_gauss", None, np.array([[0.3]]), st, 3, engine.api.ARITH_STRICT)
+    assert np.abs(r["draws"][0] - ref).max() <= TOL
+    assert np.abs(ref[:, 0] - [0.29999999999999999, 0.87358199970259187, 0.86317002105720686]).max() < 1e-15
+
+
+@pytest.mark.parametrize("arith", ["strict", "fast"])
+def test_adaptation_aniso(engine, oracle, arith):
+    rng = np.random.default_rng(5)
+    d, C = 12, 6
+    w = np.exp(rng.uniform(-1.5, 1.5, size=d))
+    x0 = rng.normal(size=(C, d))
+    st = ol.Settings(n_burnin=60, n_keep=60, n_adapt_draws=60)
+    a = engine.api.ARITH_STRICT if arith == "strict" else engine.api.ARITH_FAST
+    r, od, nlf = _run_pair(engine, oracle, ol.TGT_DIAG_GAUSS, "diag_gauss", w, x0, st, 100, a, tol=ADAPT_TOL)
+    assert (r["n_leapfrog"] < nlf).any()  # deep-enough trees occurred for the memoisation to matter
+
+
+def test_deep_trees_no_adapt(engine, oracle):
+    """Small fixed step: trees reach depth 8-10, the regime where the reference re-traverses states (Q13)."""
+    rng = np.random.default_rng(6)
+    d, C = 8, 3
+    x0 = rng.normal(size=(C, d))
+    st = ol.Settings(n_burnin=0, n_keep=25, step_size=0.005, n_adapt_draws=0)
+    r, od, nlf = _run_pair(engine, oracle, ol.TGT_ISO_GAUSS, "iso_gauss", None, x0, st, 2, engine.api.ARITH_STRICT)
+    assert (nlf / r["n_leapfrog"]).min() > 3.0  # >3x fewer leapfrogs than the literal recursion
+
+
+def test_dense_target_dense_mass_c4_like(engine, oracle, reference):
+    """C4-shaped: dense-precision Gaussian with condition number ~1e3 (scaled down to d=32), dense precond_mat."""
+    rng = np.random.default_rng(8)
+    d, C = 32, 4
+    q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.logspace(0, 3, d)
+    P = (q / lam) @ q.T
+    P = (P + P.T) / 2
+    M = _sym_pd(rng, d, 0.5)
+    x0 = rng.normal(size=(C, d))
+    st = ol.Settings(n_burnin=30, n_keep=30, n_adapt_draws=30, precond=M)
+    r, od, _ = _run_pair(engine, oracle, ol.TGT_DENSE_GAUSS, "dense_gauss", P.ravel(), x0, st, 40, engine.api.ARITH_STRICT,
+                         precond=M, tol=ADAPT_TOL)
+    ref, acc, _ = reference.run_chains(ol.NUTS, ol.TGT_DENSE_GAUSS, P.ravel(), x0, st, 40)
+    assert np.abs(r["draws"] - ref).max() <= ADAPT_TOL
+    assert np.array_equal(r["n_accept"], acc)
+    # same target and mass matrix without adaptation: contract tolerance
+    st2 = ol.Settings(n_burnin=5, n_keep=40, n_adapt_draws=0, step_size=0.1, precond=M)
+    r2, od2, _ = _run_pair(engine, oracle, ol.TGT_DENSE_GAUSS, "dense_gauss", P.ravel(), x0, st2, 41, engine.api.ARITH_STRICT,
+                           precond=M)
+    ref2, acc2, _ = reference.run_chains(ol.NUTS, ol.TGT_DENSE_GAUSS, P.ravel(), x0, st2, 41)
+    assert np.abs(r2["draws"] - ref2).max() <= TOL
+
+
+def test_philox_mode_and_mt_tape_rejected(engine, oracle):
+    d, C = 40, 5
+    x0 = ol.c2_initial(C, d)
+    for n_adapt, eps0, tol in ((0, 0.2, TOL), (40, 1.0, 50 * ADAPT_TOL)):
+        st = ol.Settings(n_burnin=40, n_keep=40, n_adapt_draws=n_adapt, step_size=eps0)
+        od, oa = [], []
+        for c in range(C):
+            o = oracle.run_chain(ol.NUTS, ol.TGT_ISO_GAUSS, None, x0[c], st, seed=777, rng_mode=ol.RNG_PHILOX, chain_id=10 + c,
+                                 sum_mode=ol.SUM_WARP)
+            od.append(o["draws"]); oa.append(o["n_accept"])
+        r = engine.nuts(x0, "iso_gauss", n_burnin=40, n_keep=40, n_adapt_draws=n_adapt, step_size=eps0,
+                        rng_mode=engine.api.RNG_PHILOX, seed=777, chain_offset=10)
+        assert np.abs(r["draws"] - np.stack(od)).max() <= tol, (n_adapt, np.abs(r["draws"] - np.stack(od)).max())
+        assert np.array_equal(r["n_accept"], np.array(oa))
+    with pytest.raises(engine.McmcB200Error):
+        engine.nuts(x0, "iso_gauss", n_burnin=1, n_keep=1, rng_mode=engine.api.RNG_MT19937_TAPE, seed=1)
+
+
+def test_many_chains_d256_moments(engine):
+    """C4 scale per GPU: 512 chains, d=256 dense Gaussian (cond 1e3), default adaptation; checks stationarity."""
+    rng = np.random.default_rng(11)
+    d, C = 256, 512
+    q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.logspace(0, 3, d)  # covariance eigenvalues
+    P = (q / lam) @ q.T
+    P = (P + P.T) / 2
+    x0 = rng.normal(size=(C, d))
+    r = engine.nuts(x0, "dense_gauss", target_data=P, n_burnin=150, n_keep=20, n_adapt_draws=150, rng_mode=engine.api.RNG_PHILOX,
+                    seed=5)
+    dr = r["draws"]
+    assert np.isfinite(dr).all()
+    proj = dr.reshape(-1, d) @ q  # coordinates in the eigenbasis: variances should be lam
+    v = proj.var(axis=0)
+    assert np.abs(np.log(v / lam)).max() < 0.35, np.abs(np.log(v / lam)).max()
+    assert r["n_accept"].mean() / 20 > 0.5
