@@ -461,6 +461,7 @@ int mcmcb200_rmhmc_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, 
     a.n_fp = (int)st->n_fp_steps;
     a.eps = st->step_size;
     a.chol_mode = st->chol_mode;
+    a.cons_term = (double)(0.5 * (double)(size_t)pr->n_dim * 1.83787706640934548356L);
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
     if ((rc = launch_rmhmc(a))) return rc;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));

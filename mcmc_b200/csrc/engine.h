@@ -64,6 +64,7 @@ struct RmhmcLaunch : CommonLaunch {
     int n_leap, n_fp;
     double eps;
     int chol_mode;
+    double cons_term;  // 0.5 * n_dim * log(2 pi), computed in long double then narrowed (src/rmhmc.cpp:188)
 };
 
 struct EvalLaunch {
