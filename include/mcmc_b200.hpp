@@ -1,0 +1,492 @@
+// mcmc_b200.hpp — C++ drop-in for the hot path of kthohr/mcmc (MCMCLib 2.1.0) on top of the C ABI (mcmc_b200.h).
+//
+// Keeps the reference's call shape and settings surface:
+//
+//   reference (include/mcmc/hmc.hpp:43-72)            this header
+//   ------------------------------------------------   ------------------------------------------------------------
+//   bool mcmc::hmc(const ColVec_t& initial_vals,       bool mcmc::hmc(const ColVec_t& initial_vals,
+//        std::function<fp_t(const ColVec_t&,                mcmc::registered_kernel target_log_kernel,
+//                           ColVec_t*, void*)> kernel,      Mat_t& draws_out,
+//        Mat_t& draws_out, void* target_data                void* target_data /* mcmc::kernel_data* */
+//        [, algo_settings_t& settings]);                    [, algo_settings_t& settings]);
+//
+// and likewise mcmc::mala / mcmc::nuts / mcmc::rmhmc (rmhmc's tensor_fn / tensor_data arguments are kept for arity;
+// the metric is the one registered with the kernel).  A std::function cannot run on the GPU, so the second argument
+// names a REGISTERED __device__ functor (mcmc::device_kernel("iso_gauss"), ...) and `target_data` points to a
+// mcmc::kernel_data {values, n} that the library copies to the device.
+//
+// algo_settings_t and the per-sampler structs have the reference's field names and defaults
+// (include/misc/mcmc_structs.hpp:66-134,151-184); n_accept_draws is written back the same way (src/hmc.cpp:220-222).
+// draws_out comes back n_keep x n_vals, column-major, exactly like the Eigen/Armadillo Mat_t.
+//
+// Extras the reference does not have:
+//   * many chains per call: pass initial_vals as a Mat_t with one COLUMN per chain and receive a Cube_t
+//     (one n_keep x n_vals matrix per chain, the layout of DE's draws_out, src/de.cpp:146,216);
+//     chain c uses rng seed  rng_seed_value + c  (the convention of BASELINE.md §3);
+//   * settings.b200: RNG mode (MCMCB200_RNG_MT19937_TAPE reproduces the reference's std::mt19937_64 stream and is
+//     the default for drop-in parity; MCMCB200_RNG_PHILOX is the in-kernel production generator), arithmetic mode,
+//     device ordinal.
+//
+// Unsupported reference features fail loudly: vals_bound = true (box constraints) makes the call
+// return false with mcmc::last_error() set; it is never silently ignored and nothing is computed on the host.
+//
+// Vector / matrix types: with MCMC_ENABLE_EIGEN_WRAPPERS or MCMC_ENABLE_ARMA_WRAPPERS defined (as for the reference)
+// the Eigen / Armadillo types are used; otherwise a minimal column-major ColVec_t / Mat_t pair is provided.
+#ifndef MCMC_B200_HPP
+#define MCMC_B200_HPP
+
+#include <cstddef>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "mcmc_b200.h"
+
+#if defined(MCMC_ENABLE_EIGEN_WRAPPERS)
+#include <Eigen/Dense>
+#elif defined(MCMC_ENABLE_ARMA_WRAPPERS)
+#include <armadillo>
+#endif
+
+namespace mcmc
+{
+
+using uint_t = unsigned int;
+using fp_t = double;  // MCMC_FPN_TYPE (include/misc/mcmc_options.hpp:80-99); the device path is fp64
+
+#if defined(MCMC_ENABLE_EIGEN_WRAPPERS)
+using ColVec_t = Eigen::Matrix<fp_t, Eigen::Dynamic, 1>;
+using Mat_t = Eigen::Matrix<fp_t, Eigen::Dynamic, Eigen::Dynamic>;
+namespace b200_detail
+{
+inline const fp_t* cdata(const ColVec_t& v) { return v.data(); }
+inline const fp_t* cdata(const Mat_t& m) { return m.data(); }
+inline fp_t* mdata(Mat_t& m) { return m.data(); }
+inline size_t vsize(const ColVec_t& v) { return static_cast<size_t>(v.size()); }
+inline size_t msize(const Mat_t& m) { return static_cast<size_t>(m.size()); }
+inline size_t mrows(const Mat_t& m) { return static_cast<size_t>(m.rows()); }
+inline size_t mcols(const Mat_t& m) { return static_cast<size_t>(m.cols()); }
+inline void mresize(Mat_t& m, size_t r, size_t c) { m.resize(static_cast<Eigen::Index>(r), static_cast<Eigen::Index>(c)); }
+constexpr int default_chol = MCMCB200_CHOL_EIGEN_LLT;  // BMO_MATOPS_CHOL_LOWER under Eigen (core/cholesky.hpp:37, Q8)
+}
+#elif defined(MCMC_ENABLE_ARMA_WRAPPERS)
+using ColVec_t = arma::Col<fp_t>;
+using Mat_t = arma::Mat<fp_t>;
+namespace b200_detail
+{
+inline const fp_t* cdata(const ColVec_t& v) { return v.memptr(); }
+inline const fp_t* cdata(const Mat_t& m) { return m.memptr(); }
+inline fp_t* mdata(Mat_t& m) { return m.memptr(); }
+inline size_t vsize(const ColVec_t& v) { return static_cast<size_t>(v.n_elem); }
+inline size_t msize(const Mat_t& m) { return static_cast<size_t>(m.n_elem); }
+inline size_t mrows(const Mat_t& m) { return static_cast<size_t>(m.n_rows); }
+inline size_t mcols(const Mat_t& m) { return static_cast<size_t>(m.n_cols); }
+inline void mresize(Mat_t& m, size_t r, size_t c) { m.set_size(r, c); }
+constexpr int default_chol = MCMCB200_CHOL_LOWER;  // arma::chol(A, "lower") (core/cholesky.hpp:31)
+}
+#else
+// minimal stand-ins so the header is usable without a linear-algebra library
+class ColVec_t
+{
+  public:
+    ColVec_t() {}
+    explicit ColVec_t(size_t n) : d_(n, fp_t(0)) {}
+    ColVec_t(std::initializer_list<fp_t> l) : d_(l) {}
+    size_t size() const { return d_.size(); }
+    void resize(size_t n) { d_.resize(n); }
+    fp_t& operator()(size_t i) { return d_[i]; }
+    const fp_t& operator()(size_t i) const { return d_[i]; }
+    fp_t* data() { return d_.data(); }
+    const fp_t* data() const { return d_.data(); }
+
+  private:
+    std::vector<fp_t> d_;
+};
+class Mat_t  // column-major, like Eigen / Armadillo
+{
+  public:
+    Mat_t() : r_(0), c_(0) {}
+    Mat_t(size_t r, size_t c) : r_(r), c_(c), d_(r * c, fp_t(0)) {}
+    size_t rows() const { return r_; }
+    size_t cols() const { return c_; }
+    size_t size() const { return d_.size(); }
+    void resize(size_t r, size_t c) { r_ = r; c_ = c; d_.resize(r * c); }
+    fp_t& operator()(size_t i, size_t j) { return d_[j * r_ + i]; }
+    const fp_t& operator()(size_t i, size_t j) const { return d_[j * r_ + i]; }
+    fp_t* data() { return d_.data(); }
+    const fp_t* data() const { return d_.data(); }
+
+  private:
+    size_t r_, c_;
+    std::vector<fp_t> d_;
+};
+namespace b200_detail
+{
+inline const fp_t* cdata(const ColVec_t& v) { return v.data(); }
+inline const fp_t* cdata(const Mat_t& m) { return m.data(); }
+inline fp_t* mdata(Mat_t& m) { return m.data(); }
+inline size_t vsize(const ColVec_t& v) { return v.size(); }
+inline size_t msize(const Mat_t& m) { return m.size(); }
+inline size_t mrows(const Mat_t& m) { return m.rows(); }
+inline size_t mcols(const Mat_t& m) { return m.cols(); }
+inline void mresize(Mat_t& m, size_t r, size_t c) { m.resize(r, c); }
+constexpr int default_chol = MCMCB200_CHOL_EIGEN_LLT;
+}
+#endif
+
+// one matrix per chain (bmo::Cube_t analogue, include/BaseMatrixOps/include/extra/cube_type.hpp:23-68)
+class Cube_t
+{
+  public:
+    size_t n_mat() const { return mats_.size(); }
+    Mat_t& mat(size_t i) { return mats_[i]; }
+    const Mat_t& mat(size_t i) const { return mats_[i]; }
+    void set_n_mat(size_t n) { mats_.resize(n); }
+
+  private:
+    std::vector<Mat_t> mats_;
+};
+
+// ---- settings: field names and defaults of include/misc/mcmc_structs.hpp ------------------------------------
+struct hmc_settings_t {
+    size_t n_burnin_draws = 1E03;
+    size_t n_keep_draws = 1E03;
+    int omp_n_threads = -1;  // accepted and ignored: there is no host loop to parallelise
+    size_t n_leap_steps = 1;
+    fp_t step_size = 1.0;
+    Mat_t precond_mat;
+    size_t n_accept_draws = 0;  // returned: post-burn-in acceptances (of chain 0 in many-chain calls)
+};
+struct nuts_settings_t {
+    size_t n_burnin_draws = 1E03;
+    size_t n_keep_draws = 1E03;
+    int omp_n_threads = -1;
+    size_t n_adapt_draws = 1E03;
+    fp_t target_accept_rate = 0.55;
+    size_t max_tree_depth = size_t(10);
+    fp_t step_size = 1.0;  // \bar{\epsilon}_0
+    fp_t gamma_val = 0.05;
+    fp_t t0_val = 10;
+    fp_t kappa_val = 0.75;
+    Mat_t precond_mat;
+    size_t n_accept_draws = 0;
+};
+struct rmhmc_settings_t {
+    size_t n_burnin_draws = 1E03;
+    size_t n_keep_draws = 1E03;
+    int omp_n_threads = -1;
+    size_t n_leap_steps = 1;
+    fp_t step_size = 1.0;
+    Mat_t precond_mat;  // never read by the reference either
+    size_t n_fp_steps = 5;
+    size_t n_accept_draws = 0;
+};
+struct mala_settings_t {
+    size_t n_burnin_draws = 1E03;
+    size_t n_keep_draws = 1E03;
+    int omp_n_threads = -1;
+    fp_t step_size = 1.0;
+    Mat_t precond_mat;
+    size_t n_accept_draws = 0;
+};
+struct b200_settings_t {
+    int rng_mode = MCMCB200_RNG_MT19937_TAPE;  // reference-compatible stream by default (NUTS: Philox, see nuts())
+    int arith = MCMCB200_ARITH_FAST;
+    int chol_mode = b200_detail::default_chol;
+    int device = -1;
+    std::vector<size_t> n_accept_per_chain;  // returned by many-chain calls
+};
+struct algo_settings_t {
+    size_t rng_seed_value = std::random_device{}();  // mcmc_structs.hpp:155
+    bool vals_bound = false;
+    ColVec_t lower_bounds;
+    ColVec_t upper_bounds;
+    hmc_settings_t hmc_settings;
+    nuts_settings_t nuts_settings;
+    rmhmc_settings_t rmhmc_settings;
+    mala_settings_t mala_settings;
+    b200_settings_t b200;
+};
+
+// ---- the registered-functor replacement for the std::function callback --------------------------------------
+struct registered_kernel {
+    int target_id;
+};
+struct kernel_data {  // what `void* target_data` points to
+    const fp_t* values;
+    size_t n;
+};
+inline registered_kernel device_kernel(const char* name) { return registered_kernel{mcmcb200_target_lookup(name)}; }
+namespace b200_detail
+{
+inline std::string& wrapper_error()
+{
+    static thread_local std::string e;
+    return e;
+}
+}
+// text of the last failure of a mcmc::* call on this thread (the reference has no error channel: it always returns true)
+inline const char* last_error()
+{
+    return b200_detail::wrapper_error().empty() ? mcmcb200_last_error() : b200_detail::wrapper_error().c_str();
+}
+
+namespace b200_detail
+{
+
+inline void fill_problem(mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, const fp_t* x0, size_t d, size_t n_chains, registered_kernel k,
+                         void* target_data, const algo_settings_t& s, int rng_mode)
+{
+    std::memset(&pr, 0, sizeof(pr));
+    std::memset(&rng, 0, sizeof(rng));
+    const kernel_data* kd = static_cast<const kernel_data*>(target_data);
+    pr.n_chains = static_cast<int64_t>(n_chains);
+    pr.n_dim = static_cast<int32_t>(d);
+    pr.target_id = k.target_id;
+    pr.target_data = kd ? kd->values : nullptr;
+    pr.target_data_len = kd ? static_cast<int64_t>(kd->n) : 0;
+    pr.initial_vals = x0;  // d x C column-major == [C][d] chain-major
+    pr.initial_mem = MCMCB200_MEM_HOST;
+    pr.device = s.b200.device;
+    rng.mode = rng_mode;
+    rng.seed = s.rng_seed_value;
+}
+
+// [C][n_keep][d] chain-major -> per-chain n_keep x d column-major matrices
+inline void unpack(const std::vector<fp_t>& buf, size_t n_chains, size_t n_keep, size_t d, Mat_t* single, Cube_t* cube)
+{
+    if (cube) cube->set_n_mat(n_chains);
+    for (size_t c = 0; c < n_chains; ++c) {
+        Mat_t& m = cube ? cube->mat(c) : *single;
+        mresize(m, n_keep, d);
+        fp_t* out = mdata(m);
+        const fp_t* in = buf.data() + c * n_keep * d;
+        for (size_t t = 0; t < n_keep; ++t)
+            for (size_t j = 0; j < d; ++j) out[j * n_keep + t] = in[t * d + j];
+    }
+}
+
+inline const fp_t* precond_or_null(const Mat_t& m, size_t d) { return (msize(m) == d * d) ? cdata(m) : nullptr; }  // src/hmc.cpp:57
+
+template <class RunFn>
+inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, size_t n_keep,
+                int rng_mode, Mat_t* single, Cube_t* cube, size_t* n_accept_field, RunFn&& fn)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    wrapper_error().clear();
+    if (s.vals_bound) {
+        // box constraints are not on the device path yet: refuse rather than sample the wrong (unbounded) target
+        wrapper_error() = "mcmc_b200: vals_bound = true (box constraints) is not supported by the device path";
+        return false;
+    }
+    mcmcb200_problem_t pr;
+    mcmcb200_rng_t rng;
+    fill_problem(pr, rng, x0, d, n_chains, k, target_data, s, rng_mode);
+    std::vector<fp_t> buf(n_chains * n_keep * d);
+    std::vector<int64_t> acc(n_chains, 0);
+    mcmcb200_output_t out;
+    std::memset(&out, 0, sizeof(out));
+    out.draws_out = buf.data();
+    out.draws_mem = MCMCB200_MEM_HOST;
+    out.n_accept_draws = acc.data();
+    if (fn(pr, rng, out, s) != MCMCB200_OK) return false;
+    unpack(buf, n_chains, n_keep, d, single, cube);
+    if (sp) {  // written back only if a settings object was passed (src/hmc.cpp:220-222)
+        *n_accept_field = static_cast<size_t>(acc[0]);
+        s.b200.n_accept_per_chain.assign(acc.begin(), acc.end());
+    }
+    return true;
+}
+
+}  // namespace b200_detail
+
+// ================================================= HMC =======================================================
+namespace internal
+{
+inline bool hmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
+                     Cube_t* cube)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.hmc_settings.n_keep_draws, s.b200.rng_mode, single, cube,
+                            &s.hmc_settings.n_accept_draws,
+                            [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
+                                mcmcb200_hmc_settings_t h;
+                                mcmcb200_hmc_settings_default(&h);
+                                h.n_burnin_draws = static_cast<int64_t>(st.hmc_settings.n_burnin_draws);
+                                h.n_keep_draws = static_cast<int64_t>(st.hmc_settings.n_keep_draws);
+                                h.n_leap_steps = static_cast<int64_t>(static_cast<uint_t>(st.hmc_settings.n_leap_steps));  // Q22
+                                h.step_size = st.hmc_settings.step_size;
+                                h.precond_mat = b200_detail::precond_or_null(st.hmc_settings.precond_mat, d);
+                                h.chol_mode = st.b200.chol_mode;
+                                h.arith = st.b200.arith;
+                                return mcmcb200_hmc_run(&pr, &rng, &h, &out);
+                            });
+}
+}  // namespace internal
+
+inline bool hmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data)
+{
+    return internal::hmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr,
+                              &draws_out, nullptr);
+}
+inline bool hmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data,
+                algo_settings_t& settings)
+{
+    return internal::hmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, &settings,
+                              &draws_out, nullptr);
+}
+// many chains: one column of initial_vals per chain
+inline bool hmc(const Mat_t& initial_vals, registered_kernel target_log_kernel, Cube_t& draws_out, void* target_data,
+                algo_settings_t& settings)
+{
+    return internal::hmc_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
+                              target_log_kernel, target_data, &settings, nullptr, &draws_out);
+}
+
+// ================================================= MALA ======================================================
+namespace internal
+{
+inline bool mala_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
+                      Cube_t* cube)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.mala_settings.n_keep_draws, s.b200.rng_mode, single, cube,
+                            &s.mala_settings.n_accept_draws,
+                            [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
+                                mcmcb200_mala_settings_t m;
+                                mcmcb200_mala_settings_default(&m);
+                                m.n_burnin_draws = static_cast<int64_t>(st.mala_settings.n_burnin_draws);
+                                m.n_keep_draws = static_cast<int64_t>(st.mala_settings.n_keep_draws);
+                                m.step_size = st.mala_settings.step_size;
+                                m.precond_mat = b200_detail::precond_or_null(st.mala_settings.precond_mat, d);
+                                m.chol_mode = st.b200.chol_mode;
+                                m.arith = st.b200.arith;
+                                return mcmcb200_mala_run(&pr, &rng, &m, &out);
+                            });
+}
+}  // namespace internal
+
+inline bool mala(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data)
+{
+    return internal::mala_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr,
+                               &draws_out, nullptr);
+}
+inline bool mala(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data,
+                 algo_settings_t& settings)
+{
+    return internal::mala_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data,
+                               &settings, &draws_out, nullptr);
+}
+inline bool mala(const Mat_t& initial_vals, registered_kernel target_log_kernel, Cube_t& draws_out, void* target_data,
+                 algo_settings_t& settings)
+{
+    return internal::mala_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
+                               target_log_kernel, target_data, &settings, nullptr, &draws_out);
+}
+
+// ================================================= NUTS ======================================================
+// NUTS consumes a data-dependent number of uniforms per draw, so the reference's mt19937 stream cannot be replayed
+// from a precomputed tape: with rng_mode == MCMCB200_RNG_MT19937_TAPE the wrapper switches to in-kernel Philox
+// (seeded by rng_seed_value) instead of failing.
+namespace internal
+{
+inline bool nuts_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
+                      Cube_t* cube)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    const int rng_mode = (s.b200.rng_mode == MCMCB200_RNG_MT19937_TAPE) ? MCMCB200_RNG_PHILOX : s.b200.rng_mode;
+    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.nuts_settings.n_keep_draws, rng_mode, single, cube,
+                            &s.nuts_settings.n_accept_draws,
+                            [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
+                                mcmcb200_nuts_settings_t n;
+                                mcmcb200_nuts_settings_default(&n);
+                                n.n_burnin_draws = static_cast<int64_t>(st.nuts_settings.n_burnin_draws);
+                                n.n_keep_draws = static_cast<int64_t>(st.nuts_settings.n_keep_draws);
+                                n.n_adapt_draws = static_cast<int64_t>(st.nuts_settings.n_adapt_draws);
+                                n.target_accept_rate = st.nuts_settings.target_accept_rate;
+                                n.max_tree_depth = static_cast<int64_t>(st.nuts_settings.max_tree_depth);
+                                n.step_size = st.nuts_settings.step_size;
+                                n.gamma_val = st.nuts_settings.gamma_val;
+                                n.t0_val = st.nuts_settings.t0_val;
+                                n.kappa_val = st.nuts_settings.kappa_val;
+                                n.precond_mat = b200_detail::precond_or_null(st.nuts_settings.precond_mat, d);
+                                n.chol_mode = st.b200.chol_mode;
+                                n.arith = st.b200.arith;
+                                return mcmcb200_nuts_run(&pr, &rng, &n, &out);
+                            });
+}
+}  // namespace internal
+
+inline bool nuts(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data)
+{
+    return internal::nuts_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr,
+                               &draws_out, nullptr);
+}
+inline bool nuts(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data,
+                 algo_settings_t& settings)
+{
+    return internal::nuts_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data,
+                               &settings, &draws_out, nullptr);
+}
+inline bool nuts(const Mat_t& initial_vals, registered_kernel target_log_kernel, Cube_t& draws_out, void* target_data,
+                 algo_settings_t& settings)
+{
+    return internal::nuts_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
+                               target_log_kernel, target_data, &settings, nullptr, &draws_out);
+}
+
+// ================================================= RM-HMC ====================================================
+// The reference takes tensor_fn and tensor_data as separate arguments (include/mcmc/rmhmc.hpp:47-86); here the
+// metric is registered together with the kernel, so `tensor_fn` must be the same registered_kernel and tensor_data
+// is ignored.
+namespace internal
+{
+inline bool rmhmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
+                       Cube_t* cube)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.rmhmc_settings.n_keep_draws, s.b200.rng_mode, single, cube,
+                            &s.rmhmc_settings.n_accept_draws,
+                            [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
+                                mcmcb200_rmhmc_settings_t r;
+                                mcmcb200_rmhmc_settings_default(&r);
+                                r.n_burnin_draws = static_cast<int64_t>(st.rmhmc_settings.n_burnin_draws);
+                                r.n_keep_draws = static_cast<int64_t>(st.rmhmc_settings.n_keep_draws);
+                                r.n_leap_steps = static_cast<int64_t>(static_cast<uint_t>(st.rmhmc_settings.n_leap_steps));
+                                r.step_size = st.rmhmc_settings.step_size;
+                                r.n_fp_steps = static_cast<int64_t>(static_cast<uint_t>(st.rmhmc_settings.n_fp_steps));
+                                r.chol_mode = st.b200.chol_mode;
+                                r.arith = st.b200.arith;
+                                return mcmcb200_rmhmc_run(&pr, &rng, &r, &out);
+                            });
+}
+}  // namespace internal
+
+inline bool rmhmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, registered_kernel /*tensor_fn*/, Mat_t& draws_out,
+                  void* target_data, void* /*tensor_data*/)
+{
+    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr,
+                                &draws_out, nullptr);
+}
+inline bool rmhmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, registered_kernel /*tensor_fn*/, Mat_t& draws_out,
+                  void* target_data, void* /*tensor_data*/, algo_settings_t& settings)
+{
+    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data,
+                                &settings, &draws_out, nullptr);
+}
+inline bool rmhmc(const Mat_t& initial_vals, registered_kernel target_log_kernel, registered_kernel /*tensor_fn*/, Cube_t& draws_out,
+                  void* target_data, void* /*tensor_data*/, algo_settings_t& settings)
+{
+    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
+                                target_log_kernel, target_data, &settings, nullptr, &draws_out);
+}
+
+}  // namespace mcmc
+
+#endif  // MCMC_B200_HPP

@@ -1,0 +1,67 @@
+// Drives the C++ drop-in header exactly like reference user code and prints the draws as C99 hex floats so the
+// Python test can compare them bit-for-bit with tests/golden/reference_golden.json (cases G2, G3, G4, C2 chain 5).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "mcmc_b200.hpp"
+
+static void dump(const char* name, const mcmc::Mat_t& m, size_t n_accept)
+{
+    std::printf("%s %zu %zu %zu", name, (size_t)m.rows(), (size_t)m.cols(), n_accept);
+    for (size_t t = 0; t < m.rows(); ++t)
+        for (size_t j = 0; j < m.cols(); ++j) std::printf(" %a", m(t, j));
+    std::printf("\n");
+}
+
+int main()
+{
+    mcmc::Mat_t draws;
+    {   // G2: HMC d=3, seed 1
+        mcmc::ColVec_t x0(3); x0(0) = 1; x0(1) = -1; x0(2) = 0.5;
+        mcmc::algo_settings_t s; s.rng_seed_value = 1; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.hmc_settings.n_burnin_draws = 0; s.hmc_settings.n_keep_draws = 5; s.hmc_settings.n_leap_steps = 10; s.hmc_settings.step_size = 0.1;
+        if (!mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        dump("G2_hmc_d3", draws, s.hmc_settings.n_accept_draws);
+    }
+    {   // G3: MALA d=3, seed 1
+        mcmc::ColVec_t x0(3); x0(0) = 1; x0(1) = -1; x0(2) = 0.5;
+        mcmc::algo_settings_t s; s.rng_seed_value = 1; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.mala_settings.n_burnin_draws = 0; s.mala_settings.n_keep_draws = 5; s.mala_settings.step_size = 0.5;
+        if (!mcmc::mala(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        dump("G3_mala_d3", draws, s.mala_settings.n_accept_draws);
+    }
+    {   // G4: RM-HMC on the Normal model, seed 1
+        // data x_k = 2 + 2 sin k, k < 100: {n, mean, sum of squared deviations} exactly as stored in the golden fixture
+        const double stats[3] = {100.0, 0x1.00f8824d3cb51p+1, 0x1.901597d089536p+7};
+        mcmc::kernel_data dta = {stats, 3};
+        mcmc::ColVec_t x0(2); x0(0) = 3; x0(1) = 3;
+        mcmc::algo_settings_t s; s.rng_seed_value = 1; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.rmhmc_settings.n_burnin_draws = 0; s.rmhmc_settings.n_keep_draws = 5; s.rmhmc_settings.n_leap_steps = 1; s.rmhmc_settings.step_size = 0.2;
+        if (!mcmc::rmhmc(x0, mcmc::device_kernel("normal_model"), mcmc::device_kernel("normal_model"), draws, &dta, &dta, s)) {
+            std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        dump("G4_rmhmc_normal", draws, s.rmhmc_settings.n_accept_draws);
+    }
+    {   // many chains in one call: 3 chains of the C2 shape, chain 2 must equal a single-chain call with seed+2
+        const size_t d = 128, C = 3;
+        mcmc::Mat_t x0(d, C);
+        for (size_t c = 0; c < C; ++c) for (size_t j = 0; j < d; ++j) x0(j, c) = std::sin(0.37 * c + 0.11 * j);
+        mcmc::algo_settings_t s; s.rng_seed_value = 12345; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.hmc_settings.n_burnin_draws = 10; s.hmc_settings.n_keep_draws = 20; s.hmc_settings.n_leap_steps = 10; s.hmc_settings.step_size = 0.1;
+        mcmc::Cube_t cube;
+        if (!mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), cube, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        mcmc::ColVec_t x2(d); for (size_t j = 0; j < d; ++j) x2(j) = x0(j, 2);
+        mcmc::algo_settings_t s2 = s; s2.rng_seed_value = 12347;
+        if (!mcmc::hmc(x2, mcmc::device_kernel("iso_gauss"), draws, nullptr, s2)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        int same = (cube.n_mat() == C) && std::memcmp(cube.mat(2).data(), draws.data(), sizeof(double) * 20 * d) == 0;
+        std::printf("multichain_consistent %d %zu\n", same, s.b200.n_accept_per_chain.size());
+    }
+    {   // box constraints must be refused, not ignored
+        mcmc::ColVec_t x0(2); x0(0) = 1; x0(1) = 1;
+        mcmc::algo_settings_t s; s.vals_bound = true;
+        const bool ok = mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s);
+        std::printf("bounds_refused %d\n", ok ? 0 : 1);
+    }
+    return 0;
+}

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""Generate tests/golden/reference_golden.json from the UNMODIFIED reference (oracle/_ref/libmcmc_ref_strict.so:
+/root/reference/src/{hmc,mala,nuts,rmhmc}.cpp compiled against the stand-in Eigen, -O2 -ffp-contract=off).
+
+Run in the build container (where /root/reference exists):   python tests/golden/make_golden.py
+The reference ships no golden vectors of its own, so these fixtures pin the oracle — and through it
+the CUDA kernels — to outputs of the reference itself.  Floats are stored as C99 hex strings (bit-exact)."""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import oracle_lib as ol  # noqa: E402
+
+
+def hexlist(a):
+    return [float(v).hex() for v in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def cases():
+    rng = np.random.default_rng(20260925)
+
+    def sym_pd(d, shift):
+        a = rng.normal(size=(d, d))
+        m = a @ a.T / d + shift * np.eye(d)
+        return (m + m.T) / 2
+
+    xs = 2 + 2 * np.sin(np.arange(100.0))
+    nm = [100.0, float(xs.mean()), float(((xs - xs.mean()) ** 2).sum())]
+    P6, M6 = sym_pd(6, 1.0), sym_pd(6, 0.5)
+    A5, b5 = sym_pd(5, 2.0), rng.normal(size=5)
+    out = [
+        # SURVEY Appendix B
+        dict(name="G2_hmc_d3", sampler=ol.HMC, target=ol.TGT_ISO_GAUSS, tdata=None, x0=[1, -1, 0.5], seed=1,
+             st=dict(n_burnin=0, n_keep=5, n_leap_steps=10, step_size=0.1)),
+        dict(name="G3_mala_d3", sampler=ol.MALA, target=ol.TGT_ISO_GAUSS, tdata=None, x0=[1, -1, 0.5], seed=1,
+             st=dict(n_burnin=0, n_keep=5, step_size=0.5)),
+        dict(name="G4_rmhmc_normal", sampler=ol.RMHMC, target=ol.TGT_NORMAL_MODEL, tdata=nm, x0=[3, 3], seed=1,
+             st=dict(n_burnin=0, n_keep=5, n_leap_steps=1, step_size=0.2)),
+        dict(name="G5_nuts_1d", sampler=ol.NUTS, target=ol.TGT_ISO_GAUSS, tdata=None, x0=[0.3], seed=3,
+             st=dict(n_burnin=0, n_keep=3, step_size=0.05, n_adapt_draws=0)),
+        # C2 parity-subset shape (one chain of it: chain 5, seed 12345+5)
+        dict(name="C2_hmc_d128_chain5", sampler=ol.HMC, target=ol.TGT_ISO_GAUSS, tdata=None,
+             x0=ol.c2_initial(1, 128, 5)[0].tolist(), seed=12350, st=dict(n_burnin=10, n_keep=20, n_leap_steps=10, step_size=0.1)),
+        dict(name="hmc_dense_mass_dense_target", sampler=ol.HMC, target=ol.TGT_DENSE_GAUSS, tdata=P6.ravel().tolist(),
+             x0=rng.normal(size=6).tolist(), seed=3, st=dict(n_burnin=5, n_keep=40, n_leap_steps=5, step_size=0.15, precond=M6.tolist())),
+        dict(name="hmc_rejections", sampler=ol.HMC, target=ol.TGT_ISO_GAUSS, tdata=None, x0=ol.c2_initial(1, 32)[0].tolist(), seed=21,
+             st=dict(n_burnin=0, n_keep=60, n_leap_steps=3, step_size=1.3)),
+        dict(name="mala_d16", sampler=ol.MALA, target=ol.TGT_ISO_GAUSS, tdata=None, x0=rng.normal(size=16).tolist(), seed=11,
+             st=dict(n_burnin=10, n_keep=60, step_size=0.6)),
+        dict(name="mala_linreg_dense_precond", sampler=ol.MALA, target=ol.TGT_LINREG, tdata=np.concatenate([A5.ravel(), b5]).tolist(),
+             x0=rng.normal(size=5).tolist(), seed=5, st=dict(n_burnin=10, n_keep=60, step_size=0.25, precond=(sym_pd(5, 0.5) / 3).tolist())),
+        dict(name="nuts_d3_adapt", sampler=ol.NUTS, target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 4.0, 0.25], x0=[0.1, 0.2, 0.3], seed=1,
+             st=dict(n_burnin=50, n_keep=50, n_adapt_draws=50)),
+        dict(name="nuts_d8_deep_trees", sampler=ol.NUTS, target=ol.TGT_ISO_GAUSS, tdata=None, x0=rng.normal(size=8).tolist(), seed=2,
+             st=dict(n_burnin=0, n_keep=30, step_size=0.005, n_adapt_draws=0)),
+        dict(name="rmhmc_L2", sampler=ol.RMHMC, target=ol.TGT_NORMAL_MODEL, tdata=nm, x0=[3, 3], seed=2,
+             st=dict(n_burnin=10, n_keep=80, n_leap_steps=2, step_size=0.15)),
+    ]
+    return out
+
+
+def main():
+    ref = ol.Reference("strict")
+    golden = dict(generator="tests/golden/make_golden.py", source="oracle/_ref/libmcmc_ref_strict.so (unmodified /root/reference sources, "
+                  "stand-in Eigen, g++ -O2 -ffp-contract=off, libstdc++ <random>)", cases=[])
+    golden["rng_G1"] = dict(seed=1, n_norm=4, n_unif=1, values=hexlist(ref.rng_stream(1, 4, 1)))
+    for c in cases():
+        st = ol.Settings(**c["st"])
+        draws, acc = ref.run_chain(c["sampler"], c["target"], c["tdata"], c["x0"], st, c["seed"])
+        e = dict(c)
+        e["draws_shape"] = list(draws.shape)
+        e["draws_hex"] = hexlist(draws)
+        e["n_accept"] = int(acc)
+        golden["cases"].append(e)
+    path = os.path.join(HERE, "reference_golden.json")
+    with open(path, "w") as f:
+        json.dump(golden, f, indent=0)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(golden["cases"]), "cases")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+import json
+import os
+
+import numpy as np
+
+import oracle_lib as ol
+
+PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_golden.json")
+
+
+def load():
+    with open(PATH) as f:
+        g = json.load(f)
+    for c in g["cases"]:
+        c["draws"] = np.array([float.fromhex(h) for h in c["draws_hex"]]).reshape(c["draws_shape"])
+        c["settings"] = ol.Settings(**c["st"])
+    return g

@@ -1,0 +1,88 @@
+"""CPU tests of the product's C-ABI library (no GPU, no compute calls): it loads, exports every symbol that
+include/mcmc_b200.h declares, reports the reference's defaults, keeps its registry, generates the reference random
+stream on the host, and FAILS LOUDLY (no fallback) when no CUDA device is usable."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def api():
+    from mcmc_b200 import api as a
+
+    a.load()
+    return a
+
+
+def test_every_declared_symbol_is_exported(api):
+    header = open(os.path.join(ROOT, "include", "mcmc_b200.h")).read()
+    declared = set(re.findall(r"\b(mcmcb200_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 16
+    lib = ctypes.CDLL(api.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    assert declared == set(api.EXPORTED_SYMBOLS)
+
+
+def test_defaults_match_reference_structs(api):
+    """include/misc/mcmc_structs.hpp:66-134."""
+    lib = api.load()
+    h = api.HmcSettings(); lib.mcmcb200_hmc_settings_default(ctypes.byref(h))
+    assert (h.n_burnin_draws, h.n_keep_draws, h.n_leap_steps, h.step_size) == (1000, 1000, 1, 1.0) and not h.precond_mat
+    m = api.MalaSettings(); lib.mcmcb200_mala_settings_default(ctypes.byref(m))
+    assert (m.n_burnin_draws, m.n_keep_draws, m.step_size) == (1000, 1000, 1.0)
+    n = api.NutsSettings(); lib.mcmcb200_nuts_settings_default(ctypes.byref(n))
+    assert (n.n_burnin_draws, n.n_keep_draws, n.n_adapt_draws, n.target_accept_rate, n.max_tree_depth, n.step_size, n.gamma_val,
+            n.t0_val, n.kappa_val) == (1000, 1000, 1000, 0.55, 10, 1.0, 0.05, 10.0, 0.75)
+    r = api.RmhmcSettings(); lib.mcmcb200_rmhmc_settings_default(ctypes.byref(r))
+    assert (r.n_burnin_draws, r.n_keep_draws, r.n_leap_steps, r.step_size, r.n_fp_steps) == (1000, 1000, 1, 1.0, 5)
+
+
+def test_target_registry(api):
+    lib = api.load()
+    names = ["iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model"]
+    assert [lib.mcmcb200_target_lookup(n.encode()) for n in names] == [0, 1, 2, 3, 4]
+    assert lib.mcmcb200_target_lookup(b"nope") == -1
+    f = lib.mcmcb200_target_data_len
+    assert [f(t, 16) for t in range(4)] == [0, 16, 256, 272]
+    assert f(4, 2) == 3 and f(4, 3) == -1 and f(9, 4) == -1
+
+
+def test_host_side_reference_stream(api, oracle):
+    """MT19937 mode's host half: the tape equals what the oracle (bit-equal to the reference) consumes."""
+    st = ol.Settings(n_burnin=3, n_keep=4, n_leap_steps=1, step_size=0.1)
+    o = oracle.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, np.zeros(7), st, seed=2024, record_tape=200)
+    assert np.array_equal(api.mt19937_tape(2024, 0, 7, 7), o["tape"])
+    o = oracle.run_chain(ol.MALA, ol.TGT_ISO_GAUSS, None, np.zeros(3), st, seed=5, record_tape=200)
+    assert np.array_equal(api.mt19937_tape(5, 0, 7, 3), o["tape"])
+
+
+def test_no_cpu_fallback(api):
+    """Without a usable CUDA device every run call returns MCMCB200_ERR_CUDA — it never computes on the host."""
+    import mcmc_b200
+
+    if api.device_count() > 0:
+        pytest.skip("a CUDA device is visible")
+    for fn in (mcmc_b200.hmc, mcmc_b200.mala, mcmc_b200.nuts):
+        with pytest.raises(mcmc_b200.McmcB200Error) as e:
+            fn(np.zeros((2, 4)), "iso_gauss", n_burnin=1, n_keep=1)
+        assert e.value.code == api.ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_reference_the_oracle():
+    """The product path must never import, link or execute anything under oracle/."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mcmc_b200")):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("oracle/oracle.cpp", "").replace(
+                    "oracle/host_targets.hpp", ""), os.path.join(dirpath, f)

@@ -1,0 +1,67 @@
+"""The C++ drop-in header (include/mcmc_b200.hpp): compiles and links against the C-ABI library on the CPU; on a GPU
+box the same program, written like reference user code, must reproduce the reference's golden draws bit for bit."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tests", "cpp", "bin")
+
+
+def _build(src, out, std="c++14"):
+    from mcmc_b200 import api
+
+    assert os.path.exists(api.LIB_PATH), "build the library first (python -c 'import __graft_entry__ as g; g.build()')"
+    os.makedirs(BIN, exist_ok=True)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.dirname(api.LIB_PATH)
+    cmd = [cxx, "-std=" + std, "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", out, "-L", libdir, "-lmcmc_b200",
+           "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return out
+
+
+def test_header_and_examples_compile_and_link():
+    _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
+    _build(os.path.join(ROOT, "examples", "hmc_normal.cpp"), os.path.join(BIN, "hmc_normal"))
+
+
+@pytest.mark.gpu
+def test_dropin_program_reproduces_reference_goldens(engine):
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    by = {c["name"]: c for c in golden_util.load()["cases"]}
+    seen = set()
+    for line in r.stdout.splitlines():
+        tok = line.split()
+        if tok[0] in by:
+            rows, cols, acc = int(tok[1]), int(tok[2]), int(tok[3])
+            draws = np.array([float.fromhex(h) for h in tok[4:]]).reshape(rows, cols)
+            g = by[tok[0]]
+            assert np.abs(draws - g["draws"]).max() <= 1e-10, tok[0]
+            if tok[0] != "G4_rmhmc_normal":  # device log() vs glibc log() in the Normal model
+                assert np.array_equal(draws, g["draws"]), tok[0]
+            assert acc == g["n_accept"], tok[0]
+            seen.add(tok[0])
+        elif tok[0] == "multichain_consistent":
+            assert tok[1] == "1" and tok[2] == "3"
+            seen.add(tok[0])
+        elif tok[0] == "bounds_refused":
+            assert tok[1] == "1"
+            seen.add(tok[0])
+    assert seen == {"G2_hmc_d3", "G3_mala_d3", "G4_rmhmc_normal", "multichain_consistent", "bounds_refused"}
+
+
+@pytest.mark.gpu
+def test_example_runs(engine):
+    exe = _build(os.path.join(ROOT, "examples", "hmc_normal.cpp"), os.path.join(BIN, "hmc_normal"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    mean = [float(v) for v in r.stdout.splitlines()[0].split(":")[1].split("(")[0].split()]
+    assert abs(mean[0] - 2.0) < 0.3 and abs(mean[1] - 2.0) < 0.3, r.stdout

@@ -1,0 +1,145 @@
+"""CPU tests (no GPU): pin the oracle.
+
+1. oracle/liboracle.so (restated samplers) reproduces, BIT FOR BIT, the committed golden vectors that
+   tests/golden/make_golden.py generated from the unmodified reference (oracle/_ref) — runs everywhere.
+2. Where oracle/_ref is available (this container; the GPU box gets the prebuilt .so) the oracle is compared with the
+   live reference on further seeded configurations, again bit for bit.
+3. The alternative oracle modes used as GPU comparators (kernel reduction order, cancelled-form MALA, Philox) are tied
+   back to the reference-equivalent mode."""
+import numpy as np
+import pytest
+
+import golden_util
+import oracle_lib as ol
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return golden_util.load()
+
+
+def test_golden_rng_stream(oracle, golden):
+    """4 x rnorm then 1 x runif from mt19937_64(1) with the BaseMatrixOps semantics."""
+    g = golden["rng_G1"]
+    want = np.array([float.fromhex(h) for h in g["values"]])
+    st = ol.Settings(n_burnin=0, n_keep=1, n_leap_steps=0, step_size=0.1)
+    o = oracle.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, np.zeros(4), st, seed=1, record_tape=16)
+    assert np.array_equal(o["tape"], want)
+    assert np.abs(want - [-0.38683176162103994, 0.68682363917932543, -0.79514624370949216, 1.9379462044713822,
+                          0.089453193644654524]).max() < 1e-16
+
+
+def test_oracle_reproduces_every_golden_case(oracle, golden):
+    assert len(golden["cases"]) >= 12
+    for c in golden["cases"]:
+        o = oracle.run_chain(c["sampler"], c["target"], c["tdata"], c["x0"], c["settings"], seed=c["seed"], rng_mode=ol.RNG_MT,
+                             sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1)
+        assert np.array_equal(o["draws"], c["draws"]), c["name"]
+        assert o["n_accept"] == c["n_accept"], c["name"]
+
+
+def test_appendix_b_values(golden):
+    by = {c["name"]: c for c in golden["cases"]}
+    g2 = by["G2_hmc_d3"]["draws"]
+    assert np.abs(g2[0] - [0.21394863357965233, 0.038869637751197325, -0.40013418025888436]).max() < 1e-16
+    assert np.abs(g2[4] - [-2.3607964856140051, 0.1836841693287658, 0.44563121994797955]).max() < 1e-15
+    g3 = by["G3_mala_d3"]["draws"]
+    assert np.abs(g3[0] - [0.68158411918948003, -0.53158818041033729, 0.039926878145253919]).max() < 1e-16
+    g4 = by["G4_rmhmc_normal"]
+    assert g4["n_accept"] == 2 and np.abs(g4["draws"][2] - [3.0733742689491672, 2.9473085318575425]).max() < 1e-15
+    g5 = by["G5_nuts_1d"]["draws"][:, 0]
+    assert np.abs(g5 - [0.29999999999999999, 0.87358199970259187, 0.86317002105720686]).max() < 1e-16
+
+
+def _rand_cases():
+    rng = np.random.default_rng(314)
+
+    def sym_pd(d, shift):
+        a = rng.normal(size=(d, d))
+        m = a @ a.T / d + shift * np.eye(d)
+        return (m + m.T) / 2
+
+    xs = 2 + 2 * np.sin(np.arange(100.0))
+    nm = [100.0, float(xs.mean()), float(((xs - xs.mean()) ** 2).sum())]
+    P, M = sym_pd(7, 1.0), sym_pd(7, 0.5)
+    A, b = sym_pd(7, 2.0), rng.normal(size=7)
+    return [
+        ("hmc iso d=70", ol.HMC, ol.TGT_ISO_GAUSS, None, rng.normal(size=70), ol.Settings(n_burnin=5, n_keep=40, n_leap_steps=7, step_size=0.3), 5),
+        ("hmc diag", ol.HMC, ol.TGT_DIAG_GAUSS, np.linspace(0.5, 2, 9), rng.normal(size=9), ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=5, step_size=0.4), 6),
+        ("hmc dense/dense", ol.HMC, ol.TGT_DENSE_GAUSS, P.ravel(), rng.normal(size=7), ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=4, step_size=0.2, precond=M), 7),
+        ("hmc linreg", ol.HMC, ol.TGT_LINREG, np.concatenate([A.ravel(), b]), rng.normal(size=7), ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=4, step_size=0.1), 8),
+        ("hmc normal model", ol.HMC, ol.TGT_NORMAL_MODEL, nm, [3, 3], ol.Settings(n_burnin=10, n_keep=100, n_leap_steps=5, step_size=0.08), 9),
+        ("hmc unstable", ol.HMC, ol.TGT_ISO_GAUSS, None, rng.normal(size=6), ol.Settings(n_burnin=0, n_keep=15, n_leap_steps=400, step_size=2.5), 10),
+        ("mala iso", ol.MALA, ol.TGT_ISO_GAUSS, None, rng.normal(size=20), ol.Settings(n_burnin=5, n_keep=80, step_size=0.5), 11),
+        ("mala linreg M", ol.MALA, ol.TGT_LINREG, np.concatenate([A.ravel(), b]), rng.normal(size=7), ol.Settings(n_burnin=5, n_keep=80, step_size=0.3, precond=M / 2), 12),
+        ("nuts aniso adapt", ol.NUTS, ol.TGT_DIAG_GAUSS, np.exp(rng.uniform(-1, 1, 6)), rng.normal(size=6), ol.Settings(n_burnin=40, n_keep=40, n_adapt_draws=40), 13),
+        ("nuts dense M", ol.NUTS, ol.TGT_DENSE_GAUSS, P.ravel(), rng.normal(size=7), ol.Settings(n_burnin=20, n_keep=30, n_adapt_draws=20, precond=M), 14),
+        ("nuts depth cap 3", ol.NUTS, ol.TGT_ISO_GAUSS, None, rng.normal(size=5), ol.Settings(n_burnin=0, n_keep=40, n_adapt_draws=0, step_size=0.01, max_tree_depth=3), 15),
+        ("rmhmc L3", ol.RMHMC, ol.TGT_NORMAL_MODEL, nm, [2.5, 2.5], ol.Settings(n_burnin=5, n_keep=100, n_leap_steps=3, step_size=0.1, n_fp_steps=4), 16),
+    ]
+
+
+def test_oracle_bit_equal_to_live_reference(oracle, reference):
+    for name, sampler, tid, tdata, x0, st, seed in _rand_cases():
+        ref, acc = reference.run_chain(sampler, tid, tdata, x0, st, seed)
+        o = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1,
+                             mala_exact=1)
+        assert np.array_equal(o["draws"], ref), name
+        assert o["n_accept"] == acc, name
+
+
+def test_comparator_modes_agree_with_reference_mode(oracle):
+    """The GPU is compared with the oracle in SUM_WARP order / cancelled-form MALA; those modes must give the same
+    draws as the reference-equivalent mode whenever no accept decision sits within rounding of its threshold."""
+    for name, sampler, tid, tdata, x0, st, seed in _rand_cases():
+        if sampler == ol.NUTS and st["n_adapt_draws"] > 0:
+            continue  # see test_nuts_adaptation_amplifies_rounding
+        a = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, sum_mode=ol.SUM_SEQ, mala_exact=1)
+        b = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, sum_mode=ol.SUM_WARP, mala_exact=0)
+        assert np.abs(a["draws"] - b["draws"]).max() <= 1e-10, name
+        assert a["n_accept"] == b["n_accept"], name
+
+
+def test_nuts_adaptation_amplifies_rounding(oracle):
+    """Documents why adaptive-NUTS parity uses a looser tolerance: the reference algorithm, run twice on the CPU with
+    only the summation order of its dot products changed (last-bit differences in U and K), keeps every decision but
+    its draws drift apart by orders of magnitude more than without adaptation (where they stay bit-identical)."""
+    rng = np.random.default_rng(5)
+    w = np.exp(rng.uniform(-1.5, 1.5, size=12))
+    x0 = rng.normal(size=(6, 12))
+    worst_adapt, worst_fixed = 0.0, 0.0
+    for c in range(6):
+        st = ol.Settings(n_burnin=60, n_keep=60, n_adapt_draws=60)
+        a = oracle.run_chain(ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=100 + c, sum_mode=ol.SUM_SEQ)
+        b = oracle.run_chain(ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=100 + c, sum_mode=ol.SUM_WARP)
+        assert a["n_accept"] == b["n_accept"]
+        worst_adapt = max(worst_adapt, np.abs(a["draws"] - b["draws"]).max())
+        st = ol.Settings(n_burnin=60, n_keep=60, n_adapt_draws=0, step_size=0.3)
+        a = oracle.run_chain(ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=100 + c, sum_mode=ol.SUM_SEQ)
+        b = oracle.run_chain(ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=100 + c, sum_mode=ol.SUM_WARP)
+        worst_fixed = max(worst_fixed, np.abs(a["draws"] - b["draws"]).max())
+    assert worst_fixed <= 1e-12
+    assert 1e-12 < worst_adapt < 2e-5
+
+
+def test_philox_normals_are_standard_normal(oracle):
+    """The engine's production RNG as restated by the oracle: moments and independence of the Box-Muller output."""
+    z = np.concatenate([oracle.rng_stream(ol.RNG_PHILOX, 7, c, 3, 512, 1)[:512] for c in range(300)])
+    n = z.size
+    assert abs(z.mean()) < 4 / np.sqrt(n)
+    assert abs(z.var() - 1) < 4 * np.sqrt(2 / n)
+    assert abs((z ** 4).mean() - 3) < 4 * np.sqrt(96 / n)
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 4 / np.sqrt(n / 2)
+    u = np.array([oracle.rng_stream(ol.RNG_PHILOX, 7, c, t, 2, 2)[2:] for c in range(50) for t in range(40)]).ravel()
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 4 / np.sqrt(12 * u.size)
+
+
+def test_philox_stream_is_sharding_invariant(oracle):
+    """Counters carry the GLOBAL chain id: a chain's draws do not depend on which shard it belongs to."""
+    st = ol.Settings(n_burnin=2, n_keep=6, n_leap_steps=3, step_size=0.2)
+    x0 = ol.c2_initial(1, 10, 77)[0]
+    a = oracle.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=77)
+    b = oracle.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=78)
+    assert not np.array_equal(a["draws"], b["draws"])
+    c = oracle.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=77)
+    assert np.array_equal(a["draws"], c["draws"])
