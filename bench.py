@@ -104,38 +104,62 @@ def ref_lib():
     return ol, None, "port"
 
 
-def cpu_reference_throughput(n_chains, steps=1, warmup=0):
-    """draws/s of the unmodified reference on all host threads; one 'step' = n_chains chains x N_TOTAL draws."""
-    ol, ref, kind = ref_lib()
-    st = ol.Settings(n_burnin=N_BURNIN, n_keep=N_KEEP, n_leap_steps=LEAP, step_size=EPS)
-    x0 = initial_vals(0, n_chains)
-    if ref is not None:
-        cores = ref.max_threads()
-        run = lambda: ref.run_chains(ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, SEED, n_threads=cores, keep_draws=False)[2]
-    else:  # reference could not be compiled here: time the restated port, single thread
-        orc = ol.Oracle()
-        cores = 1
+def usable_cpus():
+    """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota if there is one."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q[0] != "max":
+            n = min(n, max(1, int(float(q[0]) / float(q[1]))))
+    except (OSError, ValueError, IndexError):
+        try:
+            quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if quota > 0:
+                n = min(n, max(1, quota // period))
+        except (OSError, ValueError):
+            pass
+    return max(1, n)
 
-        def run():
-            t0 = time.perf_counter()
-            for c in range(n_chains):
-                orc.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, x0[c], st, seed=SEED + c)
-            return time.perf_counter() - t0
+
+def cpu_reference_throughput(steps=1, warmup=0, target_seconds=8.0):
+    """draws/s of the unmodified reference (oracle/_ref: OpenMP loop over chains, one mcmc::hmc call per chain) on all
+    usable host threads.  One 'step' = a bounded sample of the C2 workload: n_chains chains x N_TOTAL draws with the
+    same d, L, eps and seeds, n_chains sized from a short pilot so that a step takes about target_seconds."""
+    ol, ref, kind = ref_lib()
+    cores = usable_cpus()
+
+    def run(n_chains, n_burnin, n_keep):
+        st = ol.Settings(n_burnin=n_burnin, n_keep=n_keep, n_leap_steps=LEAP, step_size=EPS)
+        x0 = initial_vals(0, n_chains)
+        if ref is not None:
+            return ref.run_chains(ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, SEED, n_threads=cores, keep_draws=False)[2]
+        orc = ol.Oracle()  # reference could not be compiled here: time the restated port, single thread
+        t0 = time.perf_counter()
+        for c in range(n_chains):
+            orc.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, x0[c], st, seed=SEED + c)
+        return time.perf_counter() - t0
+
+    if ref is None:
+        cores = 1
+    pilot_chains = max(2, cores)
+    run(pilot_chains, 10, 100)                            # first call also starts the OpenMP thread pool
+    el = run(pilot_chains, N_BURNIN, N_KEEP)              # pilot: one full-length chain per thread (each call has an O(d^3) set-up)
+    rate = pilot_chains * N_TOTAL / max(el, 1e-6)
+    n_chains = int(min(4096, max(cores, round(target_seconds * rate / N_TOTAL))))
     for _ in range(warmup):
-        run()
-    el = [run() for _ in range(steps)]
-    per_step = sum(el) / len(el)
+        run(n_chains, N_BURNIN, N_KEEP)
+    els = [run(n_chains, N_BURNIN, N_KEEP) for _ in range(steps)]
+    per_step = sum(els) / len(els)
     return dict(value=n_chains * N_TOTAL / per_step, cores=cores, kind=kind, seconds_per_step=per_step,
-                sample="%d chains x %d draws per step (same d, L, eps, seeds %d+c)" % (n_chains, N_TOTAL, SEED))
+                sample="%d chains x %d draws per step (same d, L, eps, seeds %d+c), %d host threads" % (n_chains, N_TOTAL, SEED, cores))
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    ncpu = os.cpu_count() or 1
-    n_chains = max(64, min(2048, 16 * ncpu))
-    r = cpu_reference_throughput(n_chains, steps=args.steps, warmup=min(args.warmup, 1))
+    r = cpu_reference_throughput(steps=args.steps, warmup=min(args.warmup, 1), target_seconds=6.0)
     line = {
         "impl": "reference", "metric": "HMC draws/sec (chains x iters, d=128)", "value": r["value"], "unit": "draws/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": r["seconds_per_step"] * 1e3,
@@ -308,8 +332,7 @@ def main():
         if gather is not None:
             line["allgather"] = gather
         if world == 1 and not args.no_cpu_baseline:
-            ncpu = os.cpu_count() or 1
-            cb = cpu_reference_throughput(max(64, min(4096, 48 * ncpu)))
+            cb = cpu_reference_throughput(steps=1, warmup=0, target_seconds=12.0)
             line["cpu_baseline"] = {"value": cb["value"], "unit": "draws/s", "cores": cb["cores"], "kind": cb["kind"],
                                     "sample": cb["sample"]}
         print(json.dumps(line))

@@ -62,11 +62,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     if (chain >= a.n_chains) return;  // whole warp exits together; no block-level barriers below
     const int d = a.d;
     const int dpad = (d + 1) & ~1;
-    double* tscr = smem + (size_t)warp * 2 * dpad;  // target functor scratch
+    double* bscr = smem + (size_t)warp * 3 * dpad;  // backup of the current state while a trajectory runs in place
+    double* tscr = bscr + dpad;                      // target functor scratch
     double* mscr = tscr + dpad;                      // mass-matrix scratch
     const WarpCtx w{lane, d, tscr};
 
-    double x[EPL], y[EPL], p[EPL], g[EPL];
+    double x[EPL], p[EPL], g[EPL];
     if (FT) load_vec_full<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), lane, x);
     else load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
 
@@ -102,40 +103,33 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             K0 = A::mul(0.5, STRICT ? warp_dot<EPL, STRICT>(p, p) : lane_dot<EPL, STRICT>(p, p));
         }
 
-        // ---- trajectory on y; x stays untouched until the proposal is accepted ----
+        // ---- trajectory in place on x; the current state is parked in shared memory (2 x STS.128 per lane at d=128)
+        //      and only read back on a rejection ----
         double U1;
         if (L > 0) {
+            if (FT) store_vec_full<EPL>(bscr, lane, x);
+            else store_vec<EPL>(bscr, d, lane, x);
             T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
             kick_half<EPL, STRICT>(p, g, eps, heps);
-            if (DENSE_M) {
-                double tmp[EPL];
-                stage_vec<EPL>(mscr, d, lane, p);
-                gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);  // (eps M^-1) p
-#pragma unroll
-                for (int k = 0; k < EPL; ++k) y[k] = A::add(x[k], tmp[k]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < EPL; ++k) y[k] = A::mad(eps, p[k], x[k]);
-            }
-            for (int s = 1; s < L; ++s) {
-                T::template eval<EPL, STRICT, false, true>(a.tdata, w, y, g);
-                kick_full<EPL, STRICT>(p, g, eps);  // end of step s-1 and start of step s share this gradient
+            for (int s = 0; s < L; ++s) {
                 if (DENSE_M) {
                     double tmp[EPL];
                     stage_vec<EPL>(mscr, d, lane, p);
-                    gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);
+                    gemv_cm<EPL, STRICT>(a.Minv_cm, d, lane, mscr, eps, tmp);  // (eps M^-1) p
 #pragma unroll
-                    for (int k = 0; k < EPL; ++k) y[k] = A::add(y[k], tmp[k]);
+                    for (int k = 0; k < EPL; ++k) x[k] = A::add(x[k], tmp[k]);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < EPL; ++k) y[k] = A::mad(eps, p[k], y[k]);
+                    for (int k = 0; k < EPL; ++k) x[k] = A::mad(eps, p[k], x[k]);
+                }
+                if (s + 1 < L) {
+                    T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
+                    kick_full<EPL, STRICT>(p, g, eps);  // end of step s and start of step s+1 share this gradient
                 }
             }
-            U1 = -T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, y, g);  // value-only call of :178 fused in
+            U1 = -T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, x, g);  // value-only call of :178 fused in
             kick_half<EPL, STRICT>(p, g, eps, heps);
         } else {
-#pragma unroll
-            for (int k = 0; k < EPL; ++k) y[k] = x[k];
             U1 = U;
         }
 
@@ -167,8 +161,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
         }
         if (acc) {
             U = U1;
-#pragma unroll
-            for (int k = 0; k < EPL; ++k) x[k] = y[k];
+        } else if (L > 0) {
+            if (FT) load_vec_full<EPL>(bscr, lane, x);
+            else load_vec<EPL>(bscr, d, lane, x);
         }
         if (t >= n_burnin) {
             if (FT) store_vec_full<EPL>(out_row, lane, x);
@@ -189,7 +184,7 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT> static
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
-    const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dpad * sizeof(double) : 0;
+    const size_t smem = (size_t)WARPS_PER_BLOCK * ((T::needs_scratch || DENSE_M) ? 3 : 1) * dpad * sizeof(double);
     auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT>;
     if (smem > 40 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
