@@ -129,7 +129,7 @@ static int upload(int dev, Slot slot, const double* host, size_t n, cudaStream_t
 
 // tape_per_chain > 0: doubles of reference-stream tape each chain needs in MT19937 mode (0 = sampler cannot use it)
 static int stage_common(Staged& s, const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, int arith, long long n_burnin,
-                        long long n_keep, long long n_pre_normals, bool mt_tape_supported, mcmcb200_output_t* out)
+                        long long n_keep, long long n_pre_normals, bool mt_tape_supported, mcmcb200_output_t* out, int max_dim = 32 * MAX_EPL)
 {
     if (!pr || !rng || !out) { set_error("null argument"); return MCMCB200_ERR_INVALID_ARG; }
     if (pr->n_chains <= 0 || pr->n_dim <= 0) { set_error("n_chains and n_dim must be positive"); return MCMCB200_ERR_INVALID_ARG; }
@@ -146,8 +146,8 @@ static int stage_common(Staged& s, const mcmcb200_problem_t* pr, const mcmcb200_
         set_error("target %d needs %lld doubles of data, got %lld", pr->target_id, (long long)need, (long long)pr->target_data_len);
         return MCMCB200_ERR_INVALID_ARG;
     }
-    if (epl_for_dim(d) == 0) {
-        set_error("n_dim=%d exceeds the register-resident kernels (max %d)", d, 32 * MAX_EPL);
+    if (d > max_dim) {
+        set_error("n_dim=%d exceeds what this sampler/target combination supports (max %d)", d, max_dim);
         return MCMCB200_ERR_UNSUPPORTED;
     }
     int rc = s.scope.enter(pr->device);
@@ -372,7 +372,11 @@ int mcmcb200_mala_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, c
 {
     if (!st) { set_error("null settings"); return MCMCB200_ERR_INVALID_ARG; }
     Staged s;
-    int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out);
+    // dense quadratic targets with M = I run chain-batched (one fp64 tensor-core GEMM per draw for all chains) when the
+    // dimension is beyond the register-resident kernels or there are enough chains to fill GEMM tiles
+    const bool wide_ok = pr && mala_wide_supported(pr->target_id, pr->n_dim, st->precond_mat != nullptr) && !pr->broadcast_initial;
+    const bool use_wide = wide_ok && (pr->n_dim > 32 * MAX_EPL || pr->n_chains >= 256);
+    int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out, use_wide ? 2048 : 32 * MAX_EPL);
     if (rc) return rc;
     MalaLaunch a;
     static_cast<CommonLaunch&>(a) = s.c;
@@ -397,14 +401,22 @@ int mcmcb200_mala_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, c
         if ((rc = upload(s.scope.dev, SLOT_MAT_C, st->precond_mat, nn, s.stream, &a.M_cm))) return rc;
         MCMCB200_CUDA_TRY(cudaStreamSynchronize(s.stream));
     }
-    MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
-    if ((rc = launch_mala(a))) return rc;
+    int launches = 1;
+    if (use_wide) {
+        void* wp = nullptr;
+        if ((rc = pool_get(s.scope.dev, SLOT_WORK, (size_t)mala_wide_work_doubles(pr->n_chains, pr->n_dim) * sizeof(double), &wp))) return rc;
+        MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
+        if ((rc = launch_mala_wide(a, static_cast<double*>(wp), &launches))) return rc;
+    } else {
+        MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
+        if ((rc = launch_mala(a))) return rc;
+    }
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
     if (out->n_leapfrog_out)
         for (long long c = 0; c < pr->n_chains; ++c) out->n_leapfrog_out[c] = 0;
     if (out->step_size_out)
         for (long long c = 0; c < pr->n_chains; ++c) out->step_size_out[c] = st->step_size;
-    return finish_common(s, out, 1);
+    return finish_common(s, out, launches);
 }
 
 int mcmcb200_nuts_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, const mcmcb200_nuts_settings_t* st,

@@ -82,6 +82,10 @@ struct EvalLaunch {
 // each returns a cudaError_t-like status: 0 ok, MCMCB200_ERR_* otherwise (message via set_error)
 int launch_hmc(const HmcLaunch& a);
 int launch_mala(const MalaLaunch& a);
+// chain-batched path (mala_wide.cu): dense quadratic targets, M = I, n_dim <= 2048
+bool mala_wide_supported(int target_id, int d, bool has_precond);
+long long mala_wide_work_doubles(long long n_chains, int d);
+int launch_mala_wide(const MalaLaunch& a, double* work, int* launches);
 int launch_nuts(const NutsLaunch& a);
 int launch_rmhmc(const RmhmcLaunch& a);
 int launch_target_eval(const EvalLaunch& a);

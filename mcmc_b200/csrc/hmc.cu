@@ -62,7 +62,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     if (chain >= a.n_chains) return;  // whole warp exits together; no block-level barriers below
     const int d = a.d;
     const int dpad = (d + 1) & ~1;
-    double* bscr = smem + (size_t)warp * 3 * dpad;  // backup of the current state while a trajectory runs in place
+    constexpr bool NEED_SCR = T::needs_scratch || DENSE_M;  // must match the launcher's shared-memory size
+    double* bscr = smem + (size_t)warp * (NEED_SCR ? 3 : 1) * dpad;  // backup of the current state while a trajectory runs in place
     double* tscr = bscr + dpad;                      // target functor scratch
     double* mscr = tscr + dpad;                      // mass-matrix scratch
     const WarpCtx w{lane, d, tscr};
