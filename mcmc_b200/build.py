@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcmc_b200.so")
 
-CU_SOURCES = ["engine.cu", "hmc.cu", "mala.cu", "mala_wide.cu", "nuts.cu", "rmhmc.cu", "util_kernels.cu"]
+CU_SOURCES = ["engine.cu", "hmc.cu", "hmc_wide.cu", "mala.cu", "mala_wide.cu", "nuts.cu", "rmhmc.cu", "util_kernels.cu"]
 CPP_SOURCES = ["host_tape.cpp", "host_linalg.cpp"]
 
 NVCC_FLAGS = [

@@ -348,7 +348,8 @@ int mcmcb200_hmc_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, co
     if (!st) { set_error("null settings"); return MCMCB200_ERR_INVALID_ARG; }
     if (st->n_leap_steps < 0 || st->n_leap_steps > 0x7fffffff) { set_error("bad n_leap_steps"); return MCMCB200_ERR_INVALID_ARG; }
     Staged s;
-    int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out);
+    const bool wide = pr && hmc_wide_supported(pr->target_id, pr->n_dim, st->precond_mat != nullptr);
+    int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out, wide ? 2048 : 32 * MAX_EPL);
     if (rc) return rc;
     HmcLaunch a;
     static_cast<CommonLaunch&>(a) = s.c;
@@ -358,7 +359,7 @@ int mcmcb200_hmc_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, co
     a.eps = st->step_size;
     if ((rc = stage_precond(s.scope.dev, s.stream, st->precond_mat, pr->n_dim, st->chol_mode, &a.S_cm, &a.Minv_cm, nullptr))) return rc;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
-    if ((rc = launch_hmc(a))) return rc;
+    if ((rc = wide ? launch_hmc_wide(a) : launch_hmc(a))) return rc;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
     if (out->n_leapfrog_out)
         for (long long c = 0; c < pr->n_chains; ++c) out->n_leapfrog_out[c] = (st->n_burnin_draws + st->n_keep_draws) * st->n_leap_steps;

@@ -81,6 +81,9 @@ struct EvalLaunch {
 
 // each returns a cudaError_t-like status: 0 ok, MCMCB200_ERR_* otherwise (message via set_error)
 int launch_hmc(const HmcLaunch& a);
+// 4 warps per chain, 512 < n_dim <= 2048, separable targets, M = I (hmc_wide.cu)
+bool hmc_wide_supported(int target_id, int d, bool has_precond);
+int launch_hmc_wide(const HmcLaunch& a);
 int launch_mala(const MalaLaunch& a);
 // chain-batched path (mala_wide.cu): dense quadratic targets, M = I, n_dim <= 2048
 bool mala_wide_supported(int target_id, int d, bool has_precond);

@@ -185,10 +185,12 @@ template <int MODE> struct ChainRng {
         cursor = 0;
     }
 
-    // d standard normals into the lane-striped vector z (FT: d == 32*EPL, no padding slots)
+    // d standard normals into the lane-striped vector z (FT: d == 32*EPL, no padding slots).
+    // When several warps share a chain, each warp generates its own segment: q_base = first Box-Muller pair of the
+    // segment, seg_off = first element of the segment, d_total = n_dim of the chain (d is the segment's length).
     template <int EPL, bool FT>
     __device__ __forceinline__ void normals(const RngArgs& a, long long draw, int d, int lane, const double2* __restrict__ tab,
-                                            double (&z)[EPL])
+                                            double (&z)[EPL], int q_base = 0, int seg_off = 0, int d_total = -1)
     {
         if (MODE == RNG_PHILOX) {
             constexpr int NPAIR = EPL / 2;
@@ -203,7 +205,7 @@ template <int MODE> struct ChainRng {
                     for (int i = 0; i < 2; ++i) {
                         const int q = (m0 + i) * 32 + lane;
                         unsigned r[4];
-                        philox4x32_10(static_cast<unsigned>(q), static_cast<unsigned>(draw + 1), chain, 0u, a, r);
+                        philox4x32_10(static_cast<unsigned>(q_base + q), static_cast<unsigned>(draw + 1), chain, 0u, a, r);
                         if (m0 + i == 0) spare = ((r[1] & 0xfffu) << 12) | (r[3] & 0xfffu);
                         b[i].setup(r, tab);
                     }
@@ -219,7 +221,7 @@ template <int MODE> struct ChainRng {
                     double z0[1], z1[1];
                     const int q = m0 * 32 + lane;
                     unsigned r[4];
-                    philox4x32_10(static_cast<unsigned>(q), static_cast<unsigned>(draw + 1), chain, 0u, a, r);
+                    philox4x32_10(static_cast<unsigned>(q_base + q), static_cast<unsigned>(draw + 1), chain, 0u, a, r);
                     if (m0 == 0) spare = ((r[1] & 0xfffu) << 12) | (r[3] & 0xfffu);
                     b[0].setup(r, tab);
                     bm_eval<1>(b, z0, z1);
@@ -228,13 +230,13 @@ template <int MODE> struct ChainRng {
                 }
             }
         } else {
-            const double* t = tape + cursor;
+            const double* t = tape + cursor + seg_off;
 #pragma unroll
             for (int k = 0; k < EPL; ++k) {
                 const int j = elem_index(lane, k);
                 z[k] = (j < d) ? t[j] : 0.0;
             }
-            cursor += d;
+            cursor += (d_total < 0) ? d : d_total;
         }
     }
 

@@ -22,6 +22,8 @@ namespace mcmcb200
 // log pi = -1/2 |x|^2                       (SURVEY §8d C1/C2 target)
 struct IsoGauss {
     static constexpr bool needs_scratch = false;
+    static constexpr bool separable = true;         // log pi is a sum over elements: a chain may be split across warps
+    static constexpr bool per_element_data = false;
     template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double*, const WarpCtx&, const double (&x)[EPL], double (&g)[EPL])
     {
@@ -40,6 +42,8 @@ struct IsoGauss {
 // log pi = -1/2 sum_i w_i x_i^2, data = w[d]
 struct DiagGauss {
     static constexpr bool needs_scratch = false;
+    static constexpr bool separable = true;
+    static constexpr bool per_element_data = true;  // data[j] belongs to element j
     template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
@@ -66,6 +70,8 @@ struct DiagGauss {
 // log pi = -1/2 x' P x, data = P[d*d] symmetric          (SURVEY §8d C4 target; functor data = Sigma^-1)
 struct DenseGauss {
     static constexpr bool needs_scratch = true;
+    static constexpr bool separable = false;
+    static constexpr bool per_element_data = false;
     template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
@@ -89,6 +95,8 @@ struct DenseGauss {
 // (SURVEY §8d C3 target; grad = b - A t)
 struct LinReg {
     static constexpr bool needs_scratch = true;
+    static constexpr bool separable = false;
+    static constexpr bool per_element_data = false;
     template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
@@ -120,6 +128,8 @@ struct LinReg {
 // statistics data = {n, xbar, M2 = sum (x_k - xbar)^2}:  sum (x_k - mu)^2 = M2 + n (xbar - mu)^2.
 struct NormalModel {
     static constexpr bool needs_scratch = false;
+    static constexpr bool separable = false;
+    static constexpr bool per_element_data = false;
     template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
     static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])

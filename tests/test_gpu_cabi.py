@@ -16,7 +16,7 @@ def test_error_codes(engine):
         engine.hmc(np.zeros((2, 8)), "diag_gauss", n_burnin=1, n_keep=1)  # data blob missing
     assert e.value.code == api.ERR_INVALID_ARG
     with pytest.raises(engine.McmcB200Error) as e:
-        engine.hmc(np.zeros((2, 600)), "iso_gauss", n_burnin=1, n_keep=1)  # beyond the register-resident kernels
+        engine.hmc(np.zeros((2, 2100)), "iso_gauss", n_burnin=1, n_keep=1)  # beyond every HMC kernel (max 2048)
     assert e.value.code == api.ERR_UNSUPPORTED
     with pytest.raises(engine.McmcB200Error) as e:
         engine.hmc(np.zeros((2, 4)), "iso_gauss", n_burnin=1, n_keep=1, precond_mat=-np.eye(4))

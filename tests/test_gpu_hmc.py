@@ -215,3 +215,29 @@ def test_full_size_c2_properties(engine):
     assert np.abs(v - 1).max() < 0.03, np.abs(v - 1).max()
     # chains must be distinct (different Philox substreams)
     assert np.abs(dr[0, -1] - dr[1, -1]).max() > 1e-3
+
+
+@pytest.mark.parametrize("d", [514, 600, 1024, 1500, 2048])
+def test_wide_hmc_four_warps_per_chain(engine, oracle, d):
+    """512 < n_dim <= 2048 (BASELINE config 5's dimension sweep): one CTA of four warps per chain (hmc_wide.cu).
+    The chain-wide reduction order differs from the oracle's, so STRICT is held to the contract tolerance."""
+    C = 3
+    rng = np.random.default_rng(d)
+    x0 = rng.normal(size=(C, d))
+    eps = 0.7 / d ** 0.25
+    st = ol.Settings(n_burnin=3, n_keep=15, n_leap_steps=6, step_size=eps)
+    for tname, tid, td in (("iso_gauss", ol.TGT_ISO_GAUSS, None), ("diag_gauss", ol.TGT_DIAG_GAUSS, np.linspace(0.5, 1.5, d))):
+        od, oa, olp = _oracle_chains(oracle, ol.HMC, tid, td, x0, st, 55, ol.RNG_MT, ol.SUM_WARP)
+        for a in (engine.api.ARITH_STRICT, engine.api.ARITH_FAST):
+            r = engine.hmc(x0, tname, target_data=td, n_leap_steps=6, step_size=eps, n_burnin=3, n_keep=15,
+                           rng_mode=engine.api.RNG_MT19937_TAPE, seed=55, arith=a, want_logp=True)
+            assert np.abs(r["draws"] - od).max() <= TOL, (tname, a)
+            assert np.abs(r["logp"] - olp).max() <= 1e-9 * np.abs(olp).max()
+            assert np.array_equal(r["n_accept"], oa)
+        od, oa, _ = _oracle_chains(oracle, ol.HMC, tid, td, x0, st, 56, ol.RNG_PHILOX, ol.SUM_WARP, chain_offset=9)
+        r = engine.hmc(x0, tname, target_data=td, n_leap_steps=6, step_size=eps, n_burnin=3, n_keep=15,
+                       rng_mode=engine.api.RNG_PHILOX, seed=56, chain_offset=9)
+        assert np.abs(r["draws"] - od).max() <= TOL and np.array_equal(r["n_accept"], oa)
+    assert 0 < oa.max()
+    with pytest.raises(engine.McmcB200Error):  # dense targets are not separable across warps
+        engine.hmc(np.zeros((2, d)), "dense_gauss", target_data=np.eye(d), n_burnin=1, n_keep=1)
