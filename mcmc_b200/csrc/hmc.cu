@@ -47,7 +47,9 @@ template <int EPL, bool STRICT> __device__ __forceinline__ void kick_full(double
 constexpr int hmc_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 4 : 2); }
 
 // FT ("full tile"): n_dim == 32*EPL and 16-byte aligned rows, so no padding predicates anywhere.
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT>
+// LS: number of leapfrog steps fixed at compile time (0 = runtime a.n_leap).  With LS > 0 the whole draw is straight-line
+// code, so ptxas interleaves the next Box-Muller polynomial chains, the Philox rounds and the leapfrog DFMAs freely.
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_kernel(const __grid_constant__ HmcLaunch a)
 {
     extern __shared__ double smem[];
@@ -83,13 +85,38 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     const int n_burnin = (int)a.n_burnin;
     const double eps = a.eps;
     const double heps = 0.5 * eps;
-    const int L = a.n_leap;
+    const int L = LS ? LS : a.n_leap;
     double* out_row = a.draws + chain * a.n_keep * d;
     double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
 
+    // Software pipelining (compile-time-L Philox kernels only): the variates of draw t+1 are generated in the same
+    // straight-line block as the trajectory of draw t — they do not depend on the chain state, so the integer Philox
+    // rounds and the Box-Muller chains fill the issue slots left by the dependent leapfrog DFMAs.
+    constexpr bool PIPE = (LS > 0) && (RNGM == RNG_PHILOX) && !DENSE_M;
+    double zn[PIPE ? EPL : 1];
+    double un = 0.0;
+    if (PIPE) {
+        double ztmp[EPL];
+        rng.template normals<EPL, FT>(a.rng, 0, d, lane, log_tab, ztmp);
+        un = rng.uniform(a.rng, 0, 0);
+#pragma unroll
+        for (int k = 0; k < (PIPE ? EPL : 1); ++k) zn[k] = ztmp[k];
+    }
+
     for (int t = 0; t < n_total; ++t) {
         // ---- momentum refresh: p = sqrtM z, K0 = p.(M^-1 p)/2 (lane partial in FAST) ----
-        rng.template normals<EPL, FT>(a.rng, t, d, lane, log_tab, p);
+        double u_pipe = un;
+        if (PIPE) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) p[k] = zn[k < (PIPE ? EPL : 1) ? k : 0];
+            double ztmp[EPL];
+            rng.template normals<EPL, FT>(a.rng, t + 1, d, lane, log_tab, ztmp);   // one spare draw past the end: harmless
+            un = rng.uniform(a.rng, t + 1, 0);
+#pragma unroll
+            for (int k = 0; k < (PIPE ? EPL : 1); ++k) zn[k] = ztmp[k];
+        } else {
+            rng.template normals<EPL, FT>(a.rng, t, d, lane, log_tab, p);
+        }
         double K0;
         if (DENSE_M) {
             double tmp[EPL];
@@ -112,7 +139,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             else store_vec<EPL>(bscr, d, lane, x);
             T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
             kick_half<EPL, STRICT>(p, g, eps, heps);
-            for (int s = 0; s < L; ++s) {
+            auto step = [&](int s) {
                 if (DENSE_M) {
                     double tmp[EPL];
                     stage_vec<EPL>(mscr, d, lane, p);
@@ -127,6 +154,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
                     T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
                     kick_full<EPL, STRICT>(p, g, eps);  // end of step s and start of step s+1 share this gradient
                 }
+            };
+            if (LS > 0) {
+#pragma unroll
+                for (int s = 0; s < LS; ++s) step(s);
+            } else {
+                for (int s = 0; s < L; ++s) step(s);
             }
             U1 = -T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, x, g);  // value-only call of :178 fused in
             kick_half<EPL, STRICT>(p, g, eps, heps);
@@ -145,7 +178,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
         }
 
         // ---- Metropolis test ----
-        const double u = rng.uniform(a.rng, t, 0);
+        const double u = PIPE ? u_pipe : rng.uniform(a.rng, t, 0);
         bool acc;
         if (STRICT) {
             // the reference's expression, evaluated literally (src/hmc.cpp:180-191)
@@ -181,12 +214,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT> static int launch_one(const HmcLaunch& a)
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0> static int launch_one(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (size_t)WARPS_PER_BLOCK * ((T::needs_scratch || DENSE_M) ? 3 : 1) * dpad * sizeof(double);
-    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT>;
+    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT, LS>;
     if (smem > 40 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -198,8 +231,12 @@ template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch
     if (a.rng.mode == RNG_PHILOX) {
         // the unpredicated full-tile kernels exist for the production configuration: Philox, identity mass
         const bool ft = !DENSE_M && a.d == 32 * EPL && ((reinterpret_cast<uintptr_t>(a.x0) | reinterpret_cast<uintptr_t>(a.draws)) & 15) == 0;
-        if (!DENSE_M && ft)
-            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
+        if (!DENSE_M && ft) {
+            if (a.strict) return launch_one<T, EPL, false, true, RNG_PHILOX, true>(a);
+            // the most common trajectory lengths get fully unrolled, software-pipelined kernels
+            if (a.n_leap == 10) return launch_one<T, EPL, false, false, RNG_PHILOX, true, 10>(a);
+            return launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
+        }
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, false>(a);
     }
     return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE, false>(a);

@@ -1,0 +1,29 @@
+"""Timing of the non-headline BASELINE configs on one GPU (kernel time from CUDA events inside the library)."""
+import sys, os, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+import mcmc_b200
+from mcmc_b200 import api
+which = sys.argv[1:] or ["c4", "c3", "sweep"]
+if "c4" in which:
+    rng = np.random.default_rng(11)
+    d = 256
+    q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.logspace(0, 3, d)
+    P = (q / lam) @ q.T; P = (P + P.T) / 2
+    for C in (512, 4096):
+        x0 = rng.normal(size=(C, d))
+        t0 = time.time()
+        r = mcmc_b200.nuts(x0, "dense_gauss", target_data=P, n_burnin=200, n_keep=200, n_adapt_draws=200, rng_mode=api.RNG_PHILOX, seed=5)
+        nlf = r["n_leapfrog"].sum()
+        print("C4 NUTS d=256 dense cond 1e3: %d chains x 400 draws: kernel %.1f ms, %.3e draws/s, %.3e leapfrogs/s (%.1f leapfrogs/draw), eps=%.3f, wall %.1fs"
+              % (C, r["kernel_ms"], C * 400 / r["kernel_ms"] * 1e3, nlf / r["kernel_ms"] * 1e3, nlf / (C * 400), r["step_size"].mean(), time.time() - t0))
+if "sweep" in which:
+    for d in (32, 128, 512, 2048):
+        C = 4096
+        x0 = np.sin(0.37 * np.arange(C)[:, None] + 0.11 * np.arange(d)[None, :])
+        r = mcmc_b200.hmc(x0, "iso_gauss", n_leap_steps=10, step_size=0.1 * (128 / d) ** 0.25, n_burnin=100, n_keep=200, rng_mode=api.RNG_PHILOX, seed=1)
+        ms = r["kernel_ms"]
+        print("HMC iso d=%d: 4096 chains x 300 draws: kernel %.2f ms, %.3e draws/s, %.1f GB/s algorithmic (2*d*8 B/draw), acc %.3f"
+              % (d, ms, C * 300 / ms * 1e3, C * 300 * 2 * d * 8 / ms * 1e-6, r["n_accept"].mean() / 200))
