@@ -99,8 +99,10 @@ typedef struct mcmcb200_problem {
     int32_t broadcast_initial;
     int64_t chain_offset;       /* global index of chain 0 of this call (multi-GPU sharding) */
     int32_t device;             /* CUDA device ordinal; -1 = current device */
-    int32_t reserved0;
+    int32_t vals_bound;         /* algo_settings_t::vals_bound (mcmc_structs.hpp:159): box constraints on          */
     void* stream;               /* cudaStream_t to launch on (NULL = default stream) */
+    const double* lower_bounds; /* HOST, n_dim entries, -inf = no lower bound (mcmc_structs.hpp:161-162,            */
+    const double* upper_bounds; /* HOST, n_dim entries, +inf = no upper bound  determine_bounds_type.hpp:39-50)     */
 } mcmcb200_problem_t;
 
 typedef struct mcmcb200_rng {

@@ -27,8 +27,10 @@
 //     the default for drop-in parity; MCMCB200_RNG_PHILOX is the in-kernel production generator), arithmetic mode,
 //     device ordinal.
 //
-// Unsupported reference features fail loudly: vals_bound = true (box constraints) makes the call
-// return false with mcmc::last_error() set; it is never silently ignored and nothing is computed on the host.
+// Box constraints (vals_bound / lower_bounds / upper_bounds, +-inf = open side) run on the device path for M = I
+// (HMC, NUTS, MALA) and for RM-HMC.  Unsupported combinations fail loudly: bounds together with a precond_mat, or on
+// the wide (n_vals > 512) kernels, make the call return false with mcmc::last_error() set; nothing is ever silently
+// ignored and nothing is computed on the host.
 //
 // Vector / matrix types: with MCMC_ENABLE_EIGEN_WRAPPERS or MCMC_ENABLE_ARMA_WRAPPERS defined (as for the reference)
 // the Eigen / Armadillo types are used; otherwise a minimal column-major ColVec_t / Mat_t pair is provided.
@@ -276,14 +278,19 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
     algo_settings_t local;
     algo_settings_t& s = sp ? *sp : local;
     wrapper_error().clear();
-    if (s.vals_bound) {
-        // box constraints are not on the device path yet: refuse rather than sample the wrong (unbounded) target
-        wrapper_error() = "mcmc_b200: vals_bound = true (box constraints) is not supported by the device path";
+    if (s.vals_bound && (vsize(s.lower_bounds) != d || vsize(s.upper_bounds) != d)) {
+        // the reference reads n_vals entries of both vectors (determine_bounds_type.hpp:27-57); a short vector is UB there
+        wrapper_error() = "mcmc_b200: vals_bound = true needs lower_bounds and upper_bounds of length n_vals";
         return false;
     }
     mcmcb200_problem_t pr;
     mcmcb200_rng_t rng;
     fill_problem(pr, rng, x0, d, n_chains, k, target_data, s, rng_mode);
+    if (s.vals_bound) {
+        pr.vals_bound = 1;
+        pr.lower_bounds = cdata(s.lower_bounds);
+        pr.upper_bounds = cdata(s.upper_bounds);
+    }
     std::vector<fp_t> buf(n_chains * n_keep * d);
     std::vector<int64_t> acc(n_chains, 0);
     mcmcb200_output_t out;

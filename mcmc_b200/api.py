@@ -28,8 +28,8 @@ c_i32, c_i64, c_u64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint
 class Problem(ctypes.Structure):
     _fields_ = [("n_chains", c_i64), ("n_dim", c_i32), ("target_id", c_i32), ("target_data", c_vp),
                 ("target_data_len", c_i64), ("initial_vals", c_vp), ("initial_mem", c_i32),
-                ("broadcast_initial", c_i32), ("chain_offset", c_i64), ("device", c_i32), ("reserved0", c_i32),
-                ("stream", c_vp)]
+                ("broadcast_initial", c_i32), ("chain_offset", c_i64), ("device", c_i32), ("vals_bound", c_i32),
+                ("stream", c_vp), ("lower_bounds", c_vp), ("upper_bounds", c_vp)]
 
 
 class Rng(ctypes.Structure):
@@ -118,7 +118,7 @@ class _Run:
 
     def __init__(self, sampler, initial_vals, target, target_data, n_keep, n_burnin, rng_mode, seed, chain_offset,
                  device, stream, tape, draws_out, want_logp, initial_dev_ptr=None, n_chains=None, n_dim=None,
-                 draws_dev_ptr=None):
+                 draws_dev_ptr=None, lower_bounds=None, upper_bounds=None):
         lib = load()
         self.lib = lib
         self.keep = []
@@ -140,8 +140,15 @@ class _Run:
         td = np.ascontiguousarray(target_data if target_data is not None else [], dtype=np.float64).ravel()
         self.keep.append(td)
         self.C, self.d, self.n_keep = C, d, int(n_keep)
+        vb, lo, hi = 0, None, None
+        if lower_bounds is not None or upper_bounds is not None:
+            lo = np.full(d, -np.inf) if lower_bounds is None else np.ascontiguousarray(lower_bounds, dtype=np.float64)
+            hi = np.full(d, np.inf) if upper_bounds is None else np.ascontiguousarray(upper_bounds, dtype=np.float64)
+            assert lo.size == d and hi.size == d
+            self.keep += [lo, hi]
+            vb = 1
         self.problem = Problem(C, d, target_id(target), _np_ptr(td) if td.size else None, td.size, x0_ptr, x0_mem, bcast,
-                               int(chain_offset), int(device), 0, c_vp(stream) if stream else None)
+                               int(chain_offset), int(device), vb, c_vp(stream) if stream else None, _np_ptr(lo), _np_ptr(hi))
         tape_ptr, tape_stride, tape_mem = None, 0, MEM_HOST
         if rng_mode == RNG_USER_TAPE:
             tp = np.ascontiguousarray(tape, dtype=np.float64).reshape(C, -1)
@@ -173,7 +180,7 @@ class _Run:
 
 _COMMON = dict(target_data=None, n_burnin=1000, n_keep=1000, rng_mode=RNG_PHILOX, seed=0, chain_offset=0, device=-1,
                stream=None, tape=None, draws_out=None, want_logp=False, initial_dev_ptr=None, n_chains=None, n_dim=None,
-               draws_dev_ptr=None)
+               draws_dev_ptr=None, lower_bounds=None, upper_bounds=None)
 
 
 def _split(kw):

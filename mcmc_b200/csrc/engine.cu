@@ -36,7 +36,7 @@ int epl_for_dim(int d)
 }
 
 // ---- grow-only device scratch, per (device, slot) -----------------------------------------
-enum Slot { SLOT_TDATA = 0, SLOT_X0, SLOT_DRAWS, SLOT_LOGP, SLOT_NACC, SLOT_TAPE, SLOT_MAT_A, SLOT_MAT_B, SLOT_MAT_C,
+enum Slot { SLOT_TDATA = 0, SLOT_LB, SLOT_UB, SLOT_X0, SLOT_DRAWS, SLOT_LOGP, SLOT_NACC, SLOT_TAPE, SLOT_MAT_A, SLOT_MAT_B, SLOT_MAT_C,
             SLOT_STEP, SLOT_NLF, SLOT_WORK, SLOT_EVAL_X, SLOT_EVAL_V, SLOT_EVAL_G, SLOT_COUNT };
 constexpr int MAX_DEVICES = 16;
 struct Buf { void* p = nullptr; size_t bytes = 0; };
@@ -166,6 +166,17 @@ static int stage_common(Staged& s, const mcmcb200_problem_t* pr, const mcmcb200_
     s.n_keep = n_keep;
 
     if ((rc = upload(dev, SLOT_TDATA, pr->target_data, (size_t)need, st, &c.tdata))) return rc;
+    c.lb = c.ub = nullptr;
+    if (pr->vals_bound) {
+        if (!pr->lower_bounds || !pr->upper_bounds) { set_error("vals_bound is set but lower_bounds / upper_bounds is null"); return MCMCB200_ERR_INVALID_ARG; }
+        for (int j = 0; j < d; ++j)
+            if (pr->lower_bounds[j] != pr->lower_bounds[j] || pr->upper_bounds[j] != pr->upper_bounds[j] || !(pr->lower_bounds[j] < pr->upper_bounds[j])) {
+                set_error("bounds of element %d are not ordered (lower < upper required)", j);
+                return MCMCB200_ERR_INVALID_ARG;
+            }
+        if ((rc = upload(dev, SLOT_LB, pr->lower_bounds, (size_t)d, st, &c.lb))) return rc;
+        if ((rc = upload(dev, SLOT_UB, pr->upper_bounds, (size_t)d, st, &c.ub))) return rc;
+    }
 
     const size_t n_x0 = (size_t)(c.broadcast_x0 ? 1 : pr->n_chains) * d;
     if (pr->initial_mem == MCMCB200_MEM_DEVICE) c.x0 = pr->initial_vals;
@@ -348,7 +359,7 @@ int mcmcb200_hmc_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, co
     if (!st) { set_error("null settings"); return MCMCB200_ERR_INVALID_ARG; }
     if (st->n_leap_steps < 0 || st->n_leap_steps > 0x7fffffff) { set_error("bad n_leap_steps"); return MCMCB200_ERR_INVALID_ARG; }
     Staged s;
-    const bool wide = pr && hmc_wide_supported(pr->target_id, pr->n_dim, st->precond_mat != nullptr);
+    const bool wide = pr && hmc_wide_supported(pr->target_id, pr->n_dim, st->precond_mat != nullptr) && !pr->vals_bound;
     int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out, wide ? 2048 : 32 * MAX_EPL);
     if (rc) return rc;
     HmcLaunch a;
@@ -375,7 +386,7 @@ int mcmcb200_mala_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, c
     Staged s;
     // dense quadratic targets with M = I run chain-batched (one fp64 tensor-core GEMM per draw for all chains) when the
     // dimension is beyond the register-resident kernels or there are enough chains to fill GEMM tiles
-    const bool wide_ok = pr && mala_wide_supported(pr->target_id, pr->n_dim, st->precond_mat != nullptr) && !pr->broadcast_initial;
+    const bool wide_ok = pr && mala_wide_supported(pr->target_id, pr->n_dim, st->precond_mat != nullptr) && !pr->broadcast_initial && !pr->vals_bound;
     const bool use_wide = wide_ok && (pr->n_dim > 32 * MAX_EPL || pr->n_chains >= 256);
     int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out, use_wide ? 2048 : 32 * MAX_EPL);
     if (rc) return rc;

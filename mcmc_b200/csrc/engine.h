@@ -29,6 +29,8 @@ struct CommonLaunch {
     long long* n_accept;    // [n_chains]
     cudaStream_t stream;
     bool strict;
+    const double* lb;       // box constraints (vals_bound): lower / upper bounds [d] on the device, or null
+    const double* ub;
 };
 
 struct HmcLaunch : CommonLaunch {

@@ -17,6 +17,7 @@
 #include "engine.h"
 #include "rng.cuh"
 #include "targets.cuh"
+#include "box.cuh"
 #include <math_constants.h>
 
 namespace mcmcb200
@@ -24,17 +25,25 @@ namespace mcmcb200
 
 // Half / full momentum kicks.  STRICT keeps the reference's rounding sequence p + (eps*g)/2 (a full kick is two
 // separately rounded half kicks, src/hmc.cpp:167,175); FAST fuses them.
-template <int EPL, bool STRICT> __device__ __forceinline__ void kick_half(double (&p)[EPL], const double (&g)[EPL], double eps, double heps)
-{
-#pragma unroll
-    for (int k = 0; k < EPL; ++k)
-        p[k] = STRICT ? Ar<STRICT>::add(p[k], Ar<STRICT>::mul(Ar<STRICT>::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
-}
-template <int EPL, bool STRICT> __device__ __forceinline__ void kick_full(double (&p)[EPL], const double (&g)[EPL], double eps)
+// With box constraints the force is J(v) (diagonal) times the raw gradient: p + ((eps*J)*grad)/2 (src/hmc.cpp:122).
+template <int EPL, bool STRICT, bool BOX>
+__device__ __forceinline__ void kick_half(double (&p)[EPL], const double (&g)[EPL], const double (&J)[EPL], double eps, double heps)
 {
 #pragma unroll
     for (int k = 0; k < EPL; ++k) {
-        if (STRICT) {
+        if (BOX) p[k] = Ar<STRICT>::add(p[k], Ar<STRICT>::mul(Ar<STRICT>::mul(J[k], Ar<STRICT>::mul(eps, g[k])), 0.5));
+        else p[k] = STRICT ? Ar<STRICT>::add(p[k], Ar<STRICT>::mul(Ar<STRICT>::mul(eps, g[k]), 0.5)) : fma(heps, g[k], p[k]);
+    }
+}
+template <int EPL, bool STRICT, bool BOX>
+__device__ __forceinline__ void kick_full(double (&p)[EPL], const double (&g)[EPL], const double (&J)[EPL], double eps)
+{
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+        if (BOX) {
+            const double hk = Ar<STRICT>::mul(Ar<STRICT>::mul(J[k], Ar<STRICT>::mul(eps, g[k])), 0.5);
+            p[k] = Ar<STRICT>::add(Ar<STRICT>::add(p[k], hk), hk);
+        } else if (STRICT) {
             const double hk = Ar<STRICT>::mul(Ar<STRICT>::mul(eps, g[k]), 0.5);
             p[k] = Ar<STRICT>::add(Ar<STRICT>::add(p[k], hk), hk);
         } else {
@@ -49,7 +58,8 @@ constexpr int hmc_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 4 : 2)
 // FT ("full tile"): n_dim == 32*EPL and 16-byte aligned rows, so no padding predicates anywhere.
 // LS: number of leapfrog steps fixed at compile time (0 = runtime a.n_leap).  With LS > 0 the whole draw is straight-line
 // code, so ptxas interleaves the next Box-Muller polynomial chains, the Philox rounds and the leapfrog DFMAs freely.
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0>
+// BOX: box constraints (vals_bound), see box.cuh; available with M = I on the generic (runtime-L) kernels.
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0, bool BOX = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_kernel(const __grid_constant__ HmcLaunch a)
 {
     extern __shared__ double smem[];
@@ -70,16 +80,22 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     double* mscr = tscr + dpad;                      // mass-matrix scratch
     const WarpCtx w{lane, d, tscr};
 
-    double x[EPL], p[EPL], g[EPL];
+    double x[EPL], p[EPL], g[EPL], Jr[EPL];  // Jr is dead (no registers) unless BOX
     if (FT) load_vec_full<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), lane, x);
     else load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
+    BoxLane<BOX ? EPL : 1> bx;
+    if (BOX) {
+        bx.load(a.lb, a.ub, d, lane);
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) x[k] = bx.transform(BOX ? k : 0, x[k]);   // first_draw = transform(initial_vals), src/hmc.cpp:132-136
+    }
 
     ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
 
     // U = -log pi(x): STRICT carries the reduced scalar (src/hmc.cpp:140); FAST carries this lane's partial sum,
     // so that one butterfly per draw reduces (U0 + K0) - (U1 + K1) directly.
-    double U = -T::template eval<EPL, STRICT, true, false, STRICT>(a.tdata, w, x, g);
+    double U = -box_eval<T, EPL, STRICT, BOX, true, false, STRICT>(a.tdata, w, bx, x, g, Jr);
     int n_acc = 0;
     const int n_total = (int)(a.n_burnin + a.n_keep);
     const int n_burnin = (int)a.n_burnin;
@@ -137,8 +153,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
         if (L > 0) {
             if (FT) store_vec_full<EPL>(bscr, lane, x);
             else store_vec<EPL>(bscr, d, lane, x);
-            T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
-            kick_half<EPL, STRICT>(p, g, eps, heps);
+            box_eval<T, EPL, STRICT, BOX, false, true, true>(a.tdata, w, bx, x, g, Jr);
+            kick_half<EPL, STRICT, BOX>(p, g, Jr, eps, heps);
             auto step = [&](int s) {
                 if (DENSE_M) {
                     double tmp[EPL];
@@ -151,8 +167,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
                     for (int k = 0; k < EPL; ++k) x[k] = A::mad(eps, p[k], x[k]);
                 }
                 if (s + 1 < L) {
-                    T::template eval<EPL, STRICT, false, true>(a.tdata, w, x, g);
-                    kick_full<EPL, STRICT>(p, g, eps);  // end of step s and start of step s+1 share this gradient
+                    box_eval<T, EPL, STRICT, BOX, false, true, true>(a.tdata, w, bx, x, g, Jr);
+                    kick_full<EPL, STRICT, BOX>(p, g, Jr, eps);  // end of step s and start of step s+1 share this gradient
                 }
             };
             if (LS > 0) {
@@ -161,8 +177,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             } else {
                 for (int s = 0; s < L; ++s) step(s);
             }
-            U1 = -T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, x, g);  // value-only call of :178 fused in
-            kick_half<EPL, STRICT>(p, g, eps, heps);
+            U1 = -box_eval<T, EPL, STRICT, BOX, true, true, STRICT>(a.tdata, w, bx, x, g, Jr);  // value-only call of :178 fused in
+            kick_half<EPL, STRICT, BOX>(p, g, Jr, eps, heps);
         } else {
             U1 = U;
         }
@@ -200,7 +216,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             else load_vec<EPL>(bscr, d, lane, x);
         }
         if (t >= n_burnin) {
-            if (FT) store_vec_full<EPL>(out_row, lane, x);
+            if (BOX) {   // draws_out rows are mapped back with inv_transform (src/hmc.cpp:211-218)
+                double xo[EPL];
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) xo[k] = bx.inv(BOX ? k : 0, x[k]);
+                store_vec<EPL>(out_row, d, lane, xo);
+            } else if (FT) store_vec_full<EPL>(out_row, lane, x);
             else store_vec<EPL>(out_row, d, lane, x);
             out_row += d;
             if (out_lp) {
@@ -214,12 +235,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0> static int launch_one(const HmcLaunch& a)
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0, bool BOX = false> static int launch_one(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (size_t)WARPS_PER_BLOCK * ((T::needs_scratch || DENSE_M) ? 3 : 1) * dpad * sizeof(double);
-    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT, LS>;
+    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT, LS, BOX>;
     if (smem > 40 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -228,6 +249,15 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch& a)
 {
+    if (a.lb != nullptr) {   // box constraints: generic kernels, M = I
+        if (DENSE_M) {
+            set_error("hmc: vals_bound together with precond_mat is not supported on the device path");
+            return MCMCB200_ERR_UNSUPPORTED;
+        }
+        if (a.rng.mode == RNG_PHILOX)
+            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, false, 0, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, false, 0, true>(a);
+        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, false, 0, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, false, 0, true>(a);
+    }
     if (a.rng.mode == RNG_PHILOX) {
         // the unpredicated full-tile kernels exist for the production configuration: Philox, identity mass
         const bool ft = !DENSE_M && a.d == 32 * EPL && ((reinterpret_cast<uintptr_t>(a.x0) | reinterpret_cast<uintptr_t>(a.draws)) & 15) == 0;

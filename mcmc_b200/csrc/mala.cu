@@ -17,6 +17,7 @@
 #include "engine.h"
 #include "rng.cuh"
 #include "targets.cuh"
+#include "box.cuh"
 #include <math_constants.h>
 
 namespace mcmcb200
@@ -24,7 +25,9 @@ namespace mcmcb200
 
 constexpr int mala_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 3 : 1); }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM>
+// BOX: box constraints with M = I (src/mala.cpp:104-118,152-157, mala.ipp:50-56): drift eps^2 J grad / 2, noise
+// eps sqrt(J) z, and BOTH proposal densities use the covariance eps^2 J(proposal).
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) mala_kernel(const __grid_constant__ MalaLaunch a)
 {
     extern __shared__ double smem[];
@@ -45,9 +48,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
     const double eps = a.eps;
     const double e2 = A::mul(eps, eps);  // step_size * step_size
 
-    // mean = v + ((eps^2 M) g)/2
-    auto mala_mean = [&](const double (&v)[EPL], const double (&g)[EPL], double (&out)[EPL]) {
-        if (DENSE_M) {
+    BoxLane<BOX ? EPL : 1> bx;
+    if (BOX) bx.load(a.lb, a.ub, d, lane);
+    // mean = v + ((eps^2 M) g)/2 ; bounded (M = I): v + ((J eps^2) g)/2
+    auto mala_mean = [&](const double (&v)[EPL], const double (&g)[EPL], const double (&Jv)[EPL], double (&out)[EPL]) {
+        if (BOX) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) out[k] = A::add(v[k], A::mul(A::mul(A::mul(Jv[k], e2), g[k]), 0.5));
+        } else if (DENSE_M) {
             double t[EPL];
             stage_vec<EPL>(mscr, d, lane, g);
             gemv_cm<EPL, STRICT>(a.M_cm, d, lane, mscr, e2, t);
@@ -58,8 +66,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
             for (int k = 0; k < EPL; ++k) out[k] = STRICT ? A::add(v[k], A::mul(A::mul(e2, g[k]), 0.5)) : fma(0.5 * e2, g[k], v[k]);
         }
     };
-    // lane partial of q(r) = r' Sigma^-1 r
-    auto quad_lane = [&](const double (&r)[EPL]) -> double {
+    // lane partial of q(r) = r' Sigma^-1 r ; bounded: Sigma = diag(J eps^2) with J at the proposal
+    auto quad_lane = [&](const double (&r)[EPL], const double (&Jp)[EPL]) -> double {
+        if (BOX) {
+            double t[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) t[k] = r[k] / A::mul(Jp[k], e2);
+            return lane_dot<EPL, STRICT>(r, t);
+        }
         if (DENSE_M) {
             double t[EPL];
             stage_vec<EPL>(mscr, d, lane, r);
@@ -69,14 +83,18 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
         return lane_dot<EPL, STRICT>(r, r);
     };
 
-    double x[EPL], mx[EPL], y[EPL], my[EPL], g[EPL], r[EPL];
+    double x[EPL], mx[EPL], y[EPL], my[EPL], g[EPL], r[EPL], Jx[EPL], Jy[EPL];   // Jx, Jy dead unless BOX
     load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
+    if (BOX) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) x[k] = bx.transform(BOX ? k : 0, x[k]);
+    }
     ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
 
     // LP: STRICT carries the reduced scalar, FAST the lane partial (see hmc.cu)
-    double LP = T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, x, g);  // src/mala.cpp:138
-    mala_mean(x, g, mx);
+    double LP = box_eval<T, EPL, STRICT, BOX, true, true, STRICT>(a.tdata, w, bx, x, g, Jx);  // src/mala.cpp:138
+    mala_mean(x, g, Jx, mx);
     int n_acc = 0;
     const int n_total = (int)(a.n_burnin + a.n_keep);
     const int n_burnin = (int)a.n_burnin;
@@ -85,7 +103,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
 
     for (int t = 0; t < n_total; ++t) {
         rng.template normals<EPL, false>(a.rng, t, d, lane, rng_tab, r);  // z
-        if (DENSE_M) {
+        if (BOX) {   // mean + ((eps chol(J)) sqrtM) z with chol of the diagonal J = sqrt(J_ii), sqrtM = I
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) y[k] = A::mad(A::mul(sqrt(Jx[k]), eps), r[k], mx[k]);
+        } else if (DENSE_M) {
             double tz[EPL];
             stage_vec<EPL>(mscr, d, lane, r);
             gemv_cm<EPL, STRICT>(a.S_cm, d, lane, mscr, eps, tz);  // (eps sqrtM) z
@@ -95,23 +116,23 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
 #pragma unroll
             for (int k = 0; k < EPL; ++k) y[k] = A::mad(eps, r[k], mx[k]);
         }
-        double LP1 = T::template eval<EPL, STRICT, true, true, STRICT>(a.tdata, w, y, g);
-        mala_mean(y, g, my);
+        double LP1 = box_eval<T, EPL, STRICT, BOX, true, true, STRICT>(a.tdata, w, bx, y, g, Jy);
+        mala_mean(y, g, Jy, my);
 
         // q1 = q(x - mu(y)), q2 = q(y - mu(x))
 #pragma unroll
         for (int k = 0; k < EPL; ++k) r[k] = A::sub(x[k], my[k]);
-        double q1 = quad_lane(r);
+        double q1 = quad_lane(r, Jy);
 #pragma unroll
         for (int k = 0; k < EPL; ++k) r[k] = A::sub(y[k], mx[k]);
-        double q2 = quad_lane(r);
+        double q2 = quad_lane(r, Jy);
 
         const double u = rng.uniform(a.rng, t, 0);
         bool acc;
         if (STRICT) {
             q1 = warp_sum<true>(q1);
             q2 = warp_sum<true>(q2);
-            if (!DENSE_M) {  // Sigma^-1 = I / eps^2
+            if (!DENSE_M && !BOX) {  // Sigma^-1 = I / eps^2
                 q1 = q1 / e2;
                 q2 = q2 / e2;
             }
@@ -120,7 +141,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
             const double comp = fmin(0.01, A::add(A::sub(LP1, LP), adj));      // :170
             acc = u < exp(comp);
         } else {
-            const double qs = DENSE_M ? 1.0 : 1.0 / e2;
+            const double qs = (DENSE_M || BOX) ? 1.0 : 1.0 / e2;
             const double dl = warp_sum<false>((LP1 - LP) - 0.5 * qs * (q1 - q2));
             acc = false;
             if (fabs(dl) <= 1.7976931348623157e308) acc = (u < 1.0 + dl) ? true : (u < exp(dl));
@@ -131,9 +152,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
             for (int k = 0; k < EPL; ++k) {
                 x[k] = y[k];
                 mx[k] = my[k];
+                if (BOX) Jx[k] = Jy[k];
             }
         }
         if (t >= n_burnin) {
+            if (BOX) {   // src/mala.cpp:192-199
+                double xo[EPL];
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) xo[k] = bx.inv(BOX ? k : 0, x[k]);
+                store_vec<EPL>(out_row, d, lane, xo);
+            } else
             store_vec<EPL>(out_row, d, lane, x);
             out_row += d;
             if (out_lp) {
@@ -147,12 +175,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
     if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int launch_one(const MalaLaunch& a)
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false> static int launch_one(const MalaLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dpad * sizeof(double) : 0;
-    auto kern = mala_kernel<T, EPL, DENSE_M, STRICT, RNGM>;
+    auto kern = mala_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX>;
     if (smem > 32 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -161,6 +189,15 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int laun
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const MalaLaunch& a)
 {
+    if (a.lb != nullptr) {   // box constraints: M = I only (a dense M would need an O(d^3) factorisation of J M per draw)
+        if (DENSE_M) {
+            set_error("mala: vals_bound together with precond_mat is not supported on the device path");
+            return MCMCB200_ERR_UNSUPPORTED;
+        }
+        if (a.rng.mode == RNG_PHILOX)
+            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
+        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, true>(a);
+    }
     if (a.rng.mode == RNG_PHILOX)
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
     return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE>(a);

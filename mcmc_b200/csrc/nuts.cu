@@ -19,6 +19,7 @@
 #include "engine.h"
 #include "rng.cuh"
 #include "targets.cuh"
+#include "box.cuh"
 #include <math_constants.h>
 
 namespace mcmcb200
@@ -47,7 +48,7 @@ struct NutsStack {  // per-warp recursion stack (shared memory)
 
 constexpr int nuts_min_blocks(int epl) { return epl <= 4 ? 4 : (epl == 8 ? 2 : 1); }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM>
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nuts_kernel(const __grid_constant__ NutsLaunch a)
 {
     extern __shared__ double smem[];
@@ -103,9 +104,19 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
     // one leapfrog step of (signed) size e; g holds grad log pi(x) on entry and on exit; returns log pi(new x)
     // (src/nuts.cpp:139-154: half kick, drift with (e M^-1) p, half kick — two gradient calls of which the first
     //  repeats the previous step's last one)
-    auto leapfrog = [&](double e, double (&x)[EPL], double (&p)[EPL], double (&g)[EPL]) -> double {
+    BoxLane<BOX ? EPL : 1> bx;
+    if (BOX) bx.load(a.lb, a.ub, d, lane);
+    double Jt[EPL];   // diagonal J(v) belonging to the gradient in gt (dead unless BOX)
+    // half kick p + ((e*J)*grad)/2 (src/nuts.cpp:111-126); J only with box constraints
+    auto kick = [&](double e, double (&p)[EPL], const double (&g)[EPL]) {
 #pragma unroll
-        for (int k = 0; k < EPL; ++k) p[k] = STRICT ? A::add(p[k], A::mul(A::mul(e, g[k]), 0.5)) : fma(0.5 * e, g[k], p[k]);
+        for (int k = 0; k < EPL; ++k) {
+            if (BOX) p[k] = A::add(p[k], A::mul(A::mul(Jt[k], A::mul(e, g[k])), 0.5));
+            else p[k] = STRICT ? A::add(p[k], A::mul(A::mul(e, g[k]), 0.5)) : fma(0.5 * e, g[k], p[k]);
+        }
+    };
+    auto leapfrog = [&](double e, double (&x)[EPL], double (&p)[EPL], double (&g)[EPL]) -> double {
+        kick(e, p, g);
         if (DENSE_M) {
             double t[EPL];
             stage_vec<EPL>(mscr, d, lane, p);
@@ -116,9 +127,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
 #pragma unroll
             for (int k = 0; k < EPL; ++k) x[k] = A::mad(e, p[k], x[k]);
         }
-        const double lp = T::template eval<EPL, STRICT, true, true>(a.tdata, w, x, g);
-#pragma unroll
-        for (int k = 0; k < EPL; ++k) p[k] = STRICT ? A::add(p[k], A::mul(A::mul(e, g[k]), 0.5)) : fma(0.5 * e, g[k], p[k]);
+        const double lp = box_eval<T, EPL, STRICT, BOX, true, true, true>(a.tdata, w, bx, x, g, Jt);
+        kick(e, p, g);
         return lp;
     };
     auto neg_logp_finite = [](double lp) -> double {
@@ -128,6 +138,10 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
 
     double x[EPL], xt[EPL], rt[EPL], gt[EPL];
     load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
+    if (BOX) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) x[k] = bx.transform(BOX ? k : 0, x[k]);   // src/nuts.cpp:158-162
+    }
     ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
     long long n_lf = 0;
@@ -137,7 +151,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
     momentum(rt);
     double eps = 1.0;
     {
-        const double pU = neg_logp_finite(T::template eval<EPL, STRICT, true, true>(a.tdata, w, x, gt));
+        const double pU = neg_logp_finite(box_eval<T, EPL, STRICT, BOX, true, true, true>(a.tdata, w, bx, x, gt, Jt));
         const double pK = kinetic(rt);
 #pragma unroll
         for (int k = 0; k < EPL; ++k) xt[k] = x[k];
@@ -160,7 +174,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
     const double mu = log(10.0 * eps);  // src/nuts.cpp:174
     double h = 0.0;
     double eps_bar = a.eps_bar0;
-    double prev_U = -T::template eval<EPL, STRICT, true, false>(a.tdata, w, x, gt);  // :181 (no finite clamp here)
+    double prev_U = -box_eval<T, EPL, STRICT, BOX, true, false, true>(a.tdata, w, bx, x, gt, Jt);  // :181 (no finite clamp here)
     store_vec<EPL>(Wprev, d, lane, x);
 
     int n_acc = 0;
@@ -197,7 +211,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
 #pragma unroll
             for (int k = 0; k < EPL; ++k) xt[k] = x[k];
             load_vec<EPL>(Wm, d, lane, rt);
-            T::template eval<EPL, STRICT, false, true>(a.tdata, w, xt, gt);
+            box_eval<T, EPL, STRICT, BOX, false, true, true>(a.tdata, w, bx, xt, gt, Jt);
 
             // ---- T(depth, 0) with an explicit stack ----
             int R_sel = 0, R_s = 0, R_nalpha = 0, R_far = 0;
@@ -318,7 +332,14 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
             eps = eps_bar;
         }
         if (t >= n_burnin) {
-            store_vec<EPL>(out_row, d, lane, x);
+            if (BOX) {   // src/nuts.cpp:316-323
+                double xo[EPL];
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) xo[k] = bx.inv(BOX ? k : 0, x[k]);
+                store_vec<EPL>(out_row, d, lane, xo);
+            } else {
+                store_vec<EPL>(out_row, d, lane, x);
+            }
             out_row += d;
             if (out_lp) {
                 if (lane == 0) *out_lp = -prev_U;
@@ -334,7 +355,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
     }
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int launch_one(const NutsLaunch& a)
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false> static int launch_one(const NutsLaunch& a)
 {
     if (a.max_depth + 1 > NUTS_MAX_LEVELS) {
         set_error("nuts: max_tree_depth %d exceeds %d", a.max_depth, NUTS_MAX_LEVELS - 1);
@@ -343,7 +364,7 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int laun
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dp = (a.d + 1) & ~1;
     const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dp * sizeof(double) : 0;
-    auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM>;
+    auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX>;
     if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -352,6 +373,15 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM> static int laun
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const NutsLaunch& a)
 {
+    if (a.lb != nullptr) {   // box constraints: M = I only
+        if (DENSE_M) {
+            set_error("nuts: vals_bound together with precond_mat is not supported on the device path");
+            return MCMCB200_ERR_UNSUPPORTED;
+        }
+        if (a.rng.mode == RNG_PHILOX)
+            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
+        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, true>(a);
+    }
     if (a.rng.mode == RNG_PHILOX)
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
     return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE>(a);

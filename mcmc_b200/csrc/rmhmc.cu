@@ -15,6 +15,7 @@
 // funnel (BASELINE config 5) is not built yet ("what comes next").
 #include "engine.h"
 #include "rng.cuh"
+#include "box.cuh"
 #include <math_constants.h>
 
 namespace mcmcb200
@@ -192,7 +193,9 @@ template <bool STRICT> struct NormalModelRM {
     }
 };
 
-template <class TM, bool STRICT, int RNGM>
+// BOX: box constraints (src/rmhmc.cpp:99-168,278-285): the chain runs in the transformed space, log pi gets the
+// log-Jacobian, the metric is evaluated at inv_transform(v) and the momentum update is scaled by the diagonal J (Q9).
+template <class TM, bool STRICT, int RNGM, bool BOX = false>
 __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ RmhmcLaunch a)
 {
     constexpr int D = TM::D;
@@ -240,11 +243,35 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ Rmhm
         return tape[cursor++];
     };
 
+    BoxLane<BOX ? D : 1> bx;
+    if (BOX) bx.load_seq(a.lb, a.ub, D);
+    auto to_x = [&](const double (&v)[D], double (&x)[D]) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[i] = BOX ? bx.inv(BOX ? i : 0, v[i]) : v[i];
+    };
+    // log pi in the sampler's space: log pi(inv(v)) + log_jacobian(v)
+    auto logp_v = [&](const double (&v)[D]) -> double {
+        if (!BOX) return TM::logp(a.tdata, v, nullptr);
+        double x[D];
+        to_x(v, x);
+        double lj = 0.0;
+#pragma unroll
+        for (int i = 0; i < D; ++i) lj = A::add(lj, bx.logjac(BOX ? i : 0, v[i]));
+        return A::add(TM::logp(a.tdata, x, nullptr), lj);
+    };
+    auto metric_v = [&](const double (&v)[D], double (&G)[D * D], double (*dG)[D * D]) {
+        if (!BOX) { TM::metric(a.tdata, v, G, dG); return; }
+        double x[D];
+        to_x(v, x);
+        TM::metric(a.tdata, x, G, dG);
+    };
+
     // returns (eps * F)/2, F_i = -grad_i + 1/2 (tr(Ainv dG_i) - ((Ainv dG_i)' q).(Ainv q))   (src/rmhmc.cpp:132-146, Q16)
     auto mntm_update = [&](const double (&y)[D], const double (&q)[D], const double (&Ainv)[D * D], const double (&dG)[D][D * D],
                            double (&out)[D]) {
-        double g[D], Aq[D];
-        TM::logp(a.tdata, y, g);
+        double g[D], Aq[D], yx[D];
+        to_x(y, yx);
+        TM::logp(a.tdata, yx, g);
         LA::gemv(Ainv, q, Aq);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
@@ -262,17 +289,21 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ Rmhm
             g[i] = A::add(-g[i], A::mul(0.5, A::sub(tr, dp)));
         }
 #pragma unroll
-        for (int i = 0; i < D; ++i) out[i] = A::mul(A::mul(a.eps, g[i]), 0.5);
+        for (int i = 0; i < D; ++i)
+            out[i] = BOX ? A::mul(A::mul(bx.invjac(BOX ? i : 0, y[i]), A::mul(a.eps, g[i])), 0.5) : A::mul(A::mul(a.eps, g[i]), 0.5);
     };
 
     double prev[D], cur[D], p[D], z[D];
 #pragma unroll
-    for (int i = 0; i < D; ++i) prev[i] = a.x0[(a.broadcast_x0 ? 0 : chain * D) + i];
+    for (int i = 0; i < D; ++i) {
+        prev[i] = a.x0[(a.broadcast_x0 ? 0 : chain * D) + i];
+        if (BOX) prev[i] = bx.transform(BOX ? i : 0, prev[i]);   // :166-168
+    }
     unsigned sp0 = 0, sp1 = 0;
     draw_normals(-1, z, sp0, sp1);   // src/rmhmc.cpp:176 (value unused, advances the stream: Q3)
 
     double newG[D * D], prevG[D * D], invNew[D * D], invPrev[D * D], newdG[D][D * D], prevdG[D][D * D];
-    TM::metric(a.tdata, prev, newG, newdG);   // :179
+    metric_v(prev, newG, newdG);              // :179
     LA::inverse(newG, invNew);                // :181
 #pragma unroll
     for (int k = 0; k < D * D; ++k) { prevG[k] = newG[k]; invPrev[k] = invNew[k]; }
@@ -281,7 +312,7 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ Rmhm
 #pragma unroll
         for (int k = 0; k < D * D; ++k) prevdG[i][k] = newdG[i][k];
     const double cons_term = a.cons_term;   // 0.5 * n_vals * MCMC_LOG_2PI evaluated in long double on the host (:188, Q19)
-    double prev_U = A::add(A::sub(cons_term, TM::logp(a.tdata, prev, nullptr)), A::mul(0.5, LA::logdet(newG)));   // :190
+    double prev_U = A::add(A::sub(cons_term, logp_v(prev)), A::mul(0.5, LA::logdet(newG)));   // :190
 
     int n_acc = 0;
     const int n_total = (int)(a.n_burnin + a.n_keep);
@@ -314,7 +345,7 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ Rmhm
             for (int i = 0; i < D; ++i) { p[i] = q[i]; wv[i] = cur[i]; }
             for (int kk = 0; kk < a.n_fp; ++kk) {     // :224-228
                 double Gw[D * D], sumM[D * D], tv[D];
-                TM::metric(a.tdata, wv, Gw, nullptr);
+                metric_v(wv, Gw, nullptr);
                 LA::inverse(Gw, invNew);
 #pragma unroll
                 for (int m = 0; m < D * D; ++m) sumM[m] = A::add(invPrev[m], invNew[m]);
@@ -324,13 +355,13 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ Rmhm
             }
 #pragma unroll
             for (int i = 0; i < D; ++i) cur[i] = wv[i];
-            TM::metric(a.tdata, cur, newG, newdG);    // :232
+            metric_v(cur, newG, newdG);               // :232
             LA::inverse(newG, invNew);                // :233
             mntm_update(cur, p, invNew, newdG, upd);  // :237
 #pragma unroll
             for (int i = 0; i < D; ++i) p[i] = A::add(p[i], upd[i]);
         }
-        double prop_U = A::add(A::sub(cons_term, TM::logp(a.tdata, cur, nullptr)), A::mul(0.5, LA::logdet(newG)));   // :240
+        double prop_U = A::add(A::sub(cons_term, logp_v(cur)), A::mul(0.5, LA::logdet(newG)));   // :240
         if (!isfinite(prop_U)) prop_U = CUDART_INF;
         double tmp[D];
         LA::gemv(invNew, p, tmp);
@@ -351,7 +382,7 @@ __global__ void __launch_bounds__(128) rmhmc_kernel(const __grid_constant__ Rmhm
         }
         if (t >= n_burnin) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) out_row[i] = prev[i];
+            for (int i = 0; i < D; ++i) out_row[i] = BOX ? bx.inv(BOX ? i : 0, prev[i]) : prev[i];   // :278-285
             out_row += D;
             if (out_lp) *out_lp++ = -(prev_U - cons_term);
             n_acc += acc ? 1 : 0;
@@ -364,7 +395,10 @@ template <bool STRICT, int RNGM> static int launch_nm(const RmhmcLaunch& a)
 {
     const int threads = 128;
     const long long blocks = (a.n_chains + threads - 1) / threads;
-    rmhmc_kernel<NormalModelRM<STRICT>, STRICT, RNGM><<<(unsigned)blocks, threads, 0, a.stream>>>(a);
+    if (a.lb != nullptr)
+        rmhmc_kernel<NormalModelRM<STRICT>, STRICT, RNGM, true><<<(unsigned)blocks, threads, 0, a.stream>>>(a);
+    else
+        rmhmc_kernel<NormalModelRM<STRICT>, STRICT, RNGM><<<(unsigned)blocks, threads, 0, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
     return MCMCB200_OK;
 }

@@ -157,7 +157,86 @@ struct Ctx {
     int target_id; const double* tdata; int d; int sum_mode;
     bool identity;            // precond empty -> M = I (src/hmc.cpp:57)
     vec M, Minv, S;           // precond, inverse, "sqrt" factor (CHOL_LOWER semantics per chol_mode)
+    bool bounded;             // algo_settings_t::vals_bound
+    std::vector<int> btype;   // determine_bounds_type: 1 none, 2 lower, 3 upper, 4 both
+    vec lb, ub;
 };
+
+const double EPS_DBL = std::numeric_limits<double>::epsilon();   // mcmc::eps_dbl (mcmc_options.hpp:103)
+
+// include/misc/determine_bounds_type.hpp:27-57
+void setup_bounds(Ctx& c, int vals_bound, const double* lower, const double* upper)
+{
+    c.bounded = vals_bound != 0;
+    c.btype.assign(c.d, 1);
+    if (!c.bounded) return;
+    c.lb.assign(lower, lower + c.d);
+    c.ub.assign(upper, upper + c.d);
+    for (int i = 0; i < c.d; ++i) {
+        const bool fl = std::isfinite(lower[i]), fu = std::isfinite(upper[i]);
+        c.btype[i] = (fl && fu) ? 4 : (fl ? 2 : (fu ? 3 : 1));
+    }
+}
+// include/misc/transform_vals.hpp:25-59
+void box_transform(const Ctx& c, const double* x, double* v)
+{
+    for (int i = 0; i < c.d; ++i) switch (c.btype[i]) {
+        case 1: v[i] = x[i]; break;
+        case 2: v[i] = std::log(x[i] - c.lb[i] + EPS_DBL); break;
+        case 3: v[i] = -std::log(c.ub[i] - x[i] + EPS_DBL); break;
+        default: v[i] = std::log(x[i] - c.lb[i] + EPS_DBL) - std::log(c.ub[i] - x[i] + EPS_DBL); break;
+    }
+}
+// include/misc/transform_vals.hpp:61-119
+void box_inv_transform(const Ctx& c, const double* v, double* x)
+{
+    for (int i = 0; i < c.d; ++i) switch (c.btype[i]) {
+        case 1: x[i] = v[i]; break;
+        case 2: x[i] = !std::isfinite(v[i]) ? c.lb[i] + EPS_DBL : c.lb[i] + EPS_DBL + std::exp(v[i]); break;
+        case 3: x[i] = !std::isfinite(v[i]) ? c.ub[i] - EPS_DBL : c.ub[i] - EPS_DBL - std::exp(-v[i]); break;
+        default:
+            if (!std::isfinite(v[i])) {
+                if (std::isnan(v[i])) x[i] = (c.ub[i] - c.lb[i]) / 2;
+                else if (v[i] < 0.0) x[i] = c.lb[i] + EPS_DBL;
+                else x[i] = c.ub[i] - EPS_DBL;
+            } else {
+                x[i] = (c.lb[i] - EPS_DBL + (c.ub[i] + EPS_DBL) * std::exp(v[i])) / (1.0 + std::exp(v[i]));
+                if (!std::isfinite(x[i])) x[i] = c.ub[i] - EPS_DBL;
+            }
+            break;
+    }
+}
+// include/misc/log_jacobian.hpp:25-58 (terms added in index order; SUM_WARP reduces them like every other dot product)
+double box_log_jacobian(const Ctx& c, const double* v)
+{
+    vec t(c.d, 0.0);
+    for (int i = 0; i < c.d; ++i) switch (c.btype[i]) {
+        case 2: t[i] = v[i]; break;
+        case 3: t[i] = -v[i]; break;
+        case 4: {
+            const double e = std::exp(v[i]);
+            t[i] = std::isfinite(e) ? std::log(c.ub[i] - c.lb[i]) + v[i] - 2 * std::log(1 + e) : std::log(c.ub[i] - c.lb[i]) - v[i];
+            break;
+        }
+        default: break;
+    }
+    if (c.sum_mode == otgt::SUM_SEQ) {   // ret_val starts at 0.0 and only bounded entries are added
+        double s = 0.0;
+        for (int i = 0; i < c.d; ++i) if (c.btype[i] != 1) s += t[i];
+        return s;
+    }
+    return otgt::reduce_sum(t.data(), c.d, c.sum_mode);
+}
+// diagonal of include/misc/inv_jacobian_adjust.hpp:25-56
+void box_inv_jac_diag(const Ctx& c, const double* v, double* J)
+{
+    for (int i = 0; i < c.d; ++i) switch (c.btype[i]) {
+        case 2: J[i] = std::exp(-v[i]); break;
+        case 3: J[i] = std::exp(v[i]); break;
+        case 4: { const double e = std::exp(v[i]); J[i] = ((e + 1) * (e + 1)) / (e * (c.ub[i] - c.lb[i])); break; }
+        default: J[i] = 1.0; break;
+    }
+}
 
 void mat_inverse(const vec& A, int n, vec& inv)
 {
@@ -302,6 +381,24 @@ double logp(const Ctx& c, const double* x, double* grad)
     return otgt::value_and_grad(c.target_id, c.tdata, x, grad, c.d, c.sum_mode);
 }
 
+// box_log_kernel (src/hmc.cpp:84-95): value of the transformed density at v
+double box_logp(const Ctx& c, const double* v)
+{
+    if (!c.bounded) return logp(c, v, nullptr);
+    vec x(c.d);
+    box_inv_transform(c, v, x.data());
+    return logp(c, x.data(), nullptr) + box_log_jacobian(c, v);
+}
+// gradient callback of mntm_update_fn (src/hmc.cpp:99-128): raw gradient at inv_transform(v) and the diagonal J (Q9)
+void box_grad(const Ctx& c, const double* v, double* g, double* J)
+{
+    if (!c.bounded) { logp(c, v, g); return; }
+    vec x(c.d);
+    box_inv_transform(c, v, x.data());
+    logp(c, x.data(), g);
+    box_inv_jac_diag(c, v, J);
+}
+
 // p = sqrt_precond * z   (src/hmc.cpp:158)
 void momentum_from_normals(const Ctx& c, const double* z, double* p)
 {
@@ -323,17 +420,19 @@ double kinetic(const Ctx& c, const double* p)
 void leapfrog(const Ctx& c, double eps, double* x, double* p)
 {
     const int d = c.d;
-    vec g(d), t(d);
-    logp(c, x, g.data());
-    for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
+    vec g(d), t(d), J(d);
+    box_grad(c, x, g.data(), J.data());
+    if (c.bounded) for (int i = 0; i < d; ++i) p[i] = p[i] + (J[i] * (eps * g[i])) / 2.0;   // (step*J)*grad/2: J diagonal
+    else for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
     if (c.identity) {
         for (int i = 0; i < d; ++i) x[i] = x[i] + eps * p[i];
     } else {
         gemv_scaled(c.Minv, d, eps, p, t.data());
         for (int i = 0; i < d; ++i) x[i] = x[i] + t[i];
     }
-    logp(c, x, g.data());
-    for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
+    box_grad(c, x, g.data(), J.data());
+    if (c.bounded) for (int i = 0; i < d; ++i) p[i] = p[i] + (J[i] * (eps * g[i])) / 2.0;
+    else for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
 }
 
 void setup_precond(Ctx& c, const double* precond, int chol_mode)
@@ -370,6 +469,7 @@ struct oracle_cfg_t {
     int sum_mode;
     int mala_exact_dmvnorm;  // 1: two dmvnorm() with LLT log-det + QR solve (mala.ipp:63-64); 0: cancelled form
     double* tape_out; long tape_out_cap;  // optional: every variate consumed, in order
+    int vals_bound; const double* lower; const double* upper;   // algo_settings_t::vals_bound / lower_bounds / upper_bounds
 };
 
 struct oracle_res_t {
@@ -394,6 +494,7 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -401,7 +502,8 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
     const unsigned n_leap = unsigned(cfg->n_leap_steps);  // Q22
 
     vec prev(x0, x0 + d), cur(d), p(d), z(d);
-    double prev_U = -logp(c, prev.data(), nullptr);   // :140
+    if (c.bounded) box_transform(c, x0, prev.data());   // :132-136
+    double prev_U = -box_logp(c, prev.data());          // :140
     long n_accept = 0, n_lf = 0;
 
     for (long t = 0; t < n_total; ++t) {
@@ -410,7 +512,7 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
         const double prev_K = kinetic(c, p.data());   // :160
         cur = prev;                                   // :162
         for (unsigned k = 0; k < n_leap; ++k) { leapfrog(c, eps, cur.data(), p.data()); ++n_lf; }  // :164-176
-        double prop_U = -logp(c, cur.data(), nullptr);  // :178
+        double prop_U = -box_logp(c, cur.data());       // :178
         if (!std::isfinite(prop_U)) prop_U = std::numeric_limits<double>::infinity();  // :180-182
         const double prop_K = kinetic(c, p.data());     // :184
         const double comp = std::min(0.01, -(prop_U + prop_K) + (prev_U + prev_K));  // :188 (Q6)
@@ -424,18 +526,26 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
             if (acc) ++n_accept;                        // :198 (Q7)
         }
     }
+    if (c.bounded)   // :211-218
+        for (long r = 0; r < cfg->n_keep; ++r) { vec tmp(draws + r * d, draws + (r + 1) * d); box_inv_transform(c, tmp.data(), draws + r * d); }
     res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = n_lf;
     return 0;
 }
 
 // ------------------------------------------------------------------ MALA (src/mala.cpp:30-208, mala.ipp:30-70, dmvnorm.hpp:28-54)
-static void mala_mean(const Ctx& c, double eps, const double* v, double* out)
+static void mala_mean(const Ctx& c, double eps, const double* v, double* out, double* J_out = nullptr)
 {
-    // v + (((eps*eps)*M)*grad)/2   (src/mala.cpp:123)
+    // v + (((eps*eps)*M)*grad)/2   (src/mala.cpp:123); bounded: v + ((((eps*eps)*J)*M)*grad)/2   (:118, M = I only here)
     const int d = c.d;
-    vec g(d), t(d);
-    logp(c, v, g.data());
+    vec g(d), t(d), J(d);
+    box_grad(c, v, g.data(), J.data());
     const double e2 = eps * eps;
+    if (c.bounded) {
+        // ((e2*J) * I) -> matrix product then "*= e2": entries J_ii * e2; times grad, /2, added to v
+        for (int i = 0; i < d; ++i) out[i] = v[i] + ((J[i] * e2) * g[i]) / 2.0;
+        if (J_out) for (int i = 0; i < d; ++i) J_out[i] = J[i];
+        return;
+    }
     if (c.identity) {
         for (int i = 0; i < d; ++i) out[i] = v[i] + (e2 * g[i]) / 2.0;
     } else {
@@ -458,6 +568,8 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    if (c.bounded && !c.identity) return -2;   // bounded MALA is restated for M = I only
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -470,20 +582,36 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     else for (size_t k = 0; k < Sigma.size(); ++k) Sigma[k] = c.M[k] * e2;
     if (!cfg->mala_exact_dmvnorm && !c.identity) mat_inverse(Sigma, d, SigInv);
 
-    vec prev(x0, x0 + d), cur(d), z(d), mean_prev(d), mean_prop(d), t(d), r(d);
-    double prev_LP = logp(c, prev.data(), nullptr);   // src/mala.cpp:138
+    vec prev(x0, x0 + d), cur(d), z(d), mean_prev(d), mean_prop(d), t(d), r(d), Jprev(d), Jprop(d);
+    if (c.bounded) box_transform(c, x0, prev.data());
+    double prev_LP = box_logp(c, prev.data());   // src/mala.cpp:138
     long n_accept = 0;
 
     for (long it = 0; it < n_total; ++it) {
         rng.normals(it, d, z.data());                 // :150
-        mala_mean(c, eps, prev.data(), mean_prev.data());
-        if (c.identity) for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + eps * z[i];   // :159
+        mala_mean(c, eps, prev.data(), mean_prev.data(), Jprev.data());
+        if (c.bounded)   // :155-157: mean + ((eps*chol(J)) * sqrtM) * z, chol of the diagonal J = sqrt(J_ii), sqrtM = I
+            for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + (std::sqrt(Jprev[i]) * eps) * z[i];
+        else if (c.identity) for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + eps * z[i];   // :159
         else { gemv_scaled(c.S, d, eps, z.data(), t.data()); for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + t[i]; }
-        double prop_LP = logp(c, cur.data(), nullptr);  // :162
+        double prop_LP = box_logp(c, cur.data());  // :162
         if (!std::isfinite(prop_LP)) prop_LP = -std::numeric_limits<double>::infinity();  // :164-166
-        mala_mean(c, eps, cur.data(), mean_prop.data());   // mala.ipp:60 (mean at prev is recomputed identically, :61)
+        mala_mean(c, eps, cur.data(), mean_prop.data(), Jprop.data());   // mala.ipp:60 (mean at prev is recomputed identically, :61)
         double adj;
-        if (cfg->mala_exact_dmvnorm) {
+        if (c.bounded) {
+            // both densities use Sigma = eps^2 * J(prop) * M (mala.ipp:55-56); M = I -> diagonal entries J_ii * e2
+            if (cfg->mala_exact_dmvnorm) {
+                vec Sg(size_t(d) * d, 0.0);
+                for (int i = 0; i < d; ++i) Sg[size_t(i) * d + i] = Jprop[i] * e2;
+                adj = dmvnorm_log(prev.data(), mean_prop.data(), Sg, d, c.sum_mode) - dmvnorm_log(cur.data(), mean_prev.data(), Sg, d, c.sum_mode);
+            } else {
+                for (int i = 0; i < d; ++i) { r[i] = prev[i] - mean_prop[i]; t[i] = r[i] / (Jprop[i] * e2); }
+                const double q1 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
+                for (int i = 0; i < d; ++i) { r[i] = cur[i] - mean_prev[i]; t[i] = r[i] / (Jprop[i] * e2); }
+                const double q2 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
+                adj = -0.5 * (q1 - q2);
+            }
+        } else if (cfg->mala_exact_dmvnorm) {
             adj = dmvnorm_log(prev.data(), mean_prop.data(), Sigma, d, c.sum_mode)
                 - dmvnorm_log(cur.data(), mean_prev.data(), Sigma, d, c.sum_mode);   // mala.ipp:63-64
         } else {
@@ -508,6 +636,8 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
             if (acc) ++n_accept;
         }
     }
+    if (c.bounded)   // src/mala.cpp:192-199
+        for (long rr = 0; rr < cfg->n_keep; ++rr) { vec tmp(draws + rr * d, draws + (rr + 1) * d); box_inv_transform(c, tmp.data(), draws + rr * d); }
     res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = 0;
     return 0;
 }
@@ -529,7 +659,7 @@ static void build_tree(NutsEnv& e, int dir, double eps, const vec& draw_vec, con
         new_draw = draw_vec;                       // :127
         vec new_mntm(mntm_vec);                    // :128
         leapfrog(c, dir * eps, new_draw.data(), new_mntm.data()); ++*e.n_lf;   // :132
-        double prop_U = -logp(c, new_draw.data(), nullptr);                    // :134
+        double prop_U = -box_logp(c, new_draw.data());                         // :134
         if (!std::isfinite(prop_U)) prop_U = std::numeric_limits<double>::infinity();
         const double prop_K = kinetic(c, new_mntm.data());                     // :140
         n_val = (e.log_u <= -prop_U - prop_K);                                 // :146
@@ -570,6 +700,7 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -582,18 +713,19 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     const double inf = std::numeric_limits<double>::infinity();
 
     vec first(x0, x0 + d), z(d), mntm(d);
+    if (c.bounded) box_transform(c, x0, first.data());  // :158-162
     rng.normals(-1, d, z.data());                       // :166 (Q3)
     momentum_from_normals(c, z.data(), mntm.data());    // :168
 
     // nuts_find_initial_step_size (nuts.ipp:30-93, Q14)
     double eps = 1.0;
     {
-        double pU = -logp(c, first.data(), nullptr);
+        double pU = -box_logp(c, first.data());
         if (!std::isfinite(pU)) pU = inf;
         const double pK = kinetic(c, mntm.data());
         vec nx(first), np(mntm);
         leapfrog(c, eps, nx.data(), np.data()); ++n_lf;
-        double qU = -logp(c, nx.data(), nullptr);
+        double qU = -box_logp(c, nx.data());
         if (!std::isfinite(qU)) qU = inf;
         double qK = kinetic(c, np.data());
         int a_val = 2 * (-(qU + qK) + (pU + pK) > std::log(0.5)) - 1;
@@ -601,7 +733,7 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
         while (cond) {
             eps *= std::pow(2, a_val);
             leapfrog(c, eps, nx.data(), np.data()); ++n_lf;
-            qU = -logp(c, nx.data(), nullptr);
+            qU = -box_logp(c, nx.data());
             if (!std::isfinite(qU)) qU = inf;
             qK = kinetic(c, np.data());
             a_val = 2 * ((-(qU + qK) + (pU + pK)) > std::log(0.5)) - 1;
@@ -611,7 +743,7 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     const double mu = std::log(10 * eps);   // src/nuts.cpp:174
     double h = 0.0;
 
-    double prev_U = -logp(c, first.data(), nullptr);   // :181
+    double prev_U = -box_logp(c, first.data());   // :181
     vec prev(first), new_draw(first), dpos(first), dneg(first), mpos(mntm), mneg(mntm);
     long n_accept = 0;
 
@@ -641,7 +773,7 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
             if (s_p == 1) {
                 const double z2 = rng.uniform(t, ucount++);   // :261
                 if (z2 < double(n_p) / double(n_val)) {       // :263
-                    double prop_U = -logp(c, new_draw.data(), nullptr);   // :264
+                    double prop_U = -box_logp(c, new_draw.data());   // :264
                     if (!std::isfinite(prop_U)) prop_U = inf;
                     prev = new_draw; prev_U = prop_U; good_round = 1;     // :272-277
                 }
@@ -668,26 +800,31 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
             n_accept += good_round;   // :308
         }
     }
+    if (c.bounded)   // :316-323
+        for (long r = 0; r < cfg->n_keep; ++r) { vec tmp(draws + r * d, draws + (r + 1) * d); box_inv_transform(c, tmp.data(), draws + r * d); }
     res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = n_lf;
     return 0;
 }
 
 // ------------------------------------------------------------------ RM-HMC (src/rmhmc.cpp:30-294, Appendix E)
 // only TGT_NORMAL_MODEL carries a metric in this oracle (examples/eigen/rmhmc_normal.cpp)
-static void metric(const Ctx& c, const double* x, vec& G, vec* dG)
+static void metric(const Ctx& c, const double* v, vec& G, vec* dG)
 {
+    // box_tensor_fn (src/rmhmc.cpp:150-161): the metric is evaluated at inv_transform(v) when bounded
     const int d = c.d;
     G.assign(size_t(d) * d, 0.0);
     if (dG) dG->assign(size_t(d) * d * d, 0.0);
-    otgt::metric_normal_model(c.tdata, x, G.data(), dG ? dG->data() : nullptr);
+    vec x(v, v + d);
+    if (c.bounded) box_inv_transform(c, v, x.data());
+    otgt::metric_normal_model(c.tdata, x.data(), G.data(), dG ? dG->data() : nullptr);
 }
 
 // returns (eps * F)/2 with F_i = -grad_i + 1/2 (tr(A D_i) - ((A D_i)' q).(A q))   (src/rmhmc.cpp:132-146; Q16 sign)
 static void rm_mntm_update(const Ctx& c, double eps, const double* y, const double* q, const vec& A, const vec& dG, double* out)
 {
     const int d = c.d;
-    vec g(d), Aq(d), tq(d), T, Tt(size_t(d) * d);
-    logp(c, y, g.data());
+    vec g(d), Aq(d), tq(d), T, Tt(size_t(d) * d), J(d);
+    box_grad(c, y, g.data(), J.data());
     for (int i = 0; i < d; ++i) {
         vec Di(dG.begin() + size_t(i) * d * d, dG.begin() + size_t(i + 1) * d * d);
         matmul(A, Di, d, T);                      // tmp_mat = inv_tensor * deriv.mat(i)
@@ -700,13 +837,15 @@ static void rm_mntm_update(const Ctx& c, double eps, const double* y, const doub
         const double dp = otgt::dot(tq.data(), Aq.data(), d, c.sum_mode);
         g[i] = -g[i] + 0.5 * (tr - dp);
     }
-    for (int i = 0; i < d; ++i) out[i] = (eps * g[i]) / 2.0;
+    if (c.bounded) for (int i = 0; i < d; ++i) out[i] = (J[i] * (eps * g[i])) / 2.0;   // step*J*grad/2 (src/rmhmc.cpp:125)
+    else for (int i = 0; i < d; ++i) out[i] = (eps * g[i]) / 2.0;
 }
 
 static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     c.identity = true;   // precond_mat is never read (Q18)
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -715,6 +854,7 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
     const double inf = std::numeric_limits<double>::infinity();
 
     vec prev(x0, x0 + d), cur(d), z(d), p(d), q(d), upd(d), w(d), t(d);
+    if (c.bounded) box_transform(c, x0, prev.data());   // :166-168
     rng.normals(-1, d, z.data());   // :176 (Q3: value unused)
 
     vec newG, newdG, prevG, invNew, invPrev, prevdG, L, Gw, invW, sumM(size_t(d) * d);
@@ -722,7 +862,7 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
     metric(c, cur.data(), newG, &newdG);   // :179
     prevG = newG; mat_inverse(newG, d, invNew); invPrev = invNew; prevdG = newdG;   // :181-186
     const double cons_term = double(0.5 * double(size_t(d)) * 1.83787706640934548356L);   // :188 (Q19)
-    double prev_U = cons_term - logp(c, prev.data(), nullptr) + 0.5 * logdet_llt(newG, d);  // :190
+    double prev_U = cons_term - box_logp(c, prev.data()) + 0.5 * logdet_llt(newG, d);  // :190
     long n_accept = 0, n_lf = 0;
 
     for (long it = 0; it < n_total; ++it) {
@@ -755,7 +895,7 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
             for (int i = 0; i < d; ++i) p[i] += upd[i];
             ++n_lf;
         }
-        double prop_U = cons_term - logp(c, cur.data(), nullptr) + 0.5 * logdet_llt(newG, d);   // :240
+        double prop_U = cons_term - box_logp(c, cur.data()) + 0.5 * logdet_llt(newG, d);   // :240
         if (!std::isfinite(prop_U)) prop_U = inf;
         gemv_plain(invNew, d, p.data(), t.data());
         const double prop_K = otgt::dot(p.data(), t.data(), d, c.sum_mode) / 2.0;               // :246
@@ -770,6 +910,8 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
             if (acc) ++n_accept;
         }
     }
+    if (c.bounded)   // :278-285
+        for (long r = 0; r < cfg->n_keep; ++r) { vec tmp(draws + r * d, draws + (r + 1) * d); box_inv_transform(c, tmp.data(), draws + r * d); }
     res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = eps; res->n_leapfrog = n_lf;
     return 0;
 }

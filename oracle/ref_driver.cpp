@@ -93,6 +93,9 @@ struct ref_settings_t {
     double target_accept_rate, gamma_val, t0_val, kappa_val;  // nuts
     long max_tree_depth;   // nuts
     int use_nuts_defaults; // 1 -> keep the struct defaults for the five nuts fields above
+    int vals_bound;        // algo_settings_t::vals_bound
+    const double* lower;   // d entries (+-inf = unbounded side) when vals_bound
+    const double* upper;
 };
 
 int ref_run_chain(int sampler, int target_id, const double* tdata, int d, const double* x0, const ref_settings_t* st,
@@ -104,6 +107,12 @@ int ref_run_chain(int sampler, int target_id, const double* tdata, int d, const 
 
     mcmc::algo_settings_t s;
     s.rng_seed_value = seed;
+    if (st->vals_bound) {
+        s.vals_bound = true;
+        s.lower_bounds.resize(d);
+        s.upper_bounds.resize(d);
+        for (int j = 0; j < d; ++j) { s.lower_bounds(j) = st->lower[j]; s.upper_bounds(j) = st->upper[j]; }
+    }
     mcmc::Mat_t draws;
     bool ok = false;
     long acc = 0;

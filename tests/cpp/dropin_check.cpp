@@ -57,10 +57,22 @@ int main()
         int same = (cube.n_mat() == C) && std::memcmp(cube.mat(2).data(), draws.data(), sizeof(double) * 20 * d) == 0;
         std::printf("multichain_consistent %d %zu\n", same, s.b200.n_accept_per_chain.size());
     }
-    {   // box constraints must be refused, not ignored
-        mcmc::ColVec_t x0(2); x0(0) = 1; x0(1) = 1;
-        mcmc::algo_settings_t s; s.vals_bound = true;
-        const bool ok = mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s);
+    {   // box constraints, written like reference user code (golden case hmc_box_d4: all four bound types)
+        const double inf = INFINITY;
+        const double w[4] = {1.0, 0.5, 2.0, 1.5};
+        mcmc::kernel_data dta = {w, 4};
+        mcmc::ColVec_t x0(4); x0(0) = 0.3; x0(1) = 0.7; x0(2) = 0.4; x0(3) = 0.2;
+        mcmc::algo_settings_t s; s.rng_seed_value = 31; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.vals_bound = true;
+        s.lower_bounds = mcmc::ColVec_t(4); s.upper_bounds = mcmc::ColVec_t(4);
+        s.lower_bounds(0) = -inf; s.lower_bounds(1) = 0.0; s.lower_bounds(2) = -inf; s.lower_bounds(3) = -1.0;
+        s.upper_bounds(0) = inf; s.upper_bounds(1) = inf; s.upper_bounds(2) = 2.0; s.upper_bounds(3) = 1.5;
+        s.hmc_settings.n_burnin_draws = 5; s.hmc_settings.n_keep_draws = 40; s.hmc_settings.n_leap_steps = 6; s.hmc_settings.step_size = 0.2;
+        if (!mcmc::hmc(x0, mcmc::device_kernel("diag_gauss"), draws, &dta, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        dump("hmc_box_d4", draws, s.hmc_settings.n_accept_draws);
+        // vals_bound without bound vectors of length n_vals is refused, not ignored
+        mcmc::algo_settings_t bad; bad.vals_bound = true;
+        const bool ok = mcmc::hmc(x0, mcmc::device_kernel("diag_gauss"), draws, &dta, bad);
         std::printf("bounds_refused %d\n", ok ? 0 : 1);
     }
     return 0;

@@ -60,6 +60,19 @@ def cases():
         dict(name="rmhmc_L2", sampler=ol.RMHMC, target=ol.TGT_NORMAL_MODEL, tdata=nm, x0=[3, 3], seed=2,
              st=dict(n_burnin=10, n_keep=80, n_leap_steps=2, step_size=0.15)),
     ]
+    # box constraints (algo_settings_t::vals_bound): all four bound types in one vector; +-inf = open side
+    inf = float("inf")
+    lo4, hi4 = [-inf, 0.0, -inf, -1.0], [inf, inf, 2.0, 1.5]
+    out += [
+        dict(name="hmc_box_d4", sampler=ol.HMC, target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 0.5, 2.0, 1.5], x0=[0.3, 0.7, 0.4, 0.2], seed=31,
+             st=dict(n_burnin=5, n_keep=40, n_leap_steps=6, step_size=0.2), lower=lo4, upper=hi4),
+        dict(name="mala_box_d4", sampler=ol.MALA, target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 0.5, 2.0, 1.5], x0=[0.3, 0.7, 0.4, 0.2], seed=32,
+             st=dict(n_burnin=5, n_keep=40, step_size=0.35), lower=lo4, upper=hi4),
+        dict(name="nuts_box_d4", sampler=ol.NUTS, target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 0.5, 2.0, 1.5], x0=[0.3, 0.7, 0.4, 0.2], seed=33,
+             st=dict(n_burnin=0, n_keep=30, step_size=0.15, n_adapt_draws=0), lower=lo4, upper=hi4),
+        dict(name="rmhmc_box_sigma_positive", sampler=ol.RMHMC, target=ol.TGT_NORMAL_MODEL, tdata=nm, x0=[3, 3], seed=34,
+             st=dict(n_burnin=5, n_keep=40, n_leap_steps=2, step_size=0.1), lower=[-inf, 0.0], upper=[inf, inf]),
+    ]
     return out
 
 
@@ -70,8 +83,12 @@ def main():
     golden["rng_G1"] = dict(seed=1, n_norm=4, n_unif=1, values=hexlist(ref.rng_stream(1, 4, 1)))
     for c in cases():
         st = ol.Settings(**c["st"])
+        if "lower" in c:   # bounds travel as hex strings ("inf" / "-inf" for the open sides): strict JSON has no Infinity
+            st["lower_bounds"], st["upper_bounds"] = c["lower"], c["upper"]
         draws, acc = ref.run_chain(c["sampler"], c["target"], c["tdata"], c["x0"], st, c["seed"])
         e = dict(c)
+        if "lower" in c:
+            e["lower"], e["upper"] = hexlist(c["lower"]), hexlist(c["upper"])
         e["draws_shape"] = list(draws.shape)
         e["draws_hex"] = hexlist(draws)
         e["n_accept"] = int(acc)

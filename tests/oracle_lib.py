@@ -40,7 +40,7 @@ class _RefSettings(ctypes.Structure):
         ("step_size", ctypes.c_double), ("precond", ctypes.c_void_p), ("n_fp_steps", ctypes.c_long),
         ("n_adapt_draws", ctypes.c_long), ("target_accept_rate", ctypes.c_double), ("gamma_val", ctypes.c_double),
         ("t0_val", ctypes.c_double), ("kappa_val", ctypes.c_double), ("max_tree_depth", ctypes.c_long),
-        ("use_nuts_defaults", ctypes.c_int),
+        ("use_nuts_defaults", ctypes.c_int), ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p),
     ]
 
 
@@ -55,6 +55,7 @@ class _OracleCfg(ctypes.Structure):
         ("rng_mode", ctypes.c_int), ("seed", ctypes.c_ulong), ("tape", ctypes.c_void_p), ("tape_len", ctypes.c_long),
         ("chain_id", ctypes.c_long), ("sum_mode", ctypes.c_int), ("mala_exact_dmvnorm", ctypes.c_int),
         ("tape_out", ctypes.c_void_p), ("tape_out_cap", ctypes.c_long),
+        ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p),
     ]
 
 
@@ -68,7 +69,7 @@ class Settings(dict):
 
     DEFAULTS = dict(n_burnin=1000, n_keep=1000, n_leap_steps=1, step_size=1.0, precond=None, n_fp_steps=5,
                     n_adapt_draws=1000, target_accept_rate=0.55, gamma_val=0.05, t0_val=10.0, kappa_val=0.75,
-                    max_tree_depth=10)
+                    max_tree_depth=10, lower_bounds=None, upper_bounds=None)
 
     def __init__(self, **kw):
         super().__init__(self.DEFAULTS)
@@ -76,6 +77,16 @@ class Settings(dict):
             if k not in self.DEFAULTS:
                 raise KeyError(k)
         self.update(kw)
+
+
+def _bounds(st, d, keep):
+    """(vals_bound, lower ptr, upper ptr): vals_bound is on when either bound vector is given (+-inf = open side)."""
+    if st["lower_bounds"] is None and st["upper_bounds"] is None:
+        return 0, None, None
+    lo = np.full(d, -np.inf) if st["lower_bounds"] is None else np.ascontiguousarray(st["lower_bounds"], dtype=np.float64)
+    hi = np.full(d, np.inf) if st["upper_bounds"] is None else np.ascontiguousarray(st["upper_bounds"], dtype=np.float64)
+    keep += [lo, hi]
+    return 1, _ptr(lo), _ptr(hi)
 
 
 def _precond_colmajor(precond):
@@ -99,19 +110,20 @@ class Reference:
     def available(flavour="strict"):
         return os.path.exists(os.path.join(ORACLE_DIR, "_ref", "libmcmc_ref_%s.so" % flavour))
 
-    def _settings(self, st, keep):
+    def _settings(self, st, keep, d):
         pc = _precond_colmajor(st["precond"])
         keep.append(pc)
+        vb, lo, hi = _bounds(st, d, keep)
         return _RefSettings(st["n_burnin"], st["n_keep"], st["n_leap_steps"], st["step_size"], _ptr(pc),
                             st["n_fp_steps"], st["n_adapt_draws"], st["target_accept_rate"], st["gamma_val"],
-                            st["t0_val"], st["kappa_val"], st["max_tree_depth"], 0)
+                            st["t0_val"], st["kappa_val"], st["max_tree_depth"], 0, vb, lo, hi)
 
     def run_chain(self, sampler, target_id, tdata, x0, st, seed):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         d = x0.size
         tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
         keep = []
-        rs = self._settings(st, keep)
+        rs = self._settings(st, keep, d)
         draws = np.zeros((st["n_keep"], d))
         acc = ctypes.c_long(0)
         rc = self.lib.ref_run_chain(sampler, target_id, _ptr(tdata), d, _ptr(x0), ctypes.byref(rs),
@@ -124,7 +136,7 @@ class Reference:
         C, d = x0s.shape
         tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
         keep = []
-        rs = self._settings(st, keep)
+        rs = self._settings(st, keep, d)
         draws = np.zeros((C, st["n_keep"], d)) if keep_draws else None
         acc = np.zeros(C, dtype=np.int64)
         el = ctypes.c_double(0)
@@ -160,12 +172,14 @@ class Oracle:
         pc = _precond_colmajor(st["precond"])
         tape_a = None if tape is None else np.ascontiguousarray(tape, dtype=np.float64)
         rec = np.zeros(record_tape) if record_tape else None
+        keep = []
+        vb, lo, hi = _bounds(st, d, keep)
         cfg = _OracleCfg(sampler, target_id, _ptr(tdata), d, st["n_burnin"], st["n_keep"], st["n_leap_steps"],
                          st["step_size"], _ptr(pc), chol_mode, st["n_fp_steps"], st["n_adapt_draws"],
                          st["target_accept_rate"], st["gamma_val"], st["t0_val"], st["kappa_val"],
                          st["max_tree_depth"], rng_mode, ctypes.c_ulong(seed), _ptr(tape_a),
                          0 if tape_a is None else tape_a.size, chain_id, sum_mode, mala_exact, _ptr(rec),
-                         record_tape)
+                         record_tape, vb, lo, hi)
         draws = np.zeros((st["n_keep"], d))
         logp = np.zeros(st["n_keep"]) if want_logp else None
         res = _OracleRes()

@@ -37,7 +37,8 @@ def _run_pair(engine, oracle, tid, tname, tdata, x0s, st, seed, arith, precond=N
     r = engine.nuts(x0s, tname, target_data=tdata, step_size=st["step_size"], n_adapt_draws=st["n_adapt_draws"],
                     target_accept_rate=st["target_accept_rate"], max_tree_depth=st["max_tree_depth"], gamma_val=st["gamma_val"],
                     t0_val=st["t0_val"], kappa_val=st["kappa_val"], precond_mat=precond, chol_mode=chol_mode,
-                    n_burnin=st["n_burnin"], n_keep=st["n_keep"], rng_mode=engine.api.RNG_USER_TAPE, tape=tape, arith=arith)
+                    n_burnin=st["n_burnin"], n_keep=st["n_keep"], rng_mode=engine.api.RNG_USER_TAPE, tape=tape, arith=arith,
+                    lower_bounds=st["lower_bounds"], upper_bounds=st["upper_bounds"])
     od = np.stack(od)
     assert np.abs(r["draws"] - od).max() <= tol, np.abs(r["draws"] - od).max()
     assert np.array_equal(r["n_accept"], np.array(oa))

@@ -30,7 +30,7 @@ def test_golden_rng_stream(oracle, golden):
 
 
 def test_oracle_reproduces_every_golden_case(oracle, golden):
-    assert len(golden["cases"]) >= 12
+    assert len(golden["cases"]) >= 16
     for c in golden["cases"]:
         o = oracle.run_chain(c["sampler"], c["target"], c["tdata"], c["x0"], c["settings"], seed=c["seed"], rng_mode=ol.RNG_MT,
                              sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1)
@@ -86,6 +86,53 @@ def test_oracle_bit_equal_to_live_reference(oracle, reference):
                              mala_exact=1)
         assert np.array_equal(o["draws"], ref), name
         assert o["n_accept"] == acc, name
+
+
+def _bounded_cases():
+    """Box constraints (vals_bound): every bound type, all four samplers (bounded MALA: M = I, the only form restated)."""
+    rng = np.random.default_rng(2718)
+    inf = np.inf
+    xs = 2 + 2 * np.sin(np.arange(100.0))
+    nm = [100.0, float(xs.mean()), float(((xs - xs.mean()) ** 2).sum())]
+    d = 10
+    lo = np.array([-inf, 0.0, -inf, -1.0, -2.0, -inf, 0.5, -inf, -3.0, -inf])
+    hi = np.array([inf, inf, 2.0, 1.5, 2.0, inf, inf, 0.0, 3.0, 4.0])
+    x0 = np.array([0.1, 0.4, 1.0, 0.2, -0.5, 0.3, 1.5, -0.7, 0.0, 1.0])
+    w = np.exp(rng.uniform(-0.5, 0.5, d))
+    B = dict(lower_bounds=lo, upper_bounds=hi)
+    return [
+        ("hmc box diag", ol.HMC, ol.TGT_DIAG_GAUSS, w, x0, ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=5, step_size=0.1, **B), 41),
+        ("hmc box iso lower only", ol.HMC, ol.TGT_ISO_GAUSS, None, np.abs(x0) + 0.1,
+         ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=4, step_size=0.15, lower_bounds=np.zeros(d)), 42),
+        ("hmc box normal model", ol.HMC, ol.TGT_NORMAL_MODEL, nm, [3, 3],
+         ol.Settings(n_burnin=10, n_keep=80, n_leap_steps=5, step_size=0.05, lower_bounds=[-inf, 0.0], upper_bounds=[inf, inf]), 43),
+        ("mala box diag", ol.MALA, ol.TGT_DIAG_GAUSS, w, x0, ol.Settings(n_burnin=5, n_keep=80, step_size=0.2, **B), 44),
+        ("nuts box diag", ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0, ol.Settings(n_burnin=0, n_keep=30, n_adapt_draws=0, step_size=0.1, **B), 45),
+        ("nuts box adapt", ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0, ol.Settings(n_burnin=20, n_keep=20, n_adapt_draws=20, **B), 46),
+        ("rmhmc box", ol.RMHMC, ol.TGT_NORMAL_MODEL, nm, [2.5, 2.5],
+         ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=2, step_size=0.1, lower_bounds=[-inf, 0.0], upper_bounds=[10.0, inf]), 47),
+    ]
+
+
+def test_oracle_bit_equal_to_live_reference_with_bounds(oracle, reference):
+    for name, sampler, tid, tdata, x0, st, seed in _bounded_cases():
+        ref, acc = reference.run_chain(sampler, tid, tdata, x0, st, seed)
+        o = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1)
+        assert np.array_equal(o["draws"], ref), name
+        assert o["n_accept"] == acc, name
+        lo = -np.inf if st["lower_bounds"] is None else np.asarray(st["lower_bounds"])
+        hi = np.inf if st["upper_bounds"] is None else np.asarray(st["upper_bounds"])
+        assert np.all(ref >= lo) and np.all(ref <= hi), name
+
+
+def test_comparator_modes_agree_with_reference_mode_with_bounds(oracle):
+    for name, sampler, tid, tdata, x0, st, seed in _bounded_cases():
+        if sampler == ol.NUTS and st["n_adapt_draws"] > 0:
+            continue
+        a = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, sum_mode=ol.SUM_SEQ, mala_exact=1)
+        b = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, sum_mode=ol.SUM_WARP, mala_exact=0)
+        assert np.abs(a["draws"] - b["draws"]).max() <= 1e-10, name
+        assert a["n_accept"] == b["n_accept"], name
 
 
 def test_comparator_modes_agree_with_reference_mode(oracle):
