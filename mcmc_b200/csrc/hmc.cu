@@ -19,6 +19,7 @@
 #include "targets.cuh"
 #include "box.cuh"
 #include <math_constants.h>
+#include <type_traits>
 
 namespace mcmcb200
 {
@@ -56,10 +57,8 @@ __device__ __forceinline__ void kick_full(double (&p)[EPL], const double (&g)[EP
 constexpr int hmc_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 4 : 2); }
 
 // FT ("full tile"): n_dim == 32*EPL and 16-byte aligned rows, so no padding predicates anywhere.
-// LS: number of leapfrog steps fixed at compile time (0 = runtime a.n_leap).  With LS > 0 the whole draw is straight-line
-// code, so ptxas interleaves the next Box-Muller polynomial chains, the Philox rounds and the leapfrog DFMAs freely.
 // BOX: box constraints (vals_bound), see box.cuh; available with M = I on the generic (runtime-L) kernels.
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0, bool BOX = false>
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, bool BOX = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_kernel(const __grid_constant__ HmcLaunch a)
 {
     extern __shared__ double smem[];
@@ -101,38 +100,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     const int n_burnin = (int)a.n_burnin;
     const double eps = a.eps;
     const double heps = 0.5 * eps;
-    const int L = LS ? LS : a.n_leap;
+    const int L = a.n_leap;
     double* out_row = a.draws + chain * a.n_keep * d;
     double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
 
-    // Software pipelining (compile-time-L Philox kernels only): the variates of draw t+1 are generated in the same
-    // straight-line block as the trajectory of draw t — they do not depend on the chain state, so the integer Philox
-    // rounds and the Box-Muller chains fill the issue slots left by the dependent leapfrog DFMAs.
-    constexpr bool PIPE = (LS > 0) && (RNGM == RNG_PHILOX) && !DENSE_M;
-    double zn[PIPE ? EPL : 1];
-    double un = 0.0;
-    if (PIPE) {
-        double ztmp[EPL];
-        rng.template normals<EPL, FT>(a.rng, 0, d, lane, log_tab, ztmp);
-        un = rng.uniform(a.rng, 0, 0);
-#pragma unroll
-        for (int k = 0; k < (PIPE ? EPL : 1); ++k) zn[k] = ztmp[k];
-    }
-
     for (int t = 0; t < n_total; ++t) {
         // ---- momentum refresh: p = sqrtM z, K0 = p.(M^-1 p)/2 (lane partial in FAST) ----
-        double u_pipe = un;
-        if (PIPE) {
-#pragma unroll
-            for (int k = 0; k < EPL; ++k) p[k] = zn[k < (PIPE ? EPL : 1) ? k : 0];
-            double ztmp[EPL];
-            rng.template normals<EPL, FT>(a.rng, t + 1, d, lane, log_tab, ztmp);   // one spare draw past the end: harmless
-            un = rng.uniform(a.rng, t + 1, 0);
-#pragma unroll
-            for (int k = 0; k < (PIPE ? EPL : 1); ++k) zn[k] = ztmp[k];
-        } else {
-            rng.template normals<EPL, FT>(a.rng, t, d, lane, log_tab, p);
-        }
+        rng.template normals<EPL, FT>(a.rng, t, d, lane, log_tab, p);
         double K0;
         if (DENSE_M) {
             double tmp[EPL];
@@ -171,12 +145,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
                     kick_full<EPL, STRICT, BOX>(p, g, Jr, eps);  // end of step s and start of step s+1 share this gradient
                 }
             };
-            if (LS > 0) {
-#pragma unroll
-                for (int s = 0; s < LS; ++s) step(s);
-            } else {
-                for (int s = 0; s < L; ++s) step(s);
-            }
+            for (int s = 0; s < L; ++s) step(s);
             U1 = -box_eval<T, EPL, STRICT, BOX, true, true, STRICT>(a.tdata, w, bx, x, g, Jr);  // value-only call of :178 fused in
             kick_half<EPL, STRICT, BOX>(p, g, Jr, eps, heps);
         } else {
@@ -194,7 +163,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
         }
 
         // ---- Metropolis test ----
-        const double u = PIPE ? u_pipe : rng.uniform(a.rng, t, 0);
+        const double u = rng.uniform(a.rng, t, 0);
         bool acc;
         if (STRICT) {
             // the reference's expression, evaluated literally (src/hmc.cpp:180-191)
@@ -235,13 +204,164 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, int LS = 0, bool BOX = false> static int launch_one(const HmcLaunch& a)
+// ---------------------------------------------------------------------------------------------------------------
+// Production kernel: FAST arithmetic, in-kernel Philox, identity mass, full tiles (n_dim == 32*EPL) — the
+// configuration of the headline benchmark.  Same per-draw algorithm as hmc_kernel; what differs is how the draw
+// loop is laid out for the issue-bound fp64 pipe:
+//   * software pipelining: the variates of draw t+1 (independent of the chain state) are generated in the same
+//     straight-line block as the trajectory of draw t; the draw loop is unrolled by two so the "current" and "next"
+//     variate registers swap roles without copies;
+//   * K0 = sum z^2 / 2 comes from the Box-Muller radii (z0^2 + z1^2 = -2 ln u1), not from a second dot product;
+//   * no control flow on the accept decision: the trajectory runs in place on x, the pre-trajectory state is parked
+//     in shared memory and reloaded by a PREDICATED ld.shared into the same registers on a rejection, so neither
+//     path needs register moves; exp() is evaluated only in the thin band 1 + dH <= u;
+//   * burn-in and kept draws are separate loops (no per-draw store predicate, no carried row pointer).
+// LS = compile-time number of leapfrog steps (0 = runtime a.n_leap), UNR = draw-loop unroll (1 or 2).
+template <int EPL> __device__ __forceinline__ void restore_if(const double* home, int lane, double (&x)[EPL], bool pred)
+{
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(home + 2 * lane));
+#pragma unroll
+    for (int m = 0; m < EPL / 2; ++m)
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\t@q ld.volatile.shared.v2.f64 {%0, %1}, [%2];\n\t}"
+                     : "+d"(x[2 * m]), "+d"(x[2 * m + 1])
+                     : "r"(addr + m * 512), "r"(static_cast<int>(pred))
+                     : "memory");
+}
+
+// the matching store is opaque too, so ptxas cannot forward the stored registers into the predicated reload (it
+// would keep a second copy of the state live in registers and pay a move per word)
+template <int EPL> __device__ __forceinline__ void park(double* home, int lane, const double (&x)[EPL])
+{
+    const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(home + 2 * lane));
+#pragma unroll
+    for (int m = 0; m < EPL / 2; ++m)
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" : : "r"(addr + m * 512), "d"(x[2 * m]), "d"(x[2 * m + 1]) : "memory");
+}
+
+template <class T, int EPL, int LS, int UNR>
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_pipe_kernel(const __grid_constant__ HmcLaunch a)
+{
+    extern __shared__ double smem[];
+    __shared__ double2 rng_tab[RNG_TAB_DOUBLE2];
+    build_rng_tables(rng_tab);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long chain = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (chain >= a.n_chains) return;  // whole warp exits together; no block-level barriers below
+    constexpr int d = 32 * EPL;
+    double* home = smem + (size_t)warp * (T::needs_scratch ? 2 : 1) * d;  // the chain's current state while a trajectory runs
+    const WarpCtx w{lane, d, home + d};
+
+    double x[EPL], g[EPL];
+    load_vec_full<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), lane, x);
+    ChainRng<RNG_PHILOX> rng;
+    rng.init(a.rng, chain, a.chain_offset + chain);
+    double U = -T::template eval<EPL, false, true, false, false>(a.tdata, w, x, g);  // this lane's partial sum of -log pi(x)
+    int n_acc = 0;
+    const int n_burnin = (int)a.n_burnin, n_total = (int)(a.n_burnin + a.n_keep);
+    const double eps = a.eps, heps = 0.5 * eps;
+    const int L = a.n_leap;
+    double* const out_base = a.draws + chain * a.n_keep * d + 2 * lane;
+    double* const out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
+
+    double zA[EPL], zB[EPL], uA, uB, kA, kB;  // variates of the current / next draw (roles alternate)
+    {
+        BmPipe<EPL / 2> bp;
+        bp.begin(lane, 0, rng.chain);
+        bp.template slice<0, 1>(a.rng, rng_tab, zA, kA);
+        uA = bp.uniform0();
+    }
+
+    // one transition; p holds z_t on entry (consumed), (zn, un, kn) receive the variates of draw t + 1
+    auto draw = [&](int t, double (&p)[EPL], double u, double ksum, double (&zn)[EPL], double& un, double& kn, auto keep) {
+        // the variates of draw t + 1 (one spare draw past the end: harmless), generated slice by slice between the
+        // leapfrog steps below when the trajectory length is a compile-time constant
+        BmPipe<EPL / 2> bp;
+        bp.begin(lane, t + 1, rng.chain);
+        if (LS == 0) bp.template slice<0, 1>(a.rng, rng_tab, zn, kn);
+        double dH = fma(0.5, ksum, U);   // U0 + K0 (lane partial)
+        bool acc = true;
+        if (LS > 0 || L > 0) {
+            park<EPL>(home, lane, x);
+            T::template eval<EPL, false, false, true, false>(a.tdata, w, x, g);
+            kick_half<EPL, false, false>(p, g, g, eps, heps);
+            auto step = [&](int s) {
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) x[k] = fma(eps, p[k], x[k]);
+                if (LS > 0 ? (s + 1 < LS) : (s + 1 < L)) {
+                    T::template eval<EPL, false, false, true, false>(a.tdata, w, x, g);
+                    kick_full<EPL, false, false>(p, g, g, eps);
+                }
+            };
+            if (LS > 0) {
+                static_for<0, LS>([&](auto sc) {
+                    constexpr int s = decltype(sc)::value;
+                    bp.template slice<s, (LS > 0 ? LS : 1)>(a.rng, rng_tab, zn, kn);
+                    step(s);
+                });
+            } else {
+                for (int s = 0; s < L; ++s) step(s);
+            }
+            un = bp.uniform0();
+            const double U1 = -T::template eval<EPL, false, true, true, false>(a.tdata, w, x, g);
+            kick_half<EPL, false, false>(p, g, g, eps, heps);
+            // dH = (U0 + K0) - (U1 + K1), one butterfly.  u < exp(min(0.01, dH)) holds whenever u < 1 + dH (<= exp(dH);
+            // also dH = +inf, src/hmc.cpp:187), so exp() is evaluated only in the thin band 1 + dH <= u; a NaN rejects.
+            dH = warp_sum<false>(fma(-0.5, lane_dot<EPL, false>(p, p), dH - U1));
+            acc = u < 1.0 + dH;
+            if (!acc) acc = (fabs(dH) <= 1.7976931348623157e308) && (u < exp(dH));
+            restore_if<EPL>(home, lane, x, !acc);
+            U = acc ? U1 : U;
+        }
+        if (LS == 0 && L == 0) un = bp.uniform0();
+        if (decltype(keep)::value) {
+            double* row = out_base + (size_t)(t - n_burnin) * d;
+#pragma unroll
+            for (int m = 0; m < EPL / 2; ++m) *reinterpret_cast<double2*>(row + m * 64) = make_double2(x[2 * m], x[2 * m + 1]);
+            if (out_lp) {
+                const double Ur = warp_sum<false>(U);
+                if (lane == 0) out_lp[t - n_burnin] = -Ur;
+            }
+            n_acc += acc ? 1 : 0;
+        }
+    };
+    auto run = [&](int t0, int t1, auto keep) {
+        for (int t = t0; t < t1; t += UNR) {
+            draw(t, zA, uA, kA, zB, uB, kB, keep);
+            if (UNR == 2 && t + 1 < t1) {
+                draw(t + 1, zB, uB, kB, zA, uA, kA, keep);
+            } else {
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) zA[k] = zB[k];
+                uA = uB;
+                kA = kB;
+            }
+        }
+    };
+    run(0, n_burnin, std::false_type());
+    run(n_burnin, n_total, std::true_type());
+    if (lane == 0 && a.n_accept) a.n_accept[chain] = n_acc;
+}
+
+#ifndef MCMCB200_KERNEL_ONLY   // tools/c2_variants.cu instantiates the headline kernel alone
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, bool BOX = false> static int launch_one(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (size_t)WARPS_PER_BLOCK * ((T::needs_scratch || DENSE_M) ? 3 : 1) * dpad * sizeof(double);
-    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT, LS, BOX>;
-    if (smem > 40 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = hmc_kernel<T, EPL, DENSE_M, STRICT, RNGM, FT, BOX>;
+    if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
+    MCMCB200_CUDA_TRY(cudaGetLastError());
+    return MCMCB200_OK;
+}
+
+template <class T, int EPL, int LS> static int launch_pipe(const HmcLaunch& a)
+{
+    const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
+    const size_t smem = (size_t)WARPS_PER_BLOCK * (T::needs_scratch ? 2 : 1) * a.d * sizeof(double);
+    auto kern = hmc_pipe_kernel<T, EPL, LS, 2>;
+    if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
     return MCMCB200_OK;
@@ -255,17 +375,17 @@ template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch
             return MCMCB200_ERR_UNSUPPORTED;
         }
         if (a.rng.mode == RNG_PHILOX)
-            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, false, 0, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, false, 0, true>(a);
-        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, false, 0, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, false, 0, true>(a);
+            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, false, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, false, true>(a);
+        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, false, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, false, true>(a);
     }
     if (a.rng.mode == RNG_PHILOX) {
         // the unpredicated full-tile kernels exist for the production configuration: Philox, identity mass
         const bool ft = !DENSE_M && a.d == 32 * EPL && ((reinterpret_cast<uintptr_t>(a.x0) | reinterpret_cast<uintptr_t>(a.draws)) & 15) == 0;
         if (!DENSE_M && ft) {
             if (a.strict) return launch_one<T, EPL, false, true, RNG_PHILOX, true>(a);
-            // the most common trajectory lengths get fully unrolled, software-pipelined kernels
-            if (a.n_leap == 10) return launch_one<T, EPL, false, false, RNG_PHILOX, true, 10>(a);
-            return launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
+            // production configuration: the software-pipelined kernel; the most common trajectory length is unrolled
+            if (a.n_leap == 10) return launch_pipe<T, EPL, 10>(a);
+            return launch_pipe<T, EPL, 0>(a);
         }
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, false>(a);
     }
@@ -302,5 +422,6 @@ int launch_hmc(const HmcLaunch& a)
         return MCMCB200_ERR_UNKNOWN_TARGET;
     }
 }
+#endif  // MCMCB200_KERNEL_ONLY
 
 }  // namespace mcmcb200

@@ -181,7 +181,7 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
     const int dpad = (a.d + 1) & ~1;
     const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dpad * sizeof(double) : 0;
     auto kern = mala_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX>;
-    if (smem > 32 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
     return MCMCB200_OK;

@@ -12,12 +12,14 @@
 //   draw = -1 is the pre-loop draw of NUTS / RM-HMC.
 //   This replaces bmo::stats::rnorm_vec_inplace / runif (include/BaseMatrixOps/include/stats/rnorm.hpp:120-128,
 //   runif.hpp:93-99), whose std::mt19937_64 stream is inherently serial.  ln, sqrt, sin and cos are evaluated
-//   straight from the integer bits: 256-bin table + degree-7 log1p for ln, MUFU seed + one cubic step for sqrt,
-//   256-bin (cos, sin) table + a small-angle rotation for the angle — all accurate to a few ulp; the oracle
+//   straight from the integer bits: 512-bin table + degree-5 log1p for ln, MUFU seed + one cubic step for sqrt,
+//   512-bin (cos, sin) table + a small-angle rotation for the angle — all accurate to a few ulp; the oracle
 //   restates the formulas above with libm and agrees to <= 1e-14.
 // TAPE (parity): a flat per-chain stream of doubles consumed in order — the reference's own variates,
 //   replayed on the host (host_tape.cpp) or recorded by the caller.
 #pragma once
+
+#include <type_traits>
 
 #include "rng_args.h"
 #include "warp.cuh"
@@ -25,11 +27,11 @@
 namespace mcmcb200
 {
 
-constexpr int LOG_TAB_BITS = 8;
+constexpr int LOG_TAB_BITS = 9;
 constexpr int LOG_TAB_SIZE = 1 << LOG_TAB_BITS;  // double2 entries (1/c_i, -2 ln c_i)
-constexpr int ANG_TAB_BITS = 8;
+constexpr int ANG_TAB_BITS = 9;
 constexpr int ANG_TAB_SIZE = 1 << ANG_TAB_BITS;  // double2 entries (cos, sin) of the bin-centre angles
-constexpr int RNG_TAB_DOUBLE2 = LOG_TAB_SIZE + ANG_TAB_SIZE;  // 8 KB of shared memory per CTA
+constexpr int RNG_TAB_DOUBLE2 = LOG_TAB_SIZE + ANG_TAB_SIZE;  // 16 KB of shared memory per CTA
 constexpr double LN2 = 0.69314718055994530942;
 
 // Round keys come precomputed in the kernel-parameter (constant) bank.
@@ -51,18 +53,24 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
 // Polynomial coefficients live in constant memory (loaded once per use into a uniform register and shared by
 // the two Box-Muller pairs that are evaluated in lock-step).
 static __constant__ double RNG_C[16] = {
-    // q(r) = -2 log1p(r)/r, Horner from the r^6 term down     [0..6]
-    -2.0 / 7.0, 2.0 / 6.0, -2.0 / 5.0, 2.0 / 4.0, -2.0 / 3.0, 1.0, -2.0,
-    // [7] -2 ln 2   [8] 2^52 + 1076   [9] 2 pi 2^-52   [10] 2^52 + 2^43
-    -2.0 * 0.69314718055994530942, 4503599627370496.0 + 1076.0, 6.283185307179586476925 * 2.220446049250313e-16,
-    4503599627370496.0 + 8796093022208.0,
-    // sin(t)/t - 1 ~ t^2 (S0 + t^2 (S1 + t^2 S2)),  cos(t) - 1 ~ t^2 (C0 + t^2 (C1 + t^2 C2)) for |t| <= pi/256   [11..15]
-    -1.0 / 6.0, 1.0 / 120.0, -0.5, 1.0 / 24.0, -1.0 / 720.0};
+    // q(r) = -2 log1p(r)/r, Horner from the r^4 term down     [0..4]      (|r| <= 2^-9: truncation r^6/3 <= 2e-17)
+    -2.0 / 5.0, 2.0 / 4.0, -2.0 / 3.0, 1.0, -2.0,
+    // [5] -2 ln 2   [6] 2^52 + 1076   [7] 2^-52   [8] -(2^52 + 2^42) 2^-52 = -(1 + 2^-10)
+    -2.0 * 0.69314718055994530942, 4503599627370496.0 + 1076.0, 2.220446049250313e-16, -(1.0 + 0.0009765625),
+    // with f in turns, |f| <= 2^-10, w = f^2:
+    //   sin(2 pi f) = f (2 pi + w (S0 + w S1)),  S0 = -(2 pi)^3/6, S1 = (2 pi)^5/120     (next term 7e-20)     [9..11]
+    //   cos(2 pi f) - 1 = w (C0 + w C1),         C0 = -(2 pi)^2/2, C1 = (2 pi)^4/24      (next term 7e-17)     [12..13]
+    6.283185307179586476925, -41.341702240399760233968, 81.605249276075054203397,
+    -19.739208802178717237669, 64.939394022668291490944,
+    // sqrt refinement: [14] 0.375  [15] 0.5
+    0.375, 0.5};
 
 // Shared-memory tables, built once per CTA by its own threads:
-//   tab[i], i < 256:       (A_i, B_i) with A_i ~ 1/c_i, B_i = 2 ln A_i, c_i the centre of mantissa bin i of [1,2)
+//   tab[i], i < 512:       (A_i, B_i) with A_i ~ 1/c_i, B_i = 2 ln A_i, c_i the centre of mantissa bin i of [1,2)
 //                          (anchored to exactly 1 and 2 in the first / last bin so ln u stays accurate as u -> 1);
-//   tab[256 + j], j < 256: (cos, sin) of the centre of angle bin j, (j + 1/2) 2 pi / 256.
+//   tab[512 + j], j < 512: (cos, sin) of the angle 2 pi ((2j + 1)/1024 + 2^-53): the centre of angle bin j plus the
+//                          half-step of the (k2 + 1/2) grid, so that the in-bin offset (g - 2^42) 2^-52 is an exact
+//                          double obtained with ONE fma from the raw bits.
 __device__ __forceinline__ void build_rng_tables(double2* tab)
 {
     for (int i = threadIdx.x; i < LOG_TAB_SIZE; i += blockDim.x) {
@@ -82,7 +90,8 @@ __device__ __forceinline__ void build_rng_tables(double2* tab)
     }
     for (int j = threadIdx.x; j < ANG_TAB_SIZE; j += blockDim.x) {
         double sn, cs;
-        sincospi((2 * j + 1) * (1.0 / ANG_TAB_SIZE), &sn, &cs);  // angle / pi = (j + 1/2) * 2 / 256
+        // angle / pi = (2j + 1)/512 + 2^-52, exactly representable (< 2, 53 significant bits)
+        sincospi((2 * j + 1) * (1.0 / ANG_TAB_SIZE) + 2.220446049250313e-16, &sn, &cs);
         tab[LOG_TAB_SIZE + j] = make_double2(cs, sn);
     }
 }
@@ -103,39 +112,44 @@ struct BmPair {
         m = __hiloint2double((h & 0x000fffffu) | 0x3ff00000u, __double2loint(nd));  // mantissa in [1,2)
         le = tab[(h >> (20 - LOG_TAB_BITS)) & (LOG_TAB_SIZE - 1)];
         ed = __hiloint2double(0x43300000, static_cast<int>(h >> 20));              // 2^52 + biased exponent
-        // angle: k2 = (r2:r3) >> 12; top 8 bits pick the table bin, the low 44 bits g give the offset from its centre
+        // angle: k2 = (r2:r3) >> 12; top 9 bits pick the table bin, the low 43 bits g give the offset from its centre
         const unsigned k2_hi = r[2] >> 12, k2_lo = __funnelshift_r(r[3], r[2], 12);
         cssn = tab[LOG_TAB_SIZE + (k2_hi >> (20 - ANG_TAB_BITS))];
-        dl = __hiloint2double(0x43300000 | (k2_hi & 0xfffu), k2_lo);               // 2^52 + g, g < 2^44
+        dl = __hiloint2double(0x43300000 | (k2_hi & ((1u << (20 - ANG_TAB_BITS)) - 1u)), k2_lo);   // 2^52 + g, g < 2^43
     }
 };
 
 // Evaluate NP (1 or 2) staged pairs in lock-step: every constant is fetched once for all of them.
-template <int NP> __device__ __forceinline__ void bm_eval(BmPair (&b)[NP], double (&z0)[NP], double (&z1)[NP])
+// Per pair 26 fp64 instructions: ln 8, sqrt 5, angle 7, rotation + scaling 6.  Lout (optional) receives
+// L = -2 ln u1 = z0^2 + z1^2 up to rounding, so a caller with M = I gets the kinetic energy for free.
+template <int NP> __device__ __forceinline__ void bm_eval(BmPair (&b)[NP], double (&z0)[NP], double (&z1)[NP], double* Lout = nullptr)
 {
     double L[NP], R[NP];
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        b[i].ed = b[i].ed - RNG_C[8];                     // exponent - 1023 - 53
-        b[i].rr = fma(b[i].m, b[i].le.x, -1.0);           // m / c_i - 1, |rr| <= 2^-8
-        b[i].dl = b[i].dl - RNG_C[10];                    // g - 2^43, exact
+        b[i].ed = b[i].ed - RNG_C[6];                     // exponent - 1023 - 53
+        b[i].rr = fma(b[i].m, b[i].le.x, -1.0);           // m / c_i - 1, |rr| <= 2^-9
+        b[i].dl = fma(b[i].dl, 2.220446049250313e-16, -(1.0 + 0.0009765625));       // f = (g - 2^42) 2^-52 turns, exact, |f| <= 2^-10
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) b[i].q = RNG_C[0];
 #pragma unroll
-    for (int c = 1; c <= 6; ++c) {
+    for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, 0.5);          // 0.5, 1.0, -2.0: DFMA immediates
 #pragma unroll
-        for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, RNG_C[c]);
-    }
+    for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, RNG_C[2]);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, 1.0);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, -2.0);
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        b[i].t2 = fma(b[i].ed, RNG_C[7], b[i].le.y);       // -2 (E ln2 + ln c_i)
-        b[i].dl = b[i].dl * RNG_C[9] + 0.5 * RNG_C[9];     // delta = 2 pi (g - 2^43 + 1/2) 2^-52, |delta| <= pi/256
+        b[i].t2 = fma(b[i].ed, RNG_C[5], b[i].le.y);       // -2 (E ln2 + ln c_i)
         L[i] = fma(b[i].rr, b[i].q, b[i].t2);              // -2 ln u1
         b[i].z = b[i].dl * b[i].dl;
+        if (Lout) Lout[i] = L[i];
     }
-    // R = sqrt(L): MUFU.RSQ64H seed, one cubically convergent step (relative error ~ e^3 <= 2^-60), no slow path:
-    // L is a normal number in [2^-52, 75).
+    // R = sqrt(L) = t + t e (1/2 + 3/8 e), t = L y, e = 1 - t y, y = MUFU.RSQ64H seed: one cubically convergent step
+    // (relative error ~ e^3 <= 2^-60), no slow path: L is a normal number in [2^-52, 75).
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
         double y;
@@ -143,32 +157,150 @@ template <int NP> __device__ __forceinline__ void bm_eval(BmPair (&b)[NP], doubl
         const double t = L[i] * y;
         const double e = fma(-t, y, 1.0);
         const double pe = fma(e, 0.375, 0.5);
-        const double ye = y * e;
-        y = fma(ye, pe, y);
-        R[i] = L[i] * y;
+        const double te = t * e;
+        R[i] = fma(te, pe, t);
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        b[i].sd = fma(b[i].z, RNG_C[12], RNG_C[11]);        // sin(d)/d - 1 = z (S0 + z S1) (|d| <= 0.0123: next term 2e-18)
-        b[i].cd = fma(b[i].z, RNG_C[15], RNG_C[14]);
+        b[i].sd = fma(b[i].z, RNG_C[11], RNG_C[10]);        // S0 + w S1
+        b[i].cd = fma(b[i].z, RNG_C[13], RNG_C[12]);        // C0 + w C1
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        b[i].cd = fma(b[i].z, b[i].cd, RNG_C[13]);          // cos(d) - 1 = z (C0 + z (C1 + z C2))
-        b[i].sd = b[i].sd * b[i].z;
+        b[i].sd = fma(b[i].sd, b[i].z, RNG_C[9]);           // 2 pi + w (S0 + w S1)
+        b[i].cd = b[i].cd * b[i].z;                         // cos(d) - 1
     }
 #pragma unroll
     for (int i = 0; i < NP; ++i) {
-        const double cdm = b[i].cd * b[i].z;                // cos(d) - 1
-        const double sdv = fma(b[i].sd, b[i].dl, b[i].dl);  // sin(d)
-        const double C = b[i].cssn.x, S = b[i].cssn.y;
-        // cos(a + d) = C + (C cdm - S sdv),  sin(a + d) = S + (S cdm + C sdv)
-        const double cph = C + fma(C, cdm, -S * sdv);
-        const double sph = S + fma(S, cdm, C * sdv);
-        z0[i] = R[i] * cph;
-        z1[i] = R[i] * sph;
+        const double sdv = b[i].sd * b[i].dl;               // sin(d)
+        const double RC = R[i] * b[i].cssn.x, RS = R[i] * b[i].cssn.y;
+        // R cos(a + d) = RC + RC cdm - RS sdv,  R sin(a + d) = RS + RS cdm + RC sdv
+        z0[i] = fma(RC, b[i].cd, fma(-RS, sdv, RC));
+        z1[i] = fma(RS, b[i].cd, fma(RC, sdv, RS));
     }
 }
+
+template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>());
+        static_for<I + 1, N>(f);
+    }
+}
+
+// The same NP Box-Muller pairs as ChainRng::normals (identical arithmetic, identical results), cut into 16 units of
+// work that a caller interleaves by hand with other straight-line code (hmc_pipe_kernel: one slice per leapfrog step),
+// so that the integer Philox rounds and the short polynomial chains of the NEXT draw sit between the dependent DFMAs
+// of the CURRENT trajectory in program order.  Units 0-9: Philox round r of all pairs; 10: bits -> staged operands
+// (I2F, table loads), spare bits; 11-12: ln; 13: sqrt; 14: small-angle polynomials; 15: rotation + scaling.
+template <int NP> struct BmPipe {
+    static constexpr int N_UNITS = 16;
+    unsigned c[NP][4];
+    BmPair b[NP];
+    double L[NP], R[NP];
+    unsigned spare;
+
+    __device__ __forceinline__ void begin(int lane, long long draw, unsigned chain)
+    {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            c[i][0] = static_cast<unsigned>(i * 32 + lane);
+            c[i][1] = static_cast<unsigned>(draw + 1);
+            c[i][2] = chain;
+            c[i][3] = 0u;
+        }
+    }
+
+    // z: lane-striped normals (2*NP slots); lsum: sum over pairs of -2 ln u1
+    template <int U> __device__ __forceinline__ void unit(const RngArgs& a, const double2* __restrict__ tab, double (&z)[2 * NP], double& lsum)
+    {
+        if constexpr (U < 10) {
+            constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const unsigned hi0 = __umulhi(M0, c[i][0]), lo0 = M0 * c[i][0];
+                const unsigned hi1 = __umulhi(M1, c[i][2]), lo1 = M1 * c[i][2];
+                c[i][0] = hi1 ^ c[i][1] ^ a.rk[2 * U];
+                c[i][1] = lo1;
+                c[i][2] = hi0 ^ c[i][3] ^ a.rk[2 * U + 1];
+                c[i][3] = lo0;
+            }
+        } else if constexpr (U == 10) {
+            spare = ((c[0][1] & 0xfffu) << 12) | (c[0][3] & 0xfffu);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) b[i].setup(c[i], tab);
+        } else if constexpr (U == 11) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                b[i].ed = b[i].ed - RNG_C[6];
+                b[i].rr = fma(b[i].m, b[i].le.x, -1.0);
+                b[i].dl = fma(b[i].dl, 2.220446049250313e-16, -(1.0 + 0.0009765625));
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) b[i].q = fma(RNG_C[0], b[i].rr, 0.5);
+#pragma unroll
+            for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, RNG_C[2]);
+        } else if constexpr (U == 12) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                b[i].q = fma(b[i].q, b[i].rr, 1.0);
+                b[i].t2 = fma(b[i].ed, RNG_C[5], b[i].le.y);
+                b[i].z = b[i].dl * b[i].dl;
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                b[i].q = fma(b[i].q, b[i].rr, -2.0);
+                L[i] = fma(b[i].rr, b[i].q, b[i].t2);
+                lsum = (i == 0) ? L[0] : lsum + L[i];
+            }
+        } else if constexpr (U == 13) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                double y;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(L[i]));
+                const double t = L[i] * y;
+                const double e = fma(-t, y, 1.0);
+                const double pe = fma(e, 0.375, 0.5);
+                const double te = t * e;
+                R[i] = fma(te, pe, t);
+            }
+        } else if constexpr (U == 14) {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                b[i].sd = fma(b[i].z, RNG_C[11], RNG_C[10]);
+                b[i].cd = fma(b[i].z, RNG_C[13], RNG_C[12]);
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                b[i].sd = fma(b[i].sd, b[i].z, RNG_C[9]);
+                b[i].cd = b[i].cd * b[i].z;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const double sdv = b[i].sd * b[i].dl;
+                const double RC = R[i] * b[i].cssn.x, RS = R[i] * b[i].cssn.y;
+                z[2 * i] = fma(RC, b[i].cd, fma(-RS, sdv, RC));
+                z[2 * i + 1] = fma(RS, b[i].cd, fma(RC, sdv, RS));
+            }
+        }
+    }
+
+    // slice S of NS: units [S*16/NS, (S+1)*16/NS)
+    template <int S, int NS> __device__ __forceinline__ void slice(const RngArgs& a, const double2* __restrict__ tab, double (&z)[2 * NP], double& lsum)
+    {
+        constexpr int lo = S * N_UNITS / NS, hi = (S + 1) * N_UNITS / NS;
+        static_for<lo, hi>([&](auto u) { this->template unit<decltype(u)::value>(a, tab, z, lsum); });
+    }
+
+    // uniform #0 of the draw from the spare bits of blocks 0 and 1 (valid after unit 10); same definition as ChainRng::uniform
+    __device__ __forceinline__ double uniform0() const
+    {
+        const unsigned s0 = __shfl_sync(FULL, spare, 0), s1 = __shfl_sync(FULL, spare, 1);
+        const double sd = __hiloint2double(0x43300000 | (s0 >> 8), (s0 << 24) | s1) - 4503599627370496.0;
+        return fma(sd, 3.5527136788005009e-15, 1.7763568394002505e-15);
+    }
+};
 
 // per-chain RNG cursor; MODE is RNG_PHILOX or RNG_TAPE (compile time)
 template <int MODE> struct ChainRng {
@@ -190,8 +322,9 @@ template <int MODE> struct ChainRng {
     // segment, seg_off = first element of the segment, d_total = n_dim of the chain (d is the segment's length).
     template <int EPL, bool FT>
     __device__ __forceinline__ void normals(const RngArgs& a, long long draw, int d, int lane, const double2* __restrict__ tab,
-                                            double (&z)[EPL], int q_base = 0, int seg_off = 0, int d_total = -1)
+                                            double (&z)[EPL], int q_base = 0, int seg_off = 0, int d_total = -1, double* lsum = nullptr)
     {
+        // lsum (Philox, full tiles only): receives sum over this lane's pairs of L = -2 ln u1 (= sum z^2 up to rounding)
         if (MODE == RNG_PHILOX) {
             constexpr int NPAIR = EPL / 2;
 #pragma unroll
@@ -209,7 +342,9 @@ template <int MODE> struct ChainRng {
                         if (m0 + i == 0) spare = ((r[1] & 0xfffu) << 12) | (r[3] & 0xfffu);
                         b[i].setup(r, tab);
                     }
-                    bm_eval<2>(b, z0, z1);
+                    double Lp[2];
+                    bm_eval<2>(b, z0, z1, lsum ? Lp : nullptr);
+                    if (lsum) *lsum = (m0 == 0) ? Lp[0] + Lp[1] : *lsum + (Lp[0] + Lp[1]);
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
                         const int q = (m0 + i) * 32 + lane;
@@ -224,7 +359,9 @@ template <int MODE> struct ChainRng {
                     philox4x32_10(static_cast<unsigned>(q_base + q), static_cast<unsigned>(draw + 1), chain, 0u, a, r);
                     if (m0 == 0) spare = ((r[1] & 0xfffu) << 12) | (r[3] & 0xfffu);
                     b[0].setup(r, tab);
-                    bm_eval<1>(b, z0, z1);
+                    double Lp[1];
+                    bm_eval<1>(b, z0, z1, lsum ? Lp : nullptr);
+                    if (lsum) *lsum = (m0 == 0) ? Lp[0] : *lsum + Lp[0];
                     z[2 * m0] = (FT || 2 * q < d) ? z0[0] : 0.0;
                     z[2 * m0 + 1] = (FT || 2 * q + 1 < d) ? z1[0] : 0.0;
                 }
