@@ -324,9 +324,9 @@ def main():
                        "l2": "256 MiB buffer (2x L2) written between timed iterations; each step also writes 4.19 GB of draws (33x L2)",
                        "accept_rate": acc_rate, "wall_ms_per_step_rank0": wall / args.steps * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "hmc_kernel<IsoGauss,EPL=4>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "hmc_pipe_kernel<IsoGauss,EPL=4,L=10>",
                          "kernel_ms": kernel_avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "2*d*8 B per transition x chains x draws per launch; fp64 pipe is the co-roof (DESIGN.md)"},
+                         "note": "2*d*8 B per transition x chains x draws per launch; fp64 instruction dispatch is the co-roof (DESIGN.md §4.1)"},
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         if gather is not None:

@@ -12,7 +12,9 @@
  *   mcmcb200_nuts_run   <- bool mcmc::nuts (...)   include/mcmc/nuts.hpp:43-72,  src/nuts.cpp:30-359
  *   mcmcb200_rmhmc_run  <- bool mcmc::rmhmc(..., tensor_fn, ..., tensor_data, settings)
  *                          include/mcmc/rmhmc.hpp:47-86, src/rmhmc.cpp:30-325
- *   mcmcb200_*_settings <- hmc_/mala_/nuts_/rmhmc_settings_t + algo_settings_t
+ *   mcmcb200_rwmh_run   <- bool mcmc::rwmh (initial_vals, target_log_kernel (value only), draws_out, target_data, settings)
+ *                          include/mcmc/rwmh.hpp:43-72, src/rwmh.cpp:30-199   (the gradient-free sibling)
+ *   mcmcb200_*_settings <- hmc_/mala_/nuts_/rmhmc_/rwmh_settings_t + algo_settings_t
  *                          include/misc/mcmc_structs.hpp:66-134,151-184 (same field names and defaults)
  *
  * Differences forced by the device boundary:
@@ -71,7 +73,7 @@ typedef enum {
     MCMCB200_RNG_PHILOX = 0,       /* counter-based Philox4x32-10 generated in-kernel (production mode) */
     MCMCB200_RNG_MT19937_TAPE = 1, /* reference stream: the library replays std::mt19937_64(seed + chain) through
                                       the reference's BaseMatrixOps rnorm/runif semantics on the host and the
-                                      kernel consumes that tape (drop-in parity mode; HMC/MALA/RM-HMC) */
+                                      kernel consumes that tape (drop-in parity mode; HMC/MALA/RM-HMC/RWMH) */
     MCMCB200_RNG_USER_TAPE = 2     /* caller-supplied stream of doubles per chain, consumed in order */
 } mcmcb200_rng_mode_t;
 
@@ -161,6 +163,16 @@ typedef struct mcmcb200_rmhmc_settings {
     int32_t arith;
 } mcmcb200_rmhmc_settings_t;
 
+/* rwmh_settings_t (mcmc_structs.hpp:138-149) */
+typedef struct mcmcb200_rwmh_settings {
+    int64_t n_burnin_draws; /* default 1000 */
+    int64_t n_keep_draws;   /* default 1000 */
+    double par_scale;       /* default 1.0  */
+    const double* cov_mat;  /* HOST, n_dim^2 column-major proposal covariance, or NULL -> identity (src/rwmh.cpp:57) */
+    int32_t chol_mode;      /* mcmcb200_chol_t */
+    int32_t arith;          /* mcmcb200_arith_t */
+} mcmcb200_rwmh_settings_t;
+
 typedef struct mcmcb200_output {
     double* draws_out;       /* [n_chains][n_keep_draws][n_dim] */
     int32_t draws_mem;       /* mcmcb200_mem_t */
@@ -179,6 +191,7 @@ void mcmcb200_hmc_settings_default(mcmcb200_hmc_settings_t* s);
 void mcmcb200_mala_settings_default(mcmcb200_mala_settings_t* s);
 void mcmcb200_nuts_settings_default(mcmcb200_nuts_settings_t* s);
 void mcmcb200_rmhmc_settings_default(mcmcb200_rmhmc_settings_t* s);
+void mcmcb200_rwmh_settings_default(mcmcb200_rwmh_settings_t* s);
 
 int mcmcb200_hmc_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
                      const mcmcb200_hmc_settings_t* settings, mcmcb200_output_t* out);
@@ -188,6 +201,9 @@ int mcmcb200_nuts_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* r
                       const mcmcb200_nuts_settings_t* settings, mcmcb200_output_t* out);
 int mcmcb200_rmhmc_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
                        const mcmcb200_rmhmc_settings_t* settings, mcmcb200_output_t* out);
+
+int mcmcb200_rwmh_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
+                      const mcmcb200_rwmh_settings_t* settings, mcmcb200_output_t* out);
 
 /* Target registry: id by name ("iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model"), -1 if unknown;
    number of doubles the target's data blob must hold for a given n_dim (-1 if unknown / n_dim invalid). */

@@ -10,7 +10,7 @@
 //        Mat_t& draws_out, void* target_data                void* target_data /* mcmc::kernel_data* */
 //        [, algo_settings_t& settings]);                    [, algo_settings_t& settings]);
 //
-// and likewise mcmc::mala / mcmc::nuts / mcmc::rmhmc (rmhmc's tensor_fn / tensor_data arguments are kept for arity;
+// and likewise mcmc::mala / mcmc::nuts / mcmc::rmhmc / mcmc::rwmh (rmhmc's tensor_fn / tensor_data arguments are kept for arity;
 // the metric is the one registered with the kernel).  A std::function cannot run on the GPU, so the second argument
 // names a REGISTERED __device__ functor (mcmc::device_kernel("iso_gauss"), ...) and `target_data` points to a
 // mcmc::kernel_data {values, n} that the library copies to the device.
@@ -28,7 +28,7 @@
 //     device ordinal.
 //
 // Box constraints (vals_bound / lower_bounds / upper_bounds, +-inf = open side) run on the device path for M = I
-// (HMC, NUTS, MALA) and for RM-HMC.  Unsupported combinations fail loudly: bounds together with a precond_mat, or on
+// (HMC, NUTS, MALA), for RM-HMC and for RWMH (with or without a cov_mat).  Unsupported combinations fail loudly: bounds together with a precond_mat, or on
 // the wide (n_vals > 512) kernels, make the call return false with mcmc::last_error() set; nothing is ever silently
 // ignored and nothing is computed on the host.
 //
@@ -192,6 +192,14 @@ struct mala_settings_t {
     Mat_t precond_mat;
     size_t n_accept_draws = 0;
 };
+struct rwmh_settings_t {   // mcmc_structs.hpp:138-149
+    size_t n_burnin_draws = 1E03;
+    size_t n_keep_draws = 1E03;
+    int omp_n_threads = -1;
+    fp_t par_scale = 1.0;
+    Mat_t cov_mat;
+    size_t n_accept_draws = 0;
+};
 struct b200_settings_t {
     int rng_mode = MCMCB200_RNG_MT19937_TAPE;  // reference-compatible stream by default (NUTS: Philox, see nuts())
     int arith = MCMCB200_ARITH_FAST;
@@ -208,6 +216,7 @@ struct algo_settings_t {
     nuts_settings_t nuts_settings;
     rmhmc_settings_t rmhmc_settings;
     mala_settings_t mala_settings;
+    rwmh_settings_t rwmh_settings;
     b200_settings_t b200;
 };
 
@@ -392,6 +401,50 @@ inline bool mala(const Mat_t& initial_vals, registered_kernel target_log_kernel,
                  algo_settings_t& settings)
 {
     return internal::mala_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
+                               target_log_kernel, target_data, &settings, nullptr, &draws_out);
+}
+
+// ================================================= RWMH ======================================================
+// bool mcmc::rwmh(initial_vals, target_log_kernel (value only: std::function<fp_t(const ColVec_t&, void*)>), draws_out,
+//                 target_data[, settings])   include/mcmc/rwmh.hpp:43-72, src/rwmh.cpp:176-199
+namespace internal
+{
+inline bool rwmh_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
+                      Cube_t* cube)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.rwmh_settings.n_keep_draws, s.b200.rng_mode, single, cube,
+                            &s.rwmh_settings.n_accept_draws,
+                            [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
+                                mcmcb200_rwmh_settings_t m;
+                                mcmcb200_rwmh_settings_default(&m);
+                                m.n_burnin_draws = static_cast<int64_t>(st.rwmh_settings.n_burnin_draws);
+                                m.n_keep_draws = static_cast<int64_t>(st.rwmh_settings.n_keep_draws);
+                                m.par_scale = st.rwmh_settings.par_scale;
+                                m.cov_mat = b200_detail::precond_or_null(st.rwmh_settings.cov_mat, d);
+                                m.chol_mode = st.b200.chol_mode;
+                                m.arith = st.b200.arith;
+                                return mcmcb200_rwmh_run(&pr, &rng, &m, &out);
+                            });
+}
+}  // namespace internal
+
+inline bool rwmh(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data)
+{
+    return internal::rwmh_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr,
+                               &draws_out, nullptr);
+}
+inline bool rwmh(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Mat_t& draws_out, void* target_data,
+                 algo_settings_t& settings)
+{
+    return internal::rwmh_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data,
+                               &settings, &draws_out, nullptr);
+}
+inline bool rwmh(const Mat_t& initial_vals, registered_kernel target_log_kernel, Cube_t& draws_out, void* target_data,
+                 algo_settings_t& settings)
+{
+    return internal::rwmh_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
                                target_log_kernel, target_data, &settings, nullptr, &draws_out);
 }
 

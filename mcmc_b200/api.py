@@ -46,6 +46,11 @@ class MalaSettings(ctypes.Structure):
                 ("chol_mode", c_i32), ("arith", c_i32)]
 
 
+class RwmhSettings(ctypes.Structure):
+    _fields_ = [("n_burnin_draws", c_i64), ("n_keep_draws", c_i64), ("par_scale", c_dbl), ("cov_mat", c_vp),
+                ("chol_mode", c_i32), ("arith", c_i32)]
+
+
 class NutsSettings(ctypes.Structure):
     _fields_ = [("n_burnin_draws", c_i64), ("n_keep_draws", c_i64), ("n_adapt_draws", c_i64),
                 ("target_accept_rate", c_dbl), ("max_tree_depth", c_i64), ("step_size", c_dbl), ("gamma_val", c_dbl),
@@ -82,7 +87,7 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mcmcb200_last_error.restype = ctypes.c_char_p
     lib.mcmcb200_target_data_len.restype = c_i64
-    for f in ("hmc", "mala", "nuts", "rmhmc"):
+    for f in ("hmc", "mala", "nuts", "rmhmc", "rwmh"):
         getattr(lib, "mcmcb200_%s_run" % f).restype = ctypes.c_int
     _lib = lib
     return lib
@@ -214,6 +219,17 @@ def mala(initial_vals, target, step_size=1.0, precond_mat=None, chol_mode=CHOL_E
     return run.result()
 
 
+def rwmh(initial_vals, target, par_scale=1.0, cov_mat=None, chol_mode=CHOL_EIGEN_LLT, arith=ARITH_FAST, **kw):
+    """Many-chain mcmc::rwmh (src/rwmh.cpp:176-199): proposal x + par_scale * chol(cov_mat) z, value-only target."""
+    c = _split(kw)
+    assert not kw, kw
+    run = _Run("rwmh", initial_vals, target, **c)
+    cm = _colmajor(cov_mat)
+    st = RwmhSettings(c["n_burnin"], c["n_keep"], float(par_scale), _np_ptr(cm), chol_mode, arith)
+    _check(run.lib.mcmcb200_rwmh_run(ctypes.byref(run.problem), ctypes.byref(run.rng), ctypes.byref(st), ctypes.byref(run.out)))
+    return run.result()
+
+
 def nuts(initial_vals, target, step_size=1.0, n_adapt_draws=1000, target_accept_rate=0.55, max_tree_depth=10,
          gamma_val=0.05, t0_val=10.0, kappa_val=0.75, precond_mat=None, chol_mode=CHOL_EIGEN_LLT, arith=ARITH_FAST, **kw):
     """Many-chain mcmc::nuts (src/nuts.cpp:336-359)."""
@@ -271,7 +287,7 @@ def device_count():
 EXPORTED_SYMBOLS = [
     "mcmcb200_hmc_settings_default", "mcmcb200_mala_settings_default", "mcmcb200_nuts_settings_default",
     "mcmcb200_rmhmc_settings_default", "mcmcb200_hmc_run", "mcmcb200_mala_run", "mcmcb200_nuts_run",
-    "mcmcb200_rmhmc_run", "mcmcb200_target_lookup", "mcmcb200_target_data_len", "mcmcb200_target_eval",
+    "mcmcb200_rmhmc_run", "mcmcb200_rwmh_settings_default", "mcmcb200_rwmh_run", "mcmcb200_target_lookup", "mcmcb200_target_data_len", "mcmcb200_target_eval",
     "mcmcb200_mt19937_tape", "mcmcb200_philox_stream", "mcmcb200_last_error", "mcmcb200_device_count",
     "mcmcb200_release_workspace",
 ]

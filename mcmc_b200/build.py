@@ -17,7 +17,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcmc_b200.so")
 
-CU_SOURCES = ["engine.cu", "hmc.cu", "hmc_wide.cu", "mala.cu", "mala_wide.cu", "nuts.cu", "rmhmc.cu", "util_kernels.cu"]
+CU_SOURCES = ["engine.cu", "dispatch.cu", "hmc_wide.cu", "mala_wide.cu", "rmhmc.cu", "util_kernels.cu"]
+# compiled once per registered target (-DMCMCB200_TARGET_SLICE=k), so the big template fan-out builds in parallel
+SLICED_SOURCES = ["hmc.cu", "nuts.cu", "mala.cu", "rwmh.cu"]
+N_TARGETS = 5
 CPP_SOURCES = ["host_tape.cpp", "host_linalg.cpp"]
 
 NVCC_FLAGS = [
@@ -61,17 +64,25 @@ def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
     headers = _headers()
-    flags = NVCC_FLAGS + (["-DMCMCB200_FAST_BUILD"] if os.environ.get("MCMCB200_FAST_BUILD") == "1" else [])
-    jobs = []
-    for src in CU_SOURCES + CPP_SOURCES:
+    fast = os.environ.get("MCMCB200_FAST_BUILD") == "1"
+    units = []  # (source, object name, extra flags); the slowest translation units first
+    for src in SLICED_SOURCES:
+        for k in ([0] if fast else range(N_TARGETS)):
+            units.append((src, "%s.t%d.o" % (src, k), ["-DMCMCB200_TARGET_SLICE=%d" % k]))
+    units += [(src, src + ".o", []) for src in CU_SOURCES + CPP_SOURCES]
+    base = NVCC_FLAGS + (["-DMCMCB200_FAST_BUILD"] if fast else [])
+    jobs, objs = [], []
+    for src, oname, extra in units:
         path = os.path.join(CSRC, src)
-        obj = os.path.join(OBJ, src + ".o")
+        obj = os.path.join(OBJ, oname)
+        objs.append(obj)
+        flags = base + extra
         stamp_file = obj + ".stamp"
         stamp = _stamp([path] + headers, flags)
         if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
             continue
         cmd = [nvcc, "-ccbin", _host_cxx()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
-        jobs.append((cmd, stamp_file, stamp, src))
+        jobs.append((cmd, stamp_file, stamp, oname))
 
     def run(job):
         cmd, stamp_file, stamp, src = job
@@ -82,12 +93,11 @@ def build(verbose=False, force=False):
             f.write(stamp)
         return src, r.stderr
 
-    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+    with ThreadPoolExecutor(max_workers=min(os.cpu_count() or 4, max(1, len(jobs)))) as ex:
         for src, log in ex.map(run, jobs):
             if verbose:
                 sys.stderr.write("== %s\n%s\n" % (src, log))
 
-    objs = [os.path.join(OBJ, s + ".o") for s in CU_SOURCES + CPP_SOURCES]
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-ccbin", _host_cxx(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
                "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-lpthread"]

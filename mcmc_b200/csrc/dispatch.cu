@@ -1,0 +1,44 @@
+// By-target dispatch for the samplers whose kernels are compiled one translation unit per registered target
+// (hmc.cu, mala.cu, nuts.cu, rwmh.cu with -DMCMCB200_TARGET_SLICE=k, see mcmc_b200/build.py): parallel compilation only,
+// no behavioural content.
+#include "engine.h"
+
+namespace mcmcb200
+{
+
+#ifdef MCMCB200_FAST_BUILD   // developer build: only target 0 is compiled
+#define MCMCB200_SLICE_OR_MISSING(call) \
+    (set_error("this developer build (MCMCB200_FAST_BUILD) only contains the iso_gauss target"), MCMCB200_ERR_UNKNOWN_TARGET)
+#else
+#define MCMCB200_SLICE_OR_MISSING(call) call
+#endif
+
+#define DECL(k)                                        \
+    int launch_hmc_slice##k(const HmcLaunch& a);       \
+    int launch_mala_slice##k(const MalaLaunch& a);     \
+    int launch_nuts_slice##k(const NutsLaunch& a);     \
+    int launch_rwmh_slice##k(const RwmhLaunch& a);
+DECL(0)
+#ifndef MCMCB200_FAST_BUILD
+DECL(1) DECL(2) DECL(3) DECL(4)
+#endif
+#undef DECL
+
+#define DISPATCH(fn, what)                                                   \
+    switch (a.target_id) {                                                   \
+    case 0: return fn##_slice0(a);                                           \
+    case 1: return MCMCB200_SLICE_OR_MISSING(fn##_slice1(a));                                         \
+    case 2: return MCMCB200_SLICE_OR_MISSING(fn##_slice2(a));                                         \
+    case 3: return MCMCB200_SLICE_OR_MISSING(fn##_slice3(a));                                         \
+    case 4: return MCMCB200_SLICE_OR_MISSING(fn##_slice4(a));                                         \
+    default:                                                                 \
+        set_error(what ": unknown target id %d", a.target_id);               \
+        return MCMCB200_ERR_UNKNOWN_TARGET;                                  \
+    }
+
+int launch_hmc(const HmcLaunch& a) { DISPATCH(launch_hmc, "hmc") }
+int launch_mala(const MalaLaunch& a) { DISPATCH(launch_mala, "mala") }
+int launch_nuts(const NutsLaunch& a) { DISPATCH(launch_nuts, "nuts") }
+int launch_rwmh(const RwmhLaunch& a) { DISPATCH(launch_rwmh, "rwmh") }
+
+}  // namespace mcmcb200

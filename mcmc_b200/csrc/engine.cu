@@ -353,6 +353,16 @@ void mcmcb200_rmhmc_settings_default(mcmcb200_rmhmc_settings_t* s)
     s->arith = MCMCB200_ARITH_FAST;
 }
 
+void mcmcb200_rwmh_settings_default(mcmcb200_rwmh_settings_t* s)
+{
+    std::memset(s, 0, sizeof(*s));
+    s->n_burnin_draws = 1000;  // mcmc_structs.hpp:138-149
+    s->n_keep_draws = 1000;
+    s->par_scale = 1.0;
+    s->chol_mode = MCMCB200_CHOL_EIGEN_LLT;
+    s->arith = MCMCB200_ARITH_FAST;
+}
+
 int mcmcb200_hmc_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, const mcmcb200_hmc_settings_t* st,
                      mcmcb200_output_t* out)
 {
@@ -429,6 +439,42 @@ int mcmcb200_mala_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, c
     if (out->step_size_out)
         for (long long c = 0; c < pr->n_chains; ++c) out->step_size_out[c] = st->step_size;
     return finish_common(s, out, launches);
+}
+
+int mcmcb200_rwmh_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, const mcmcb200_rwmh_settings_t* st,
+                      mcmcb200_output_t* out)
+{
+    if (!st) { set_error("null settings"); return MCMCB200_ERR_INVALID_ARG; }
+    Staged s;
+    int rc = stage_common(s, pr, rng, st->arith, st->n_burnin_draws, st->n_keep_draws, 0, true, out);
+    if (rc) return rc;
+    RwmhLaunch a;
+    static_cast<CommonLaunch&>(a) = s.c;
+    a.n_burnin = st->n_burnin_draws;
+    a.n_keep = st->n_keep_draws;
+    a.par_scale = st->par_scale;
+    a.S_cm = nullptr;
+    if (st->cov_mat) {
+        // cov_mcmc_chol = par_scale * chol(cov_mat), materialised once (src/rwmh.cpp:116)
+        const int d = pr->n_dim;
+        const size_t nn = (size_t)d * d;
+        std::vector<double> S(nn);
+        if (!host_cholesky_colmajor(st->cov_mat, d, st->chol_mode, S.data())) {
+            set_error("cov_mat is not positive definite");
+            return MCMCB200_ERR_INVALID_ARG;
+        }
+        for (size_t k = 0; k < nn; ++k) S[k] = st->par_scale * S[k];
+        if ((rc = upload(s.scope.dev, SLOT_MAT_A, S.data(), nn, s.stream, &a.S_cm))) return rc;
+        MCMCB200_CUDA_TRY(cudaStreamSynchronize(s.stream));
+    }
+    MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
+    if ((rc = launch_rwmh(a))) return rc;
+    MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
+    if (out->n_leapfrog_out)
+        for (long long c = 0; c < pr->n_chains; ++c) out->n_leapfrog_out[c] = 0;
+    if (out->step_size_out)
+        for (long long c = 0; c < pr->n_chains; ++c) out->step_size_out[c] = st->par_scale;
+    return finish_common(s, out, 1);
 }
 
 int mcmcb200_nuts_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, const mcmcb200_nuts_settings_t* st,

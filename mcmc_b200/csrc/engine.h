@@ -49,6 +49,12 @@ struct MalaLaunch : CommonLaunch {
     const double* SigInv_cm;  // (eps^2 M)^-1
 };
 
+struct RwmhLaunch : CommonLaunch {
+    long long n_burnin, n_keep;
+    double par_scale;
+    const double* S_cm;       // par_scale * chol(cov_mat), column-major, or null for cov = I
+};
+
 struct NutsLaunch : CommonLaunch {
     long long n_burnin, n_keep, n_adapt;
     int max_depth;
@@ -92,6 +98,7 @@ bool mala_wide_supported(int target_id, int d, bool has_precond);
 long long mala_wide_work_doubles(long long n_chains, int d);
 int launch_mala_wide(const MalaLaunch& a, double* work, int* launches);
 int launch_nuts(const NutsLaunch& a);
+int launch_rwmh(const RwmhLaunch& a);
 int launch_rmhmc(const RmhmcLaunch& a);
 int launch_target_eval(const EvalLaunch& a);
 int launch_philox_stream(unsigned long long seed, long long chain, long long draw, int d, int n_unif, double* out_dev,

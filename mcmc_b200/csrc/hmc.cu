@@ -273,6 +273,11 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
     }
 
     // one transition; p holds z_t on entry (consumed), (zn, un, kn) receive the variates of draw t + 1
+#ifndef MCMCB200_PIPE_TAIL
+#define MCMCB200_PIPE_TAIL 5   // measured on B200 (tools/c2_variants.cu): 0 -> 2.23 ms, 2 -> 2.18, 3/4 -> 2.10, 5 -> 2.08 ms
+#endif
+    constexpr int TAIL = LS > 0 ? MCMCB200_PIPE_TAIL : 0;   // slices of RNG work deferred to the butterfly
+    constexpr int NS = (LS > 0 ? LS : 1) + TAIL;
     auto draw = [&](int t, double (&p)[EPL], double u, double ksum, double (&zn)[EPL], double& un, double& kn, auto keep) {
         // the variates of draw t + 1 (one spare draw past the end: harmless), generated slice by slice between the
         // leapfrog steps below when the trajectory length is a compile-time constant
@@ -296,7 +301,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             if (LS > 0) {
                 static_for<0, LS>([&](auto sc) {
                     constexpr int s = decltype(sc)::value;
-                    bp.template slice<s, (LS > 0 ? LS : 1)>(a.rng, rng_tab, zn, kn);
+                    bp.template slice<s, NS>(a.rng, rng_tab, zn, kn);
                     step(s);
                 });
             } else {
@@ -307,7 +312,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             kick_half<EPL, false, false>(p, g, g, eps, heps);
             // dH = (U0 + K0) - (U1 + K1), one butterfly.  u < exp(min(0.01, dH)) holds whenever u < 1 + dH (<= exp(dH);
             // also dH = +inf, src/hmc.cpp:187), so exp() is evaluated only in the thin band 1 + dH <= u; a NaN rejects.
-            dH = warp_sum<false>(fma(-0.5, lane_dot<EPL, false>(p, p), dH - U1));
+            dH = fma(-0.5, lane_dot<EPL, false>(p, p), dH - U1);
+            static_for<0, 5>([&](auto st) {   // the butterfly, with the last slices of the next draw's variates in its shadow
+                constexpr int k = decltype(st)::value;
+                dH += __shfl_xor_sync(FULL, dH, 16 >> k);
+                if constexpr (k < TAIL) bp.template slice<(LS > 0 ? LS : 1) + k, NS>(a.rng, rng_tab, zn, kn);
+            });
             acc = u < 1.0 + dH;
             if (!acc) acc = (fabs(dH) <= 1.7976931348623157e308) && (u < exp(dH));
             restore_if<EPL>(home, lane, x, !acc);
@@ -360,7 +370,7 @@ template <class T, int EPL, int LS> static int launch_pipe(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const size_t smem = (size_t)WARPS_PER_BLOCK * (T::needs_scratch ? 2 : 1) * a.d * sizeof(double);
-    auto kern = hmc_pipe_kernel<T, EPL, LS, 2>;
+    auto kern = hmc_pipe_kernel<T, EPL, LS, 1>;   // UNR = 2 is slower on B200 (instruction cache): 2.33 vs 2.23 ms
     if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -384,7 +394,7 @@ template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch
         if (!DENSE_M && ft) {
             if (a.strict) return launch_one<T, EPL, false, true, RNG_PHILOX, true>(a);
             // production configuration: the software-pipelined kernel; the most common trajectory length is unrolled
-            if (a.n_leap == 10) return launch_pipe<T, EPL, 10>(a);
+            if (a.n_leap == 10 && T::separable) return launch_pipe<T, EPL, 10>(a);
             return launch_pipe<T, EPL, 0>(a);
         }
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, false>(a);
@@ -410,7 +420,7 @@ template <class T> static int launch_target(const HmcLaunch& a)
     }
 }
 
-int launch_hmc(const HmcLaunch& a)
+int MCMCB200_SLICED(launch_hmc)(const HmcLaunch& a)
 {
     switch (a.target_id) {
 #define X(ID, TYPE) \

@@ -217,7 +217,7 @@ template <class T> static int launch_target(const MalaLaunch& a)
     }
 }
 
-int launch_mala(const MalaLaunch& a)
+int MCMCB200_SLICED(launch_mala)(const MalaLaunch& a)
 {
     switch (a.target_id) {
 #define X(ID, TYPE) \

@@ -31,12 +31,14 @@ static __host__ __device__ int nuts_m_max(int max_depth)
     return 1 + j * (j + 1) / 2;
 }
 
+#if !defined(MCMCB200_TARGET_SLICE) || MCMCB200_TARGET_SLICE == 0   // one definition across the per-target translation units
 long long nuts_work_doubles_per_chain(int d, int max_depth)
 {
     const long long dp = (d + 1) & ~1;
     const long long m = nuts_m_max(max_depth);
     return 6 * dp + 2 * dp * m + 2 * m + 2;
 }
+#endif
 
 constexpr int NUTS_MAX_LEVELS = 22;
 
@@ -400,7 +402,7 @@ template <class T> static int launch_target(const NutsLaunch& a)
     }
 }
 
-int launch_nuts(const NutsLaunch& a)
+int MCMCB200_SLICED(launch_nuts)(const NutsLaunch& a)
 {
     switch (a.target_id) {
 #define X(ID, TYPE) \

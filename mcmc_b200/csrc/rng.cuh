@@ -188,13 +188,22 @@ template <int I, int N, class F> __device__ __forceinline__ void static_for(F&& 
     }
 }
 
-// The same NP Box-Muller pairs as ChainRng::normals (identical arithmetic, identical results), cut into 16 units of
+// The same NP Box-Muller pairs as ChainRng::normals (identical arithmetic, identical results), cut into 20 units of
 // work that a caller interleaves by hand with other straight-line code (hmc_pipe_kernel: one slice per leapfrog step),
 // so that the integer Philox rounds and the short polynomial chains of the NEXT draw sit between the dependent DFMAs
-// of the CURRENT trajectory in program order.  Units 0-9: Philox round r of all pairs; 10: bits -> staged operands
-// (I2F, table loads), spare bits; 11-12: ln; 13: sqrt; 14: small-angle polynomials; 15: rotation + scaling.
+// of the CURRENT trajectory in program order.  Units 0-9: Philox round r of all pairs; 10-11: bits -> staged operands
+// (I2F, table loads; first / second half of the pairs), spare bits; 12-15: ln; 16: sqrt; 17-18: small-angle
+// polynomials; 19: rotation + scaling.  slice<S, NS>() runs the units whose cumulative issue cost (UNIT_COST, in
+// dispatch cycles: fp64 = 2, everything else = 1) starts inside the S-th of NS equal shares.
 template <int NP> struct BmPipe {
-    static constexpr int N_UNITS = 16;
+    static constexpr int N_UNITS = 20;
+    static constexpr int UNIT_COST[N_UNITS] = {8, 8, 8, 8, 8, 8, 8, 8, 8, 8, 17, 17, 12, 8, 12, 10, 22, 8, 8, 24};
+    static constexpr int cost_before(int u)
+    {
+        int c = 0;
+        for (int i = 0; i < u; ++i) c += UNIT_COST[i];
+        return c;
+    }
     unsigned c[NP][4];
     BmPair b[NP];
     double L[NP], R[NP];
@@ -214,6 +223,7 @@ template <int NP> struct BmPipe {
     // z: lane-striped normals (2*NP slots); lsum: sum over pairs of -2 ln u1
     template <int U> __device__ __forceinline__ void unit(const RngArgs& a, const double2* __restrict__ tab, double (&z)[2 * NP], double& lsum)
     {
+        constexpr int H = (NP + 1) / 2;   // pairs staged by unit 10; the rest by unit 11
         if constexpr (U < 10) {
             constexpr unsigned M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
 #pragma unroll
@@ -228,32 +238,37 @@ template <int NP> struct BmPipe {
         } else if constexpr (U == 10) {
             spare = ((c[0][1] & 0xfffu) << 12) | (c[0][3] & 0xfffu);
 #pragma unroll
-            for (int i = 0; i < NP; ++i) b[i].setup(c[i], tab);
+            for (int i = 0; i < H; ++i) b[i].setup(c[i], tab);
         } else if constexpr (U == 11) {
+#pragma unroll
+            for (int i = H; i < NP; ++i) b[i].setup(c[i], tab);
+        } else if constexpr (U == 12) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 b[i].ed = b[i].ed - RNG_C[6];
                 b[i].rr = fma(b[i].m, b[i].le.x, -1.0);
                 b[i].dl = fma(b[i].dl, 2.220446049250313e-16, -(1.0 + 0.0009765625));
             }
+        } else if constexpr (U == 13) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) b[i].q = fma(RNG_C[0], b[i].rr, 0.5);
 #pragma unroll
             for (int i = 0; i < NP; ++i) b[i].q = fma(b[i].q, b[i].rr, RNG_C[2]);
-        } else if constexpr (U == 12) {
+        } else if constexpr (U == 14) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 b[i].q = fma(b[i].q, b[i].rr, 1.0);
                 b[i].t2 = fma(b[i].ed, RNG_C[5], b[i].le.y);
                 b[i].z = b[i].dl * b[i].dl;
             }
+        } else if constexpr (U == 15) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 b[i].q = fma(b[i].q, b[i].rr, -2.0);
                 L[i] = fma(b[i].rr, b[i].q, b[i].t2);
                 lsum = (i == 0) ? L[0] : lsum + L[i];
             }
-        } else if constexpr (U == 13) {
+        } else if constexpr (U == 16) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 double y;
@@ -264,12 +279,13 @@ template <int NP> struct BmPipe {
                 const double te = t * e;
                 R[i] = fma(te, pe, t);
             }
-        } else if constexpr (U == 14) {
+        } else if constexpr (U == 17) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 b[i].sd = fma(b[i].z, RNG_C[11], RNG_C[10]);
                 b[i].cd = fma(b[i].z, RNG_C[13], RNG_C[12]);
             }
+        } else if constexpr (U == 18) {
 #pragma unroll
             for (int i = 0; i < NP; ++i) {
                 b[i].sd = fma(b[i].sd, b[i].z, RNG_C[9]);
@@ -286,11 +302,15 @@ template <int NP> struct BmPipe {
         }
     }
 
-    // slice S of NS: units [S*16/NS, (S+1)*16/NS)
+    // slice S of NS: the units whose cumulative cost starts in [S, S+1) * total / NS
     template <int S, int NS> __device__ __forceinline__ void slice(const RngArgs& a, const double2* __restrict__ tab, double (&z)[2 * NP], double& lsum)
     {
-        constexpr int lo = S * N_UNITS / NS, hi = (S + 1) * N_UNITS / NS;
-        static_for<lo, hi>([&](auto u) { this->template unit<decltype(u)::value>(a, tab, z, lsum); });
+        constexpr int total = cost_before(N_UNITS);
+        static_for<0, N_UNITS>([&](auto u) {
+            constexpr int U = decltype(u)::value;
+            constexpr int at = cost_before(U) * NS;
+            if constexpr (at >= S * total && at < (S + 1) * total) this->template unit<U>(a, tab, z, lsum);
+        });
     }
 
     // uniform #0 of the draw from the spare bits of blocks 0 and 1 (valid after unit 10); same definition as ChainRng::uniform

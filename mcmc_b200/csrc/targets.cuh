@@ -160,8 +160,30 @@ struct NormalModel {
 
 // X-macro: (enum id, functor type).  MCMCB200_FAST_BUILD (developer builds for kernel tuning, see
 // mcmc_b200/build.py) keeps only the headline target so the library compiles in seconds.
-#ifdef MCMCB200_FAST_BUILD
+// MCMCB200_TARGET_SLICE = k (build.py compiles hmc.cu / mala.cu / nuts.cu once per target, in parallel): the
+// translation unit instantiates the kernels of target k only and exports launch_<sampler>_slice<k>; the
+// by-target dispatch lives in dispatch.cu.
+#define MCMCB200_N_TARGETS 5
+#if defined(MCMCB200_TARGET_SLICE)
+#if MCMCB200_TARGET_SLICE == 0
 #define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)
+#elif MCMCB200_TARGET_SLICE == 1
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_DIAG_GAUSS, DiagGauss)
+#elif MCMCB200_TARGET_SLICE == 2
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_DENSE_GAUSS, DenseGauss)
+#elif MCMCB200_TARGET_SLICE == 3
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_LINREG, LinReg)
+#elif MCMCB200_TARGET_SLICE == 4
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_NORMAL_MODEL, NormalModel)
+#else
+#error "MCMCB200_TARGET_SLICE out of range"
+#endif
+#define MCMCB200_CAT2(a, b) a##b
+#define MCMCB200_CAT(a, b) MCMCB200_CAT2(a, b)
+#define MCMCB200_SLICED(name) MCMCB200_CAT(MCMCB200_CAT(name, _slice), MCMCB200_TARGET_SLICE)
+#elif defined(MCMCB200_FAST_BUILD)
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)
+#define MCMCB200_SLICED(name) name
 #else
 #define MCMCB200_FOREACH_TARGET(X)          \
     X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)   \
@@ -169,4 +191,5 @@ struct NormalModel {
     X(MCMCB200_TARGET_DENSE_GAUSS, DenseGauss) \
     X(MCMCB200_TARGET_LINREG, LinReg)        \
     X(MCMCB200_TARGET_NORMAL_MODEL, NormalModel)
+#define MCMCB200_SLICED(name) name
 #endif

@@ -2,7 +2,7 @@
 // product path (mcmc_b200/, include/).  Only tests/, __graft_entry__.smoke() and
 // bench.py's cpu_baseline / --impl reference legs may load liboracle.so.
 //
-// A plain-C++ CPU restatement of the reference's four samplers with a pluggable
+// A plain-C++ CPU restatement of the reference's four gradient samplers (+ rwmh) with a pluggable
 // RNG source and a pluggable reduction order, written from SURVEY.md Appendices
 // C/D/E and checked bit-for-bit against the UNMODIFIED reference sources
 // (oracle/_ref, built by oracle/Makefile) in tests/test_oracle_vs_reference.py.
@@ -42,7 +42,7 @@ namespace
 typedef std::vector<double> vec;
 
 enum { RNG_MT = 0, RNG_TAPE = 1, RNG_PHILOX = 2 };
-enum { S_HMC = 0, S_MALA = 1, S_NUTS = 2, S_RMHMC = 3 };
+enum { S_HMC = 0, S_MALA = 1, S_NUTS = 2, S_RMHMC = 3, S_RWMH = 4 };
 
 // ---------------------------------------------------------------- Philox4x32-10
 
@@ -642,6 +642,58 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     return 0;
 }
 
+// ------------------------------------------------------------------ RWMH (src/rwmh.cpp:30-172)
+// cfg->step_size carries rwmh_settings_t::par_scale, cfg->precond carries rwmh_settings_t::cov_mat.
+static int run_rwmh(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
+{
+    Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
+    c.identity = (cfg->precond == nullptr);   // cov_mat empty -> EYE (:57)
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    Rng rng; init_rng(rng, cfg);
+    const int d = c.d;
+    const long n_total = cfg->n_burnin + cfg->n_keep;
+    const double par_scale = cfg->step_size;
+
+    // cov_mcmc_chol = par_scale * CHOL_LOWER(cov_mcmc), materialised as a Mat_t (:116)
+    vec S;
+    if (!c.identity) {
+        vec cov(cfg->precond, cfg->precond + size_t(d) * d);
+        mat_chol(cov, d, cfg->chol_mode, S);
+        for (size_t k = 0; k < S.size(); ++k) S[k] = par_scale * S[k];
+    }
+    vec prev(x0, x0 + d), cur(d), z(d), t(d);
+    if (c.bounded) box_transform(c, x0, prev.data());    // :105-107
+    double prev_LP = box_logp(c, prev.data());           // :111
+    long n_accept = 0;
+
+    for (long it = 0; it < n_total; ++it) {
+        rng.normals(it, d, z.data());                     // :124
+        if (c.identity) {
+            // dense product with par_scale * I: every off-diagonal term is an exact zero
+            for (int i = 0; i < d; ++i) cur[i] = prev[i] + par_scale * z[i];
+        } else {
+            gemv_plain(S, d, z.data(), t.data());
+            for (int i = 0; i < d; ++i) cur[i] = prev[i] + t[i];   // :125
+        }
+        double prop_LP = box_logp(c, cur.data());         // :127
+        if (!std::isfinite(prop_LP)) prop_LP = -std::numeric_limits<double>::infinity();   // :129-131
+        const double comp = std::min(0.0, prop_LP - prev_LP);   // :135
+        const double u = rng.uniform(it, 0);              // :136
+        const bool acc = u < std::exp(comp);              // :138
+        if (acc) { prev = cur; prev_LP = prop_LP; }
+        if (it >= cfg->n_burnin) {
+            const long row = it - cfg->n_burnin;
+            if (acc) ++n_accept;                          // :142-144
+            for (int j = 0; j < d; ++j) draws[row * d + j] = prev[j];   // :149-151
+            if (logp_out) logp_out[row] = prev_LP;
+        }
+    }
+    if (c.bounded)   // :158-165
+        for (long r = 0; r < cfg->n_keep; ++r) { vec tmp(draws + r * d, draws + (r + 1) * d); box_inv_transform(c, tmp.data(), draws + r * d); }
+    res->n_accept = n_accept; res->tape_used = rng.rec_n; res->final_step = par_scale; res->n_leapfrog = 0;
+    return 0;
+}
+
 // ------------------------------------------------------------------ NUTS (src/nuts.cpp:30-332, nuts.ipp:30-241, Appendix C)
 struct NutsEnv {
     const Ctx* c; Rng* rng; long draw; int* ucount; long* n_lf;
@@ -923,6 +975,7 @@ int oracle_run_chain(const oracle_cfg_t* cfg, const double* x0, double* draws_ou
     case S_MALA: return run_mala(cfg, x0, draws_out, logp_out, res);
     case S_NUTS: return run_nuts(cfg, x0, draws_out, logp_out, res);
     case S_RMHMC: return run_rmhmc(cfg, x0, draws_out, logp_out, res);
+    case S_RWMH: return run_rwmh(cfg, x0, draws_out, logp_out, res);
     default: return -1;
     }
 }

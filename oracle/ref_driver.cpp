@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (oracle/).  Thin extern "C" driver around the
 // UNMODIFIED reference samplers.  It is compiled together with
-// /root/reference/src/{hmc,mala,nuts,rmhmc}.cpp (where they lie; nothing is copied
+// /root/reference/src/{hmc,mala,nuts,rmhmc,rwmh}.cpp (where they lie; nothing is copied
 // into this repo) against the stand-in Eigen header — see oracle/Makefile —
 // into oracle/_ref/libmcmc_ref_{strict,fast}.so.
 //
@@ -44,6 +44,13 @@ double log_kernel_cb(const mcmc::ColVec_t& vals, mcmc::ColVec_t* grad_out, void*
     return otgt::value_and_grad(ctx->target_id, ctx->data, vals.data(), nullptr, ctx->d, otgt::SUM_SEQ);
 }
 
+// value-only callback of mcmc::rwmh (include/mcmc/rwmh.hpp:46)
+double log_kernel_val_cb(const mcmc::ColVec_t& vals, void* ctx_v)
+{
+    const tgt_ctx_t* ctx = static_cast<const tgt_ctx_t*>(ctx_v);
+    return otgt::value_and_grad(ctx->target_id, ctx->data, vals.data(), nullptr, ctx->d, otgt::SUM_SEQ);
+}
+
 mcmc::Mat_t tensor_cb(const mcmc::ColVec_t& vals, mcmc::Cube_t* deriv_out, void* ctx_v)
 {
     const tgt_ctx_t* ctx = static_cast<const tgt_ctx_t*>(ctx_v);
@@ -81,13 +88,13 @@ void copy_draws(const mcmc::Mat_t& draws, double* out, long n_keep, int d)
 extern "C" {
 
 // sampler ids shared by the entry points below
-enum { REF_HMC = 0, REF_MALA = 1, REF_NUTS = 2, REF_RMHMC = 3 };
+enum { REF_HMC = 0, REF_MALA = 1, REF_NUTS = 2, REF_RMHMC = 3, REF_RWMH = 4 };
 
 struct ref_settings_t {
     long n_burnin, n_keep;
     long n_leap_steps;     // hmc, rmhmc
-    double step_size;      // all (nuts: eps_bar_0)
-    const double* precond; // d*d column-major or null (hmc, mala, nuts)
+    double step_size;      // all (nuts: eps_bar_0; rwmh: par_scale)
+    const double* precond; // d*d column-major or null (hmc, mala, nuts; rwmh: cov_mat)
     long n_fp_steps;       // rmhmc
     long n_adapt_draws;    // nuts
     double target_accept_rate, gamma_val, t0_val, kappa_val;  // nuts
@@ -159,6 +166,14 @@ int ref_run_chain(int sampler, int target_id, const double* tdata, int d, const 
         s.rmhmc_settings.n_fp_steps = size_t(st->n_fp_steps);
         ok = mcmc::rmhmc(init, log_kernel_cb, tensor_cb, draws, &ctx, &ctx, s);
         acc = long(s.rmhmc_settings.n_accept_draws);
+        break;
+    case REF_RWMH:
+        s.rwmh_settings.n_burnin_draws = size_t(st->n_burnin);
+        s.rwmh_settings.n_keep_draws = size_t(st->n_keep);
+        s.rwmh_settings.par_scale = st->step_size;
+        fill_precond(s.rwmh_settings.cov_mat, st->precond, d);
+        ok = mcmc::rwmh(init, log_kernel_val_cb, draws, &ctx, s);
+        acc = long(s.rwmh_settings.n_accept_draws);
         break;
     default:
         return -1;

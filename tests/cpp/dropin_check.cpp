@@ -32,6 +32,13 @@ int main()
         if (!mcmc::mala(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
         dump("G3_mala_d3", draws, s.mala_settings.n_accept_draws);
     }
+    {   // golden rwmh_d3: RWMH d=3, seed 1, par_scale 0.5 (value-only kernel slot, include/mcmc/rwmh.hpp:43-72)
+        mcmc::ColVec_t x0(3); x0(0) = 1; x0(1) = -1; x0(2) = 0.5;
+        mcmc::algo_settings_t s; s.rng_seed_value = 1; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.rwmh_settings.n_burnin_draws = 0; s.rwmh_settings.n_keep_draws = 8; s.rwmh_settings.par_scale = 0.5;
+        if (!mcmc::rwmh(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        dump("rwmh_d3", draws, s.rwmh_settings.n_accept_draws);
+    }
     {   // G4: RM-HMC on the Normal model, seed 1
         // data x_k = 2 + 2 sin k, k < 100: {n, mean, sum of squared deviations} exactly as stored in the golden fixture
         const double stats[3] = {100.0, 0x1.00f8824d3cb51p+1, 0x1.901597d089536p+7};

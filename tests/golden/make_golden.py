@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Generate tests/golden/reference_golden.json from the UNMODIFIED reference (oracle/_ref/libmcmc_ref_strict.so:
-/root/reference/src/{hmc,mala,nuts,rmhmc}.cpp compiled against the stand-in Eigen, -O2 -ffp-contract=off).
+/root/reference/src/{hmc,mala,nuts,rmhmc,rwmh}.cpp compiled against the stand-in Eigen, -O2 -ffp-contract=off).
 
 Run in the build container (where /root/reference exists):   python tests/golden/make_golden.py
 The reference ships no golden vectors of its own, so these fixtures pin the oracle — and through it
@@ -72,6 +72,19 @@ def cases():
              st=dict(n_burnin=0, n_keep=30, step_size=0.15, n_adapt_draws=0), lower=lo4, upper=hi4),
         dict(name="rmhmc_box_sigma_positive", sampler=ol.RMHMC, target=ol.TGT_NORMAL_MODEL, tdata=nm, x0=[3, 3], seed=34,
              st=dict(n_burnin=5, n_keep=40, n_leap_steps=2, step_size=0.1), lower=[-inf, 0.0], upper=[inf, inf]),
+    ]
+    # mcmc::rwmh (src/rwmh.cpp): st.step_size carries par_scale, st.precond carries cov_mat.  Appended last so that
+    # the cases above keep consuming the same numpy stream as before (their fixtures do not change).
+    C6 = sym_pd(6, 0.5)
+    out += [
+        dict(name="rwmh_d3", sampler=ol.RWMH, target=ol.TGT_ISO_GAUSS, tdata=None, x0=[1, -1, 0.5], seed=1,
+             st=dict(n_burnin=0, n_keep=8, step_size=0.5)),
+        dict(name="rwmh_dense_cov_dense_target", sampler=ol.RWMH, target=ol.TGT_DENSE_GAUSS, tdata=P6.ravel().tolist(),
+             x0=rng.normal(size=6).tolist(), seed=41, st=dict(n_burnin=10, n_keep=60, step_size=0.45, precond=C6.tolist())),
+        dict(name="rwmh_d128", sampler=ol.RWMH, target=ol.TGT_ISO_GAUSS, tdata=None, x0=ol.c2_initial(1, 128, 7)[0].tolist(), seed=12352,
+             st=dict(n_burnin=10, n_keep=40, step_size=0.2)),
+        dict(name="rwmh_box_d4", sampler=ol.RWMH, target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 0.5, 2.0, 1.5], x0=[0.3, 0.7, 0.4, 0.2], seed=35,
+             st=dict(n_burnin=5, n_keep=50, step_size=0.6), lower=lo4, upper=hi4),
     ]
     return out
 

@@ -16,7 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 
-HMC, MALA, NUTS, RMHMC = 0, 1, 2, 3
+HMC, MALA, NUTS, RMHMC, RWMH = 0, 1, 2, 3, 4
 RNG_MT, RNG_TAPE, RNG_PHILOX = 0, 1, 2
 SUM_SEQ, SUM_WARP = 0, 1
 TGT_ISO_GAUSS, TGT_DIAG_GAUSS, TGT_DENSE_GAUSS, TGT_LINREG, TGT_NORMAL_MODEL = 0, 1, 2, 3, 4

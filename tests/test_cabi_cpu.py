@@ -43,6 +43,8 @@ def test_defaults_match_reference_structs(api):
             n.t0_val, n.kappa_val) == (1000, 1000, 1000, 0.55, 10, 1.0, 0.05, 10.0, 0.75)
     r = api.RmhmcSettings(); lib.mcmcb200_rmhmc_settings_default(ctypes.byref(r))
     assert (r.n_burnin_draws, r.n_keep_draws, r.n_leap_steps, r.step_size, r.n_fp_steps) == (1000, 1000, 1, 1.0, 5)
+    w = api.RwmhSettings(); lib.mcmcb200_rwmh_settings_default(ctypes.byref(w))   # mcmc_structs.hpp:138-149
+    assert (w.n_burnin_draws, w.n_keep_draws, w.par_scale) == (1000, 1000, 1.0) and not w.cov_mat
 
 
 def test_target_registry(api):
@@ -62,6 +64,8 @@ def test_host_side_reference_stream(api, oracle):
     assert np.array_equal(api.mt19937_tape(2024, 0, 7, 7), o["tape"])
     o = oracle.run_chain(ol.MALA, ol.TGT_ISO_GAUSS, None, np.zeros(3), st, seed=5, record_tape=200)
     assert np.array_equal(api.mt19937_tape(5, 0, 7, 3), o["tape"])
+    o = oracle.run_chain(ol.RWMH, ol.TGT_ISO_GAUSS, None, np.zeros(5), st, seed=6, record_tape=200)
+    assert np.array_equal(api.mt19937_tape(6, 0, 7, 5), o["tape"])
 
 
 def test_no_cpu_fallback(api):
@@ -70,7 +74,7 @@ def test_no_cpu_fallback(api):
 
     if api.device_count() > 0:
         pytest.skip("a CUDA device is visible")
-    for fn in (mcmc_b200.hmc, mcmc_b200.mala, mcmc_b200.nuts):
+    for fn in (mcmc_b200.hmc, mcmc_b200.mala, mcmc_b200.nuts, mcmc_b200.rwmh):
         with pytest.raises(mcmc_b200.McmcB200Error) as e:
             fn(np.zeros((2, 4)), "iso_gauss", n_burnin=1, n_keep=1)
         assert e.value.code == api.ERR_CUDA and "no CPU fallback" in str(e.value)

@@ -42,13 +42,15 @@ def _engine_run(engine, sampler, tid, tdata, x0s, st, arith, **kw):
         return engine.mala(x0s, TNAME[tid], step_size=st["step_size"], **common)
     if sampler == ol.RMHMC:
         return engine.rmhmc(x0s, TNAME[tid], n_leap_steps=st["n_leap_steps"], step_size=st["step_size"], n_fp_steps=st["n_fp_steps"], **common)
+    if sampler == ol.RWMH:
+        return engine.rwmh(x0s, TNAME[tid], par_scale=st["step_size"], cov_mat=st["precond"], **common)
     raise ValueError(sampler)
 
 
 def test_bounded_golden_vectors_of_the_reference(engine, oracle):
     g = golden_util.load()
     cases = [c for c in g["cases"] if "lower" in c]
-    assert {c["name"] for c in cases} == {"hmc_box_d4", "mala_box_d4", "nuts_box_d4", "rmhmc_box_sigma_positive"}
+    assert {c["name"] for c in cases} == {"hmc_box_d4", "mala_box_d4", "nuts_box_d4", "rmhmc_box_sigma_positive", "rwmh_box_d4"}
     for c in cases:
         st = c["settings"]
         x0 = np.array([c["x0"]], dtype=np.float64)

@@ -30,7 +30,7 @@ def test_golden_rng_stream(oracle, golden):
 
 
 def test_oracle_reproduces_every_golden_case(oracle, golden):
-    assert len(golden["cases"]) >= 16
+    assert len(golden["cases"]) >= 20
     for c in golden["cases"]:
         o = oracle.run_chain(c["sampler"], c["target"], c["tdata"], c["x0"], c["settings"], seed=c["seed"], rng_mode=ol.RNG_MT,
                              sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1)
@@ -76,6 +76,11 @@ def _rand_cases():
         ("nuts dense M", ol.NUTS, ol.TGT_DENSE_GAUSS, P.ravel(), rng.normal(size=7), ol.Settings(n_burnin=20, n_keep=30, n_adapt_draws=20, precond=M), 14),
         ("nuts depth cap 3", ol.NUTS, ol.TGT_ISO_GAUSS, None, rng.normal(size=5), ol.Settings(n_burnin=0, n_keep=40, n_adapt_draws=0, step_size=0.01, max_tree_depth=3), 15),
         ("rmhmc L3", ol.RMHMC, ol.TGT_NORMAL_MODEL, nm, [2.5, 2.5], ol.Settings(n_burnin=5, n_keep=100, n_leap_steps=3, step_size=0.1, n_fp_steps=4), 16),
+        # mcmc::rwmh: step_size carries par_scale, precond carries cov_mat
+        ("rwmh iso d=70", ol.RWMH, ol.TGT_ISO_GAUSS, None, rng.normal(size=70), ol.Settings(n_burnin=5, n_keep=80, step_size=0.15), 17),
+        ("rwmh dense cov", ol.RWMH, ol.TGT_DENSE_GAUSS, P.ravel(), rng.normal(size=7), ol.Settings(n_burnin=5, n_keep=80, step_size=0.5, precond=M), 18),
+        ("rwmh linreg", ol.RWMH, ol.TGT_LINREG, np.concatenate([A.ravel(), b]), rng.normal(size=7), ol.Settings(n_burnin=0, n_keep=80, step_size=0.3), 19),
+        ("rwmh normal model", ol.RWMH, ol.TGT_NORMAL_MODEL, nm, [3, 3], ol.Settings(n_burnin=10, n_keep=100, step_size=0.1), 20),
     ]
 
 
@@ -111,6 +116,9 @@ def _bounded_cases():
         ("nuts box adapt", ol.NUTS, ol.TGT_DIAG_GAUSS, w, x0, ol.Settings(n_burnin=20, n_keep=20, n_adapt_draws=20, **B), 46),
         ("rmhmc box", ol.RMHMC, ol.TGT_NORMAL_MODEL, nm, [2.5, 2.5],
          ol.Settings(n_burnin=5, n_keep=60, n_leap_steps=2, step_size=0.1, lower_bounds=[-inf, 0.0], upper_bounds=[10.0, inf]), 47),
+        ("rwmh box diag", ol.RWMH, ol.TGT_DIAG_GAUSS, w, x0, ol.Settings(n_burnin=5, n_keep=80, step_size=0.3, **B), 48),
+        ("rwmh box diag cov", ol.RWMH, ol.TGT_DIAG_GAUSS, w, x0,
+         ol.Settings(n_burnin=5, n_keep=80, step_size=0.3, precond=np.diag(np.linspace(0.5, 2.0, d)) + 0.1, **B), 49),
     ]
 
 
