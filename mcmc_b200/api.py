@@ -68,6 +68,11 @@ class Output(ctypes.Structure):
                 ("kernel_launches", c_i32)]
 
 
+class Summary(ctypes.Structure):
+    _fields_ = [("mean", c_vp), ("var", c_vp), ("rhat", c_vp), ("chain_mean", c_vp), ("chain_var", c_vp),
+                ("kernel_ms", ctypes.c_float), ("reserved0", c_i32)]
+
+
 class McmcB200Error(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("mcmc_b200 error %d: %s" % (code, msg))
@@ -280,6 +285,30 @@ def philox_stream(seed, chain, draw, n_dim, n_unif):
     return out
 
 
+def summarize(draws=None, draws_dev_ptr=None, n_chains=None, n_keep=None, n_dim=None, device=-1, stream=None, per_chain=False):
+    """On-device summaries of draws_out[n_chains][n_keep][n_dim] (include/mcmc_b200_summary.h): pooled mean / variance and
+    Gelman-Rubin R-hat per element, optionally the per-chain means and variances.  Pass a numpy array (uploaded) or a raw
+    device pointer with the three sizes (reduced in place, nothing but the summaries crosses PCIe)."""
+    lib = load()
+    if draws_dev_ptr is None:
+        a = np.ascontiguousarray(draws, dtype=np.float64)
+        assert a.ndim == 3
+        C, T, d = a.shape
+        ptr, mem = _np_ptr(a), MEM_HOST
+    else:
+        C, T, d = int(n_chains), int(n_keep), int(n_dim)
+        ptr, mem = c_vp(draws_dev_ptr), MEM_DEVICE
+    mean, var, rhat = np.empty(d), np.empty(d), np.empty(d)
+    cm = np.empty((C, d)) if per_chain else None
+    cv = np.empty((C, d)) if per_chain else None
+    out = Summary(_np_ptr(mean), _np_ptr(var), _np_ptr(rhat), _np_ptr(cm), _np_ptr(cv), 0.0, 0)
+    _check(lib.mcmcb200_summarize_draws(ptr, mem, c_i64(C), c_i64(T), d, int(device), c_vp(stream) if stream else None, ctypes.byref(out)))
+    r = dict(mean=mean, var=var, rhat=rhat, kernel_ms=float(out.kernel_ms))
+    if per_chain:
+        r.update(chain_mean=cm, chain_var=cv)
+    return r
+
+
 def device_count():
     return load().mcmcb200_device_count()
 
@@ -289,5 +318,5 @@ EXPORTED_SYMBOLS = [
     "mcmcb200_rmhmc_settings_default", "mcmcb200_hmc_run", "mcmcb200_mala_run", "mcmcb200_nuts_run",
     "mcmcb200_rmhmc_run", "mcmcb200_rwmh_settings_default", "mcmcb200_rwmh_run", "mcmcb200_target_lookup", "mcmcb200_target_data_len", "mcmcb200_target_eval",
     "mcmcb200_mt19937_tape", "mcmcb200_philox_stream", "mcmcb200_last_error", "mcmcb200_device_count",
-    "mcmcb200_release_workspace",
+    "mcmcb200_release_workspace", "mcmcb200_summarize_draws",
 ]

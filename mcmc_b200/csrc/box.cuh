@@ -101,8 +101,8 @@ template <int EPL> struct BoxLane {
 // Target evaluation in the transformed space.  Returns log pi(inv(v)) + log_jacobian(v) (REDUCE: warp-uniform total,
 // else this lane's partial) when WANT_VALUE; g = raw gradient at inv(v) and J = diagonal of inv_jacobian_adjust(v)
 // when WANT_GRAD.  With BOX = false it is exactly T::eval.
-template <class T, int EPL, bool STRICT, bool BOX, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE>
-__device__ __forceinline__ double box_eval(const double* __restrict__ tdata, const WarpCtx& w, const BoxLane<BOX ? EPL : 1>& bx,
+template <class T, int EPL, bool STRICT, bool BOX, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE, class Ctx>
+__device__ __forceinline__ double box_eval(const double* __restrict__ tdata, const Ctx& w, const BoxLane<BOX ? EPL : 1>& bx,
                                            const double (&v)[EPL], double (&g)[EPL], double (&J)[EPL])
 {
     if (!BOX) return T::template eval<EPL, STRICT, WANT_VALUE, WANT_GRAD, REDUCE>(tdata, w, v, g);

@@ -5,6 +5,7 @@
 // every run call fails with MCMCB200_ERR_CUDA.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -506,6 +507,12 @@ int mcmcb200_nuts_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, c
     a.work_stride = nuts_work_doubles_per_chain(pr->n_dim, a.max_depth);
     if ((rc = pool_get(s.scope.dev, SLOT_WORK, (size_t)pr->n_chains * (size_t)a.work_stride * sizeof(double), &p))) return rc;
     a.work = static_cast<double*>(p);
+    // dense targets with enough chains to fill the GPU run 8 chains per CTA with cooperative gradients (nuts.cu);
+    // MCMCB200_NUTS_COOP=0/1 forces the choice (tests compare the two kernels bit for bit)
+    a.coop = pr->n_chains >= 64;
+    if (const char* e = std::getenv("MCMCB200_NUTS_COOP")) a.coop = (e[0] == '1');
+    a.coop_batch = 6;   // measured on B200 (C4 shape, 1184 chains x 40 draws): 2 -> 456 ms, 4 -> 332, 6 -> 314, 8 -> 332
+    if (const char* e = std::getenv("MCMCB200_NUTS_BATCH")) a.coop_batch = std::atoi(e) > 0 ? std::atoi(e) : 1;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
     if ((rc = launch_nuts(a))) return rc;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));

@@ -65,6 +65,8 @@ struct NutsLaunch : CommonLaunch {
     long long* n_leapfrog;     // [n_chains] or null
     double* work;              // per-chain scratch for the memoised tree states
     long long work_stride;     // doubles per chain
+    bool coop;                 // dense targets: 8 chains per CTA with cooperative gradients (nuts.cu)
+    int coop_batch;            // requests that must be pending before busy warps attend a cooperative round
 };
 
 struct RmhmcLaunch : CommonLaunch {

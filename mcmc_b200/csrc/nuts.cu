@@ -21,6 +21,7 @@
 #include "targets.cuh"
 #include "box.cuh"
 #include <math_constants.h>
+#include <type_traits>
 
 namespace mcmcb200
 {
@@ -48,27 +49,58 @@ struct NutsStack {  // per-warp recursion stack (shared memory)
     double alpha[NUTS_MAX_LEVELS];
 };
 
+// U-turn results of the subtrees T(j, a) of the current doubling, per warp: within one doubling the 2^j - 1 merges of
+// the replay touch far fewer distinct (j, a) pairs (172 of 511 at j = 9), and the four state vectors + two dot products
+// of a repeated pair give the same answer.  Entry = (epoch << 1) | result; the epoch changes with every doubling.
+constexpr int NUTS_UC_J = 10, NUTS_UC_A = 46;   // covers the default max_tree_depth = 10; larger trees compute directly
+
 constexpr int nuts_min_blocks(int epl) { return epl <= 4 ? 4 : (epl == 8 ? 2 : 1); }
 
-template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false>
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nuts_kernel(const __grid_constant__ NutsLaunch a)
+// NW = warps (chains) per CTA.  NW = 4 is the independent-warps kernel.  NW = 8 (dense targets, many chains) is the
+// CTA-cooperative variant: the 8 chains of a CTA evaluate their gradients in lock-step, so the target's d x d matrix is
+// read from L2 once per 8 gradients instead of once per gradient (coop_gemv in warp.cuh; at d = 256 every warp used to
+// stream the 512 KB precision matrix by itself and the kernel was L2-bound).  Chains consume different numbers of
+// gradients, so a warp whose chain is finished (or that has no chain) keeps serving the remaining chains' products in a
+// drain loop until the CTA's active-chain counter reaches zero.  Results are bit-identical to the NW = 4 kernel.
+template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false, int NW = WARPS_PER_BLOCK>
+__global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) nuts_kernel(const __grid_constant__ NutsLaunch a)
 {
+    constexpr bool COOP = (NW == 8);
     extern __shared__ double smem[];
     __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
-    __shared__ NutsStack stacks[WARPS_PER_BLOCK];
+    __shared__ NutsStack stacks[NW];
+    __shared__ int ucache[NW][NUTS_UC_J][NUTS_UC_A];
+    __shared__ int n_active;   // COOP: chains of this CTA still running
+    __shared__ int coop_want;  // COOP: products requested and not yet served
     typedef Ar<STRICT> A;
-    if (RNGM == RNG_PHILOX) {
-        build_rng_tables(rng_tab);
-        __syncthreads();
+    if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
+    for (int i = threadIdx.x; i < NW * NUTS_UC_J * NUTS_UC_A; i += NW * 32) (&ucache[0][0][0])[i] = 0;
+    if (COOP && threadIdx.x == 0) {
+        const long long left = a.n_chains - (long long)blockIdx.x * NW;
+        n_active = left < NW ? (int)left : NW;
+        coop_want = 0;
     }
+    __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long chain = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (chain >= a.n_chains) return;
+    const long long chain = (long long)blockIdx.x * NW + warp;
     const int d = a.d;
     const int dp = (d + 1) & ~1;
     double* tscr = smem + (size_t)warp * 2 * dp;
     double* mscr = tscr + dp;
-    const WarpCtx w{lane, d, tscr};
+    typename std::conditional<COOP, CoopWarpCtx<NW>, WarpCtx>::type w;
+    w.lane = lane; w.d = d; w.scr = tscr;
+    if constexpr (COOP) {
+        // dynamic shared memory: NW x (x, y) vectors, then (when the TMA path applies) two panel buffers and two mbarriers
+        w.warp = warp; w.coop_base = smem; w.coop_stride = 2 * dp; w.phase = 0u; w.n_active = &n_active; w.want = &coop_want;
+        const bool tma = (d % 2 == 0) && d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);
+        w.panels = tma ? smem + (size_t)NW * 2 * dp : nullptr;
+        w.mbar = tma ? reinterpret_cast<unsigned long long*>(w.panels + (size_t)2 * COOP_PANEL_COLS * d) : nullptr;
+        if (tma) {
+            if (threadIdx.x == 0) { mbar_init(w.mbar, 1); mbar_init(w.mbar + 1, 1); mbar_init_fence(); }
+            __syncthreads();
+        }
+    }
+    if (chain < a.n_chains) {   // ---- this warp's chain (no early return: COOP warps must reach the drain loop) ----
     NutsStack& st = stacks[warp];
     const int m_max = nuts_m_max(a.max_depth);
 
@@ -147,6 +179,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
     ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
     long long n_lf = 0;
+    int uc_epoch = 0;
 
     // ---- pre-loop momentum draw (src/nuts.cpp:166-168) and nuts_find_initial_step_size (nuts.ipp:30-93) ----
     rng.template normals<EPL, false>(a.rng, -1, d, lane, rng_tab, rt);
@@ -210,6 +243,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
 
             // tip of the lazily extended trajectory LF^k (prev_draw, draw momentum): always restarts here (Q12)
             int computed = 0;
+            ++uc_epoch;   // new restart point / direction: the cached U-turn results of the previous doubling are void
 #pragma unroll
             for (int k = 0; k < EPL; ++k) xt[k] = x[k];
             load_vec<EPL>(Wm, d, lane, rt);
@@ -222,6 +256,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
             int level = 0;
             st.j[0] = depth; st.a[0] = 0; st.phase[0] = 0;
             while (level >= 0) {
+                if constexpr (COOP) {
+                    // the replay needs no gradients: attend the other chains' product rounds instead of making them wait
+                    // — but only once enough requests are pending to share the matrix pass (a.coop_batch, or every chain
+                    // that is still running): a round costs the same whether it serves one chain or eight
+                    int wv = *reinterpret_cast<volatile int*>(&coop_want);
+                    int na = *reinterpret_cast<volatile int*>(&n_active);
+                    wv = __shfl_sync(FULL, wv, 0);
+                    na = __shfl_sync(FULL, na, 0);
+                    if (wv > 0 && wv >= (a.coop_batch < na - 1 ? a.coop_batch : na - 1)) coop_round<STRICT>(a.tdata, w, true);
+                }
                 const int j = st.j[level], ao = st.a[level], ph = st.phase[level];
                 if (ph == 0) {
                     if (j == 0) {
@@ -266,20 +310,36 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
                     const double prob = (double)R_n / (double)(nA + R_n);        // :213
                     const double z2 = rng.uniform(a.rng, t, ucount++);           // :214
                     const int sel = (z2 < prob) ? R_sel : st.sel[level];
-                    // U-turn test on the updated slots: near = ao+1, far = ao+j+1 (Appendix C)
-                    double xn_[EPL], xf_[EPL], rn_[EPL], rf_[EPL];
+                    // U-turn test on the updated slots: near = ao+1, far = ao+j+1 (Appendix C).  Its outcome only matters while
+                    // the subtree has not stopped (R_s = R_s * ... , nuts.ipp:229) and is a function of (j, ao) within a doubling.
                     const int near = ao + 1, far = ao + j + 1;
-                    load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp, d, lane, xn_);
-                    load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp + dp, d, lane, rn_);
-                    load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp, d, lane, xf_);
-                    load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp + dp, d, lane, rf_);
-                    double diff[EPL];
+                    if (R_s == 1) {
+                        const bool cacheable = (j < NUTS_UC_J) && (ao < NUTS_UC_A);
+                        int ut = -1;
+                        if (cacheable) {
+                            const int e = reinterpret_cast<volatile int*>(&ucache[warp][j][ao])[0];
+                            if ((e >> 1) == uc_epoch) ut = e & 1;
+                        }
+                        if (ut < 0) {
+                            double xn_[EPL], xf_[EPL], rn_[EPL], rf_[EPL];
+                            load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp, d, lane, xn_);
+                            load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp + dp, d, lane, rn_);
+                            load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp, d, lane, xf_);
+                            load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp + dp, d, lane, rf_);
+                            double diff[EPL];
 #pragma unroll
-                    for (int k = 0; k < EPL; ++k) diff[k] = (dir == 1) ? A::sub(xf_[k], xn_[k]) : A::sub(xn_[k], xf_[k]);   // pos - neg
-                    // dir=+1: pos=far, neg=near; dir=-1: pos=near, neg=far
-                    const double d_neg = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rn_) : warp_dot<EPL, STRICT>(diff, rf_);   // :226
-                    const double d_pos = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rf_) : warp_dot<EPL, STRICT>(diff, rn_);   // :227
-                    R_s = R_s * ((d_neg >= 0.0) ? 1 : 0) * ((d_pos >= 0.0) ? 1 : 0);                                           // :229
+                            for (int k = 0; k < EPL; ++k) diff[k] = (dir == 1) ? A::sub(xf_[k], xn_[k]) : A::sub(xn_[k], xf_[k]);   // pos - neg
+                            // dir=+1: pos=far, neg=near; dir=-1: pos=near, neg=far
+                            const double d_neg = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rn_) : warp_dot<EPL, STRICT>(diff, rf_);   // :226
+                            const double d_pos = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rf_) : warp_dot<EPL, STRICT>(diff, rn_);   // :227
+                            ut = ((d_neg >= 0.0) ? 1 : 0) * ((d_pos >= 0.0) ? 1 : 0);                                                  // :229
+                            if (cacheable) {
+                                if (lane == 0) ucache[warp][j][ao] = (uc_epoch << 1) | ut;
+                                __syncwarp();
+                            }
+                        }
+                        R_s = ut;
+                    }
                     R_sel = sel;
                     R_n = nA + R_n;
                     R_alpha = st.alpha[level] + R_alpha;
@@ -354,6 +414,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, nuts_min_blocks(EPL)) nu
         if (a.n_accept) a.n_accept[chain] = n_acc;
         if (a.step_out) a.step_out[chain] = eps;
         if (a.n_leapfrog) a.n_leapfrog[chain] = n_lf;
+        if (COOP) atomicSub(&n_active, 1);
+    }
+    }   // chain < n_chains
+    if constexpr (COOP) {
+        // drain: keep serving the cooperative products of the chains that are still running
+        __syncwarp();
+        while (coop_round<STRICT>(a.tdata, w, true)) {}
     }
 }
 
@@ -363,8 +430,19 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
         set_error("nuts: max_tree_depth %d exceeds %d", a.max_depth, NUTS_MAX_LEVELS - 1);
         return MCMCB200_ERR_UNSUPPORTED;
     }
-    const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const int dp = (a.d + 1) & ~1;
+    if (T::dense_matrix && !BOX && !DENSE_M && a.coop) {   // dense target, M = I, many chains: cooperative gradients, 8 chains per CTA
+        constexpr int NW = (T::dense_matrix && !BOX && !DENSE_M) ? 8 : WARPS_PER_BLOCK;
+        const long long blocks = (a.n_chains + NW - 1) / NW;
+        const bool tma = (a.d % 2 == 0) && a.d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);   // same test as the kernel
+        const size_t smem = (size_t)NW * 2 * dp * sizeof(double) + (tma ? (size_t)2 * COOP_PANEL_COLS * a.d * sizeof(double) + 16 : 0);
+        auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX, NW>;
+        if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)blocks, NW * 32, smem, a.stream>>>(a);
+        MCMCB200_CUDA_TRY(cudaGetLastError());
+        return MCMCB200_OK;
+    }
+    const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dp * sizeof(double) : 0;
     auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX>;
     if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -22,10 +22,11 @@ namespace mcmcb200
 // log pi = -1/2 |x|^2                       (SURVEY §8d C1/C2 target)
 struct IsoGauss {
     static constexpr bool needs_scratch = false;
+    static constexpr bool dense_matrix = false;   // data starts with a d x d matrix applied through dense_matvec
     static constexpr bool separable = true;         // log pi is a sum over elements: a chain may be split across warps
     static constexpr bool per_element_data = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
-    static __device__ __forceinline__ double eval(const double*, const WarpCtx&, const double (&x)[EPL], double (&g)[EPL])
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true, class Ctx = WarpCtx>
+    static __device__ __forceinline__ double eval(const double*, const Ctx&, const double (&x)[EPL], double (&g)[EPL])
     {
         if (WANT_GRAD) {
 #pragma unroll
@@ -42,10 +43,11 @@ struct IsoGauss {
 // log pi = -1/2 sum_i w_i x_i^2, data = w[d]
 struct DiagGauss {
     static constexpr bool needs_scratch = false;
+    static constexpr bool dense_matrix = false;   // data starts with a d x d matrix applied through dense_matvec
     static constexpr bool separable = true;
     static constexpr bool per_element_data = true;  // data[j] belongs to element j
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
-    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true, class Ctx = WarpCtx>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const Ctx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
         double t[EPL];
@@ -70,15 +72,15 @@ struct DiagGauss {
 // log pi = -1/2 x' P x, data = P[d*d] symmetric          (SURVEY §8d C4 target; functor data = Sigma^-1)
 struct DenseGauss {
     static constexpr bool needs_scratch = true;
+    static constexpr bool dense_matrix = true;   // data starts with a d x d matrix applied through dense_matvec
     static constexpr bool separable = false;
     static constexpr bool per_element_data = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
-    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true, class Ctx = WarpCtx>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const Ctx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
         double y[EPL];
-        stage_vec<EPL>(w.scr, w.d, w.lane, x);
-        gemv_cm<EPL, STRICT>(data, w.d, w.lane, w.scr, 1.0, y);
+        dense_matvec<EPL, STRICT>(data, w, x, y);   // per warp, or CTA-cooperative when w.coop_nw > 0 (NUTS, many chains)
         if (WANT_GRAD) {
 #pragma unroll
             for (int k = 0; k < EPL; ++k) g[k] = -y[k];
@@ -95,15 +97,15 @@ struct DenseGauss {
 // (SURVEY §8d C3 target; grad = b - A t)
 struct LinReg {
     static constexpr bool needs_scratch = true;
+    static constexpr bool dense_matrix = true;   // data starts with a d x d matrix applied through dense_matvec
     static constexpr bool separable = false;
     static constexpr bool per_element_data = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
-    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true, class Ctx = WarpCtx>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const Ctx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
         double y[EPL], b[EPL];
-        stage_vec<EPL>(w.scr, w.d, w.lane, x);
-        gemv_cm<EPL, STRICT>(data, w.d, w.lane, w.scr, 1.0, y);
+        dense_matvec<EPL, STRICT>(data, w, x, y);   // per warp, or CTA-cooperative when w.coop_nw > 0 (NUTS, many chains)
         const double* __restrict__ bp = data + (size_t)w.d * (size_t)w.d;
 #pragma unroll
         for (int k = 0; k < EPL; ++k) {
@@ -128,10 +130,11 @@ struct LinReg {
 // statistics data = {n, xbar, M2 = sum (x_k - xbar)^2}:  sum (x_k - mu)^2 = M2 + n (xbar - mu)^2.
 struct NormalModel {
     static constexpr bool needs_scratch = false;
+    static constexpr bool dense_matrix = false;   // data starts with a d x d matrix applied through dense_matvec
     static constexpr bool separable = false;
     static constexpr bool per_element_data = false;
-    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true>
-    static __device__ __forceinline__ double eval(const double* __restrict__ data, const WarpCtx& w, const double (&x)[EPL],
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true, class Ctx = WarpCtx>
+    static __device__ __forceinline__ double eval(const double* __restrict__ data, const Ctx& w, const double (&x)[EPL],
                                                   double (&g)[EPL])
     {
         const double n = __ldg(data), xbar = __ldg(data + 1), M2 = __ldg(data + 2);

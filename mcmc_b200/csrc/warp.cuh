@@ -33,9 +33,24 @@ template <bool STRICT> struct Ar {
 };
 
 struct WarpCtx {
+    static constexpr int coop = 0;
     int lane;
     int d;
     double* scr;  // per-warp shared scratch (>= d doubles) for target functors that need all of x
+};
+// Context of a kernel whose NW warps per CTA evaluate dense products cooperatively (coop_gemv below): warp c stages its
+// vector at coop_base + c*coop_stride (== its scr) and receives the product at + coop_stride/2.  panels / mbar: the two
+// TMA panel buffers (COOP_PANEL_COLS columns of the matrix each) and their mbarriers, or null for the direct-load path.
+template <int NW> struct CoopWarpCtx : WarpCtx {
+    static constexpr int coop = NW;
+    int warp;
+    double* coop_base;
+    int coop_stride;
+    double* panels;
+    unsigned long long* mbar;
+    const int* n_active;      // chains of this CTA still running (shared memory)
+    int* want;                // products requested and not yet served (shared memory): busy warps poll it, see coop_round
+    mutable unsigned phase;   // bit b = parity of panel buffer b's next completed phase (identical in every thread)
 };
 
 __device__ __forceinline__ int elem_index(int lane, int k) { return (k >> 1) * 64 + 2 * lane + (k & 1); }
@@ -175,6 +190,182 @@ __device__ __forceinline__ void gemv_cm(const double* __restrict__ A, int d, int
 #pragma unroll
     for (int k = 0; k < EPL; ++k)
         if (elem_index(lane, k) >= d) y[k] = 0.0;
+}
+
+
+// ---- CTA-cooperative dense product -----------------------------------------------------------------------------
+// y_c = A x_c for the NW chains of a CTA at once (A column-major d x d, read ONCE per call for all chains instead of
+// once per chain): every warp of the CTA calls coop_gemv the same number of times; between the two named barriers
+// warp w computes rows {lane + 32 (w + NW m)} of all NW products from the vectors staged in shared memory.  Each
+// output element is accumulated over j = 0..d-1 in increasing order with one multiply-add per term — exactly the order
+// of gemv_cm — so the result is bit-identical to the per-warp product in both arithmetic modes.
+// The matrix is streamed through shared memory in panels of COOP_PANEL_COLS columns (one contiguous d*32*8-byte block
+// of the column-major array) by TMA bulk copies (cp.async.bulk + mbarrier complete_tx), double-buffered: with only
+// NW = 8 resident warps per SM, per-lane global loads cannot keep enough bytes in flight to cover the L2 latency
+// (measured: 38 us per product at d = 256 with direct loads), a 64 KB bulk copy per panel can.
+// Barrier 1 is used (bar.sync 1, 32*NW): all 32*NW threads of the CTA must arrive, from any call site.
+constexpr int COOP_PANEL_COLS = 32;
+
+template <int NW> __device__ __forceinline__ void coop_barrier() { asm volatile("bar.sync 1, %0;" : : "n"(32 * NW) : "memory"); }
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" : : "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" : : : "memory"); }
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t}"
+        : : "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: announce `bytes` on the mbarrier and start the bulk copy global -> shared that will complete them
+__device__ __forceinline__ void bulk_load_panel(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" : : "r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 : : "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// direct-load body (ragged / odd n_dim, or no panel buffers): four columns in flight per lane
+template <int NW, bool STRICT>
+__device__ __forceinline__ void coop_gemv_body(const double* __restrict__ A, int d, int warp, int lane, double* __restrict__ base, int stride)
+{
+    const int half = stride >> 1;
+    for (int i0 = 32 * warp; i0 < d; i0 += 32 * NW) {
+        const int i = i0 + lane;
+        const bool row_ok = i < d;
+        double acc[NW];
+#pragma unroll
+        for (int c = 0; c < NW; ++c) acc[c] = 0.0;
+        const double* __restrict__ col = A + (row_ok ? i : 0);
+        int j = 0;
+        for (; j + 4 <= d; j += 4) {
+            double a4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a4[u] = __ldg(col + (size_t)(j + u) * (size_t)d);
+#pragma unroll
+            for (int u = 0; u < 4; u += 2) {
+#pragma unroll
+                for (int c = 0; c < NW; ++c) {
+                    const double2 xv = *reinterpret_cast<const double2*>(base + (size_t)c * stride + j + u);
+                    acc[c] = Ar<STRICT>::mad(a4[u], xv.x, acc[c]);
+                    acc[c] = Ar<STRICT>::mad(a4[u + 1], xv.y, acc[c]);
+                }
+            }
+        }
+        for (; j < d; ++j) {
+            const double aj = __ldg(col + (size_t)j * (size_t)d);
+#pragma unroll
+            for (int c = 0; c < NW; ++c) acc[c] = Ar<STRICT>::mad(aj, base[(size_t)c * stride + j], acc[c]);
+        }
+        if (row_ok) {
+#pragma unroll
+            for (int c = 0; c < NW; ++c) base[(size_t)c * stride + half + i] = acc[c];
+        }
+    }
+}
+
+// TMA-panel body: requires d even, d <= 32*NW (one row per lane), A 16-byte aligned.  Called by all 32*NW threads
+// after every chain's x is staged; thread 0 is the producer.  Ends with every panel buffer free again.
+template <int NW, bool STRICT>
+__device__ __forceinline__ void coop_gemv_body_tma(const double* __restrict__ A, int d, int warp, int lane, double* __restrict__ base,
+                                                   int stride, double* __restrict__ panels, unsigned long long* mbar, unsigned& phase)
+{
+    const int half = stride >> 1;
+    const int np = (d + COOP_PANEL_COLS - 1) / COOP_PANEL_COLS;
+    const size_t pan_elems = (size_t)COOP_PANEL_COLS * d;
+    const int i = 32 * warp + lane;
+    const bool row_ok = i < d;
+    const int ir = row_ok ? i : 0;
+    double acc[NW];
+#pragma unroll
+    for (int c = 0; c < NW; ++c) acc[c] = 0.0;
+    for (int k = 0; k < np; ++k) {
+        const int b = k & 1;
+        mbar_wait(mbar + b, (phase >> b) & 1u);
+        phase ^= 1u << b;
+        const double* __restrict__ pan = panels + (size_t)b * pan_elems + ir;
+        const int j0 = k * COOP_PANEL_COLS;
+        const int ncols = (d - j0 < COOP_PANEL_COLS) ? d - j0 : COOP_PANEL_COLS;   // even
+#pragma unroll 4
+        for (int jl = 0; jl < ncols; jl += 2) {
+            const double a0 = pan[(size_t)jl * d], a1 = pan[(size_t)(jl + 1) * d];
+#pragma unroll
+            for (int c = 0; c < NW; ++c) {
+                const double2 xv = *reinterpret_cast<const double2*>(base + (size_t)c * stride + j0 + jl);
+                acc[c] = Ar<STRICT>::mad(a0, xv.x, acc[c]);
+                acc[c] = Ar<STRICT>::mad(a1, xv.y, acc[c]);
+            }
+        }
+        coop_barrier<NW>();   // every warp is done with buffer b
+        if (threadIdx.x == 0 && k + 2 < np) {
+            const int j2 = (k + 2) * COOP_PANEL_COLS;
+            const int nc2 = (d - j2 < COOP_PANEL_COLS) ? d - j2 : COOP_PANEL_COLS;
+            bulk_load_panel(panels + (size_t)b * pan_elems, A + (size_t)j2 * d, (unsigned)((size_t)nc2 * d * sizeof(double)), mbar + b);
+        }
+    }
+    if (row_ok) {
+#pragma unroll
+        for (int c = 0; c < NW; ++c) base[(size_t)c * stride + half + i] = acc[c];
+    }
+}
+
+// producer prologue: the first two panels (their buffers are free: the previous product ended with a CTA barrier)
+__device__ __forceinline__ void coop_panels_prologue(const double* __restrict__ A, int d, double* panels, unsigned long long* mbar)
+{
+    if (threadIdx.x == 0) {
+        const int np = (d + COOP_PANEL_COLS - 1) / COOP_PANEL_COLS;
+        for (int k = 0; k < 2 && k < np; ++k) {
+            const int j0 = k * COOP_PANEL_COLS;
+            const int nc = (d - j0 < COOP_PANEL_COLS) ? d - j0 : COOP_PANEL_COLS;
+            bulk_load_panel(panels + (size_t)k * COOP_PANEL_COLS * d, A + (size_t)j0 * d, (unsigned)((size_t)nc * d * sizeof(double)), mbar + k);
+        }
+    }
+}
+
+// The whole cooperative round for one context; active chains (draining = false) and the drain loop of warps whose chain
+// is finished (draining = true) call exactly this, so every warp of the CTA passes the same barriers.  *w.n_active (chains
+// of the CTA still running) only changes between a round's last barrier and the next round's first one, so the value read
+// after the first barrier is the same in every warp; it can only be zero when every warp is draining.
+// A warp that needs a product posts it in *w.want before the first barrier; warps that are busy with work that needs
+// no product (the NUTS tree replay) poll *w.want and attend the round as helpers (draining = true) within one step of
+// their own work, so a requester never waits for another chain's whole replay.  The counter is cleared inside the
+// round, when every warp is present and nobody can be posting.
+template <bool STRICT, class Ctx> __device__ __forceinline__ bool coop_round(const double* __restrict__ A, const Ctx& w, bool draining)
+{
+    constexpr int NW = Ctx::coop;
+    if (!draining && w.lane == 0) atomicAdd(w.want, 1);
+    coop_barrier<NW>();   // every chain's x is staged
+    if (draining && *reinterpret_cast<const volatile int*>(w.n_active) == 0) return false;
+    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(w.want) = 0;   // visible to everyone after the last barrier
+    if (w.panels) {
+        coop_panels_prologue(A, w.d, w.panels, w.mbar);
+        coop_gemv_body_tma<NW, STRICT>(A, w.d, w.warp, w.lane, w.coop_base, w.coop_stride, w.panels, w.mbar, w.phase);
+    } else {
+        coop_gemv_body<NW, STRICT>(A, w.d, w.warp, w.lane, w.coop_base, w.coop_stride);
+    }
+    coop_barrier<NW>();   // every chain's y is complete
+    return true;
+}
+
+// y = A x through the cooperative path when the context asks for it (NW is the CTA's warp count), else per warp.
+template <int EPL, bool STRICT, class Ctx>
+__device__ __forceinline__ void dense_matvec(const double* __restrict__ A, const Ctx& w, const double (&x)[EPL], double (&y)[EPL])
+{
+    stage_vec<EPL>(w.scr, w.d, w.lane, x);
+    if constexpr (Ctx::coop > 0) {
+        coop_round<STRICT>(A, w, false);
+        load_vec<EPL>(w.scr + (w.coop_stride >> 1), w.d, w.lane, y);
+    } else {
+        gemv_cm<EPL, STRICT>(A, w.d, w.lane, w.scr, 1.0, y);
+    }
 }
 
 }  // namespace mcmcb200

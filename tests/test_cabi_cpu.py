@@ -22,7 +22,7 @@ def api():
 
 
 def test_every_declared_symbol_is_exported(api):
-    header = open(os.path.join(ROOT, "include", "mcmc_b200.h")).read()
+    header = "".join(open(os.path.join(ROOT, "include", h)).read() for h in sorted(os.listdir(os.path.join(ROOT, "include"))) if h.endswith(".h"))
     declared = set(re.findall(r"\b(mcmcb200_[a-z0-9_]+)\s*\(", header))
     assert len(declared) >= 16
     lib = ctypes.CDLL(api.LIB_PATH)

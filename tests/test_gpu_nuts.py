@@ -138,3 +138,46 @@ def test_many_chains_d256_moments(engine):
     v = proj.var(axis=0)
     assert np.abs(np.log(v / lam)).max() < 0.35, np.abs(np.log(v / lam)).max()
     assert r["n_accept"].mean() / 20 > 0.5
+
+
+@pytest.mark.parametrize("d,C", [(200, 100), (256, 72), (64, 66), (129, 70)])   # 129: odd n_dim takes the direct-load fallback
+def test_cooperative_kernel_matches_independent_kernel_and_oracle(engine, oracle, monkeypatch, d, C):
+    """Dense targets with >= 64 chains run 8 chains per CTA with CTA-cooperative gradients (the target's matrix is read
+    once per 8 gradients, nuts.cu).  The cooperative kernel must be bit-identical to the independent-warps kernel —
+    including ragged n_dim, a chain count that is not a multiple of 8 and chains that finish at different times (the
+    drain loop) — and a subset of its chains is checked against the oracle (C4-shaped target: N(0, Sigma), cond 1e3)."""
+    rng = np.random.default_rng(d)
+    q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+    lam = np.logspace(0, 3, d)
+    P = (q * (1.0 / lam)) @ q.T
+    P = (P + P.T) / 2
+    x0 = rng.normal(size=(C, d)) * 0.5
+    kw = dict(target_data=P.ravel(), step_size=0.05, n_adapt_draws=6, n_burnin=6, n_keep=6, rng_mode=engine.api.RNG_PHILOX, seed=77,
+              max_tree_depth=6)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("MCMCB200_NUTS_COOP", mode)
+        for arith in (engine.api.ARITH_STRICT, engine.api.ARITH_FAST):
+            res[mode, arith] = engine.nuts(x0, "dense_gauss", arith=arith, want_logp=True, **kw)
+    monkeypatch.delenv("MCMCB200_NUTS_COOP")
+    for arith in (engine.api.ARITH_STRICT, engine.api.ARITH_FAST):
+        a, b = res["1", arith], res["0", arith]
+        assert np.array_equal(a["draws"], b["draws"])
+        assert np.array_equal(a["logp"], b["logp"])
+        assert np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["n_leapfrog"], b["n_leapfrog"])
+        assert np.array_equal(a["step_size"], b["step_size"])
+    assert len(set(res["1", engine.api.ARITH_FAST]["n_leapfrog"].tolist())) > 4   # chains really do finish at different times
+    # auto selection (>= 64 chains -> cooperative) gives the same thing
+    auto = engine.nuts(x0, "dense_gauss", arith=engine.api.ARITH_FAST, **kw)
+    assert np.array_equal(auto["draws"], res["1", engine.api.ARITH_FAST]["draws"])
+    # oracle on a subset of chains, adaptation off (see the module docstring)
+    kw2 = dict(kw, n_adapt_draws=0, n_burnin=2, n_keep=6)
+    monkeypatch.setenv("MCMCB200_NUTS_COOP", "1")
+    r = engine.nuts(x0, "dense_gauss", arith=engine.api.ARITH_FAST, **kw2)
+    monkeypatch.delenv("MCMCB200_NUTS_COOP")
+    st = ol.Settings(n_burnin=2, n_keep=6, step_size=0.05, n_adapt_draws=0, max_tree_depth=6)
+    for c in (0, C // 2 + 1, C - 1):
+        o = oracle.run_chain(ol.NUTS, ol.TGT_DENSE_GAUSS, P.ravel(), x0[c], st, seed=77, rng_mode=ol.RNG_PHILOX, chain_id=c,
+                             sum_mode=ol.SUM_WARP)
+        assert np.abs(r["draws"][c] - o["draws"]).max() <= TOL
+        assert r["n_accept"][c] == o["n_accept"]

@@ -40,12 +40,15 @@ using namespace mcmcb200;
 #define C2_LS 10
 #endif
 #ifndef C2_UNR
-#define C2_UNR 2
+#define C2_UNR 1
+#endif
+#ifndef C2_EPL
+#define C2_EPL 4
 #endif
 
 int main(int argc, char** argv)
 {
-    const int C = argc > 1 ? atoi(argv[1]) : 4096, d = 128, nb = 100, nk = 1000, reps = argc > 2 ? atoi(argv[2]) : 6;
+    const int C = argc > 1 ? atoi(argv[1]) : 4096, d = 32 * C2_EPL, nb = 100, nk = argc > 3 ? atoi(argv[3]) : 1000, reps = argc > 2 ? atoi(argv[2]) : 6;
     std::vector<double> x0((size_t)C * d);
     for (int c = 0; c < C; ++c)
         for (int j = 0; j < d; ++j) x0[(size_t)c * d + j] = sin(0.37 * c + 0.11 * j);
@@ -61,11 +64,11 @@ int main(int argc, char** argv)
     a.draws = ddraws; a.logp = nullptr; a.n_accept = dacc; a.stream = 0; a.strict = false; a.lb = a.ub = nullptr;
     a.n_burnin = nb; a.n_keep = nk; a.n_leap = 10; a.eps = 0.1; a.S_cm = nullptr; a.Minv_cm = nullptr;
 #ifdef C2_OLD
-    auto kern = hmc_kernel<IsoGauss, 4, false, false, RNG_PHILOX, true, false>;
+    auto kern = hmc_kernel<IsoGauss, C2_EPL, false, false, RNG_PHILOX, true, false>;
 #else
-    auto kern = hmc_pipe_kernel<IsoGauss, 4, C2_LS, C2_UNR>;
+    auto kern = hmc_pipe_kernel<IsoGauss, C2_EPL, C2_LS, C2_UNR>;
 #endif
-    const size_t smem = (size_t)WARPS_PER_BLOCK * 128 * sizeof(double);
+    const size_t smem = (size_t)WARPS_PER_BLOCK * d * sizeof(double);
     cudaFuncAttributes fa;
     CK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0;
@@ -85,7 +88,7 @@ int main(int argc, char** argv)
         if (r > 0) { best = ms < best ? ms : best; sum += ms; }
     }
     // checksum over a slice: draws of chains 0..63, plus all accept counts
-    std::vector<double> h((size_t)64 * nk * d);
+    std::vector<double> h((size_t)(C < 64 ? C : 64) * nk * d);
     std::vector<long long> acc(C);
     CK(cudaMemcpy(h.data(), ddraws, h.size() * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(acc.data(), dacc, (size_t)C * 8, cudaMemcpyDeviceToHost));
@@ -94,7 +97,7 @@ int main(int argc, char** argv)
     long long na = 0;
     for (int c = 0; c < C; ++c) na += acc[c];
     printf("%-28s regs=%d occ=%d  best %.4f ms  mean %.4f ms  -> %.3e draws/s  roofline %.3f | sum %.10e var %.10f acc %lld last %.17g\n", argv[0],
-           fa.numRegs, occ, best, sum / (reps - 1), (double)C * (nb + nk) / best * 1e3, (double)C * (nb + nk) * 2048.0 / (best * 1e-3) / 6454.6e9, cs,
+           fa.numRegs, occ, best, sum / (reps - 1), (double)C * (nb + nk) / best * 1e3, (double)C * (nb + nk) * 16.0 * d / (best * 1e-3) / 6454.6e9, cs,
            cs2 / h.size(), na, h[h.size() - 1]);
     return 0;
 }
