@@ -104,6 +104,31 @@ def ref_lib():
     return ol, None, "port"
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Run this rank on the host cores of the NUMA node its GPU hangs off (so the pinned staging buffers of the end-to-end
+    leg are allocated there and the D2H stream does not cross the socket interconnect).  Best effort: any missing piece
+    (sysfs entry, empty intersection with the cpuset) leaves the affinity untouched.  Returns a short description."""
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return "numa node %d has no allowed cpu" % node
+        os.sched_setaffinity(0, allowed)
+        return "numa node %d (%d cpus)" % (node, len(allowed))
+    except Exception as e:  # noqa: BLE001
+        return "not bound (%s)" % type(e).__name__
+
+
 def usable_cpus():
     """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota if there is one."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -198,6 +223,7 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torchrun --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -347,7 +373,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "chains_total": world * C, "leapfrog_steps_per_s": value * LEAP,
-                       "rng": "Philox4x32-10 in-kernel", "arith": "fast (FMA)", "parallelism": "chains sharded, %d rank(s)" % world,
+                       "rng": "Philox4x32-10 in-kernel", "arith": "fast (FMA)", "parallelism": "chains sharded, %d rank(s)" % world, "host_binding_rank0": numa,
                        "l2": "256 MiB buffer (2x L2) written between timed iterations; each step also writes 4.19 GB of draws (33x L2)",
                        "accept_rate": acc_rate, "wall_ms_per_step_rank0": wall / args.steps * 1e3},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -41,6 +41,7 @@
 #include <cstring>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mcmc_b200.h"
@@ -205,6 +206,9 @@ struct b200_settings_t {
     int arith = MCMCB200_ARITH_FAST;
     int chol_mode = b200_detail::default_chol;
     int device = -1;
+    // many-chain calls: CUDA ordinals to shard the chains over (contiguous shards, one host thread per device, each
+    // shard with its global chain offset, so the result does not depend on the list); empty = `device` alone
+    std::vector<int> devices;
     std::vector<size_t> n_accept_per_chain;  // returned by many-chain calls
 };
 struct algo_settings_t {
@@ -307,7 +311,38 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
     out.draws_out = buf.data();
     out.draws_mem = MCMCB200_MEM_HOST;
     out.n_accept_draws = acc.data();
-    if (fn(pr, rng, out, s) != MCMCB200_OK) return false;
+    const size_t n_dev = s.b200.devices.size();
+    if (n_dev <= 1 || n_chains < 2) {
+        if (n_dev == 1) pr.device = s.b200.devices[0];
+        if (fn(pr, rng, out, s) != MCMCB200_OK) return false;
+    } else {
+        // one blocking call drives the listed GPUs (SURVEY §8b "Threading"): the C ABI is re-entrant per host thread
+        const size_t n_sh = n_dev < n_chains ? n_dev : n_chains;
+        std::vector<int> rcs(n_sh, MCMCB200_OK);
+        std::vector<std::string> errs(n_sh);
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < n_sh; ++g) {
+            const size_t c0 = n_chains * g / n_sh, c1 = n_chains * (g + 1) / n_sh;
+            th.emplace_back([&, g, c0, c1]() {
+                mcmcb200_problem_t p2 = pr;
+                mcmcb200_output_t o2 = out;
+                p2.n_chains = static_cast<int64_t>(c1 - c0);
+                p2.initial_vals = pr.initial_vals + c0 * d;
+                p2.chain_offset = pr.chain_offset + static_cast<int64_t>(c0);
+                p2.device = s.b200.devices[g];
+                o2.draws_out = buf.data() + c0 * n_keep * d;
+                o2.n_accept_draws = acc.data() + c0;
+                rcs[g] = fn(p2, rng, o2, s);
+                if (rcs[g] != MCMCB200_OK) errs[g] = mcmcb200_last_error();   // the C ABI's error text is per thread
+            });
+        }
+        for (auto& t : th) t.join();
+        for (size_t g = 0; g < n_sh; ++g)
+            if (rcs[g] != MCMCB200_OK) {
+                wrapper_error() = errs[g];
+                return false;
+            }
+    }
     unpack(buf, n_chains, n_keep, d, single, cube);
     if (sp) {  // written back only if a settings object was passed (src/hmc.cpp:220-222)
         *n_accept_field = static_cast<size_t>(acc[0]);

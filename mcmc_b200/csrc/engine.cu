@@ -40,14 +40,24 @@ int epl_for_dim(int d)
 enum Slot { SLOT_TDATA = 0, SLOT_LB, SLOT_UB, SLOT_X0, SLOT_DRAWS, SLOT_LOGP, SLOT_NACC, SLOT_TAPE, SLOT_MAT_A, SLOT_MAT_B, SLOT_MAT_C,
             SLOT_STEP, SLOT_NLF, SLOT_WORK, SLOT_EVAL_X, SLOT_EVAL_V, SLOT_EVAL_G, SLOT_COUNT };
 constexpr int MAX_DEVICES = 16;
+// The scratch belongs to the calling HOST THREAD: like the reference's samplers (no globals, src/hmc.cpp) the run calls
+// are re-entrant — several host threads may sample at the same time, on the same or on different devices, each with its
+// own buffers.  A thread's buffers are freed when it exits (or by mcmcb200_release_workspace()).
 struct Buf { void* p = nullptr; size_t bytes = 0; };
-static Buf g_pool[MAX_DEVICES][SLOT_COUNT];
-static std::mutex g_pool_mu;
+struct Pool {
+    Buf b[MAX_DEVICES][SLOT_COUNT];
+    ~Pool()
+    {
+        for (int d = 0; d < MAX_DEVICES; ++d)
+            for (int s = 0; s < SLOT_COUNT; ++s)
+                if (b[d][s].p) cudaFree(b[d][s].p);   // errors at process teardown (runtime already unloading) are harmless
+    }
+};
+static thread_local Pool g_pool;
 
 static int pool_get(int dev, Slot s, size_t bytes, void** out)
 {
-    std::lock_guard<std::mutex> lk(g_pool_mu);
-    Buf& b = g_pool[dev][s];
+    Buf& b = g_pool.b[dev][s];
     if (bytes == 0) bytes = 8;
     if (b.bytes < bytes) {
         if (b.p) cudaFree(b.p);
@@ -629,10 +639,9 @@ void mcmcb200_release_workspace(void)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEVICES) return;
-    std::lock_guard<std::mutex> lk(g_pool_mu);
     for (int s = 0; s < SLOT_COUNT; ++s) {
-        if (g_pool[dev][s].p) cudaFree(g_pool[dev][s].p);
-        g_pool[dev][s] = Buf();
+        if (g_pool.b[dev][s].p) cudaFree(g_pool.b[dev][s].p);
+        g_pool.b[dev][s] = Buf();
     }
 }
 

@@ -125,16 +125,36 @@ extern "C" int mcmcb200_summarize_draws(const double* draws, int32_t draws_mem, 
     if (dev != prev) MCMCB200_CUDA_TRY(cudaSetDevice(dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 
-    struct DevBuf { void* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } } up, stats, res;
+    // grow-only scratch of the calling host thread, per device (same policy as the engine's workspace)
+    struct Scratch {
+        void* p[16][3] = {};
+        size_t n[16][3] = {};
+        ~Scratch() { for (auto& d : p) for (void* q : d) if (q) cudaFree(q); }
+        int get(int dev_, int slot, size_t bytes, void** out_)
+        {
+            if (n[dev_][slot] < bytes) {
+                if (p[dev_][slot]) cudaFree(p[dev_][slot]);
+                p[dev_][slot] = nullptr; n[dev_][slot] = 0;
+                MCMCB200_CUDA_TRY(cudaMalloc(&p[dev_][slot], bytes));
+                n[dev_][slot] = bytes;
+            }
+            *out_ = p[dev_][slot];
+            return MCMCB200_OK;
+        }
+    };
+    static thread_local Scratch scratch;
+    if (dev >= 16) { set_error("device %d beyond the supported 16", dev); return MCMCB200_ERR_INVALID_ARG; }
+    struct { void* p = nullptr; } up, stats, res;
+    int rc;
     const size_t n_elem = (size_t)n_chains * (size_t)n_keep * (size_t)n_dim, n_cd = (size_t)n_chains * (size_t)n_dim;
     const double* d_draws = draws;
     if (draws_mem == MCMCB200_MEM_HOST) {
-        MCMCB200_CUDA_TRY(cudaMalloc(&up.p, n_elem * sizeof(double)));
+        if ((rc = scratch.get(dev, 0, n_elem * sizeof(double), &up.p))) return rc;
         MCMCB200_CUDA_TRY(cudaMemcpyAsync(up.p, draws, n_elem * sizeof(double), cudaMemcpyHostToDevice, st));
         d_draws = static_cast<const double*>(up.p);
     }
-    MCMCB200_CUDA_TRY(cudaMalloc(&stats.p, 2 * n_cd * sizeof(double)));
-    MCMCB200_CUDA_TRY(cudaMalloc(&res.p, 3 * (size_t)n_dim * sizeof(double)));
+    if ((rc = scratch.get(dev, 1, 2 * n_cd * sizeof(double), &stats.p))) return rc;
+    if ((rc = scratch.get(dev, 2, 3 * (size_t)n_dim * sizeof(double), &res.p))) return rc;
     double* cmean = static_cast<double*>(stats.p);
     double* cvar = cmean + n_cd;
     double* r = static_cast<double*>(res.p);

@@ -63,6 +63,16 @@ int main()
         if (!mcmc::hmc(x2, mcmc::device_kernel("iso_gauss"), draws, nullptr, s2)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
         int same = (cube.n_mat() == C) && std::memcmp(cube.mat(2).data(), draws.data(), sizeof(double) * 20 * d) == 0;
         std::printf("multichain_consistent %d %zu\n", same, s.b200.n_accept_per_chain.size());
+        // the same call sharded over a device list (one host thread per entry; the list {0, 0, 0} also exercises the
+        // re-entrancy of the C ABI: three concurrent calls on one device) must return the same cube
+        mcmc::algo_settings_t s3 = s;
+        s3.b200.devices = {0, 0, 0};
+        mcmc::Cube_t cube3;
+        if (!mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), cube3, nullptr, s3)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        int same3 = (cube3.n_mat() == C);
+        for (size_t c = 0; c < C && same3; ++c) same3 = std::memcmp(cube3.mat(c).data(), cube.mat(c).data(), sizeof(double) * 20 * d) == 0;
+        same3 = same3 && s3.b200.n_accept_per_chain == s.b200.n_accept_per_chain;
+        std::printf("sharded_consistent %d\n", same3);
     }
     {   // box constraints, written like reference user code (golden case hmc_box_d4: all four bound types)
         const double inf = INFINITY;

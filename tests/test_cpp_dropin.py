@@ -52,10 +52,13 @@ def test_dropin_program_reproduces_reference_goldens(engine):
         elif tok[0] == "multichain_consistent":
             assert tok[1] == "1" and tok[2] == "3"
             seen.add(tok[0])
+        elif tok[0] == "sharded_consistent":
+            assert tok[1] == "1"
+            seen.add(tok[0])
         elif tok[0] == "bounds_refused":
             assert tok[1] == "1"
             seen.add(tok[0])
-    assert seen == {"G2_hmc_d3", "G3_mala_d3", "G4_rmhmc_normal", "rwmh_d3", "multichain_consistent", "hmc_box_d4", "bounds_refused"}
+    assert seen == {"G2_hmc_d3", "G3_mala_d3", "G4_rmhmc_normal", "rwmh_d3", "multichain_consistent", "sharded_consistent", "hmc_box_d4", "bounds_refused"}
 
 
 @pytest.mark.gpu

@@ -62,3 +62,25 @@ def test_library_tape_matches_oracle_stream(engine, oracle):
     td = np.array([100.0, xs.mean(), ((xs - xs.mean()) ** 2).sum()])
     o = oracle.run_chain(ol.RMHMC, ol.TGT_NORMAL_MODEL, td, [3, 3], st, seed=43, record_tape=100)
     assert np.array_equal(engine.api.mt19937_tape(43, 2, 5, 2), o["tape"])
+
+
+def test_run_calls_are_reentrant_across_host_threads(engine):
+    """Like the reference's samplers (no globals), the run calls may be issued from several host threads at once, on
+    the same device: every thread has its own device scratch.  Concurrent results equal the sequential ones."""
+    import threading
+
+    d, C = 128, 64
+    x0 = ol.c2_initial(4 * C, d)
+    kw = dict(n_leap_steps=10, step_size=0.1, n_burnin=20, n_keep=50, rng_mode=engine.api.RNG_PHILOX, seed=9)
+    want = [engine.hmc(x0[i * C:(i + 1) * C], "iso_gauss", chain_offset=i * C, **kw)["draws"].copy() for i in range(4)]
+    got = [None] * 4
+
+    def work(i):
+        for _ in range(5):
+            got[i] = engine.hmc(x0[i * C:(i + 1) * C], "iso_gauss", chain_offset=i * C, **kw)["draws"]
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(4):
+        assert np.array_equal(got[i], want[i]), i
