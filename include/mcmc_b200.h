@@ -64,9 +64,12 @@ typedef enum {
     MCMCB200_TARGET_DIAG_GAUSS = 1,  /* log pi = -1/2 sum_i w_i x_i^2 ; data = w[n_dim]                  */
     MCMCB200_TARGET_DENSE_GAUSS = 2, /* log pi = -1/2 x' P x ; data = P[n_dim^2], symmetric             */
     MCMCB200_TARGET_LINREG = 3,      /* log pi = -1/2 t' A t + b' t ; data = A[n_dim^2] (sym), b[n_dim]  */
-    MCMCB200_TARGET_NORMAL_MODEL = 4 /* Normal(mu, sigma) likelihood of examples/eigen/*_normal.cpp on
+    MCMCB200_TARGET_NORMAL_MODEL = 4, /* Normal(mu, sigma) likelihood of examples/eigen/*_normal.cpp on
                                         sufficient statistics; n_dim = 2, data = {n, xbar, sum (x-xbar)^2};
                                         carries the Fisher metric used by mcmcb200_rmhmc_run */
+    MCMCB200_TARGET_FUNNEL = 5       /* Neal's funnel (BASELINE config 5): x[0] = v ~ N(0, 3^2), x[i] | v ~ N(0, e^v);
+                                        n_dim >= 2, no data; metrics for mcmcb200_rmhmc_run (n_dim <= 64):
+                                        1 = "funnel_fisher" diag(1/9 + (n_dim-1)/2, e^-v, ..., e^-v) (default) */
 } mcmcb200_target_t;
 
 typedef enum {
@@ -161,6 +164,8 @@ typedef struct mcmcb200_rmhmc_settings {
     int64_t n_fp_steps; /* default 5 */
     int32_t chol_mode;
     int32_t arith;
+    int32_t metric_id;  /* which of the target's registered metrics plays the reference's tensor_fn; 0 = its default */
+    int32_t reserved0;
 } mcmcb200_rmhmc_settings_t;
 
 /* rwmh_settings_t (mcmc_structs.hpp:138-149) */
@@ -205,7 +210,7 @@ int mcmcb200_rmhmc_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* 
 int mcmcb200_rwmh_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
                       const mcmcb200_rwmh_settings_t* settings, mcmcb200_output_t* out);
 
-/* Target registry: id by name ("iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model"), -1 if unknown;
+/* Target registry: id by name ("iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model", "funnel"), -1 if unknown;
    number of doubles the target's data blob must hold for a given n_dim (-1 if unknown / n_dim invalid). */
 int mcmcb200_target_lookup(const char* name);
 int64_t mcmcb200_target_data_len(int target_id, int32_t n_dim);

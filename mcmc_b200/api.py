@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmcmc_b200.so")
 
 OK, ERR_INVALID_ARG, ERR_UNKNOWN_TARGET, ERR_UNSUPPORTED, ERR_CUDA, ERR_OOM = range(6)
-TARGET_ISO_GAUSS, TARGET_DIAG_GAUSS, TARGET_DENSE_GAUSS, TARGET_LINREG, TARGET_NORMAL_MODEL = range(5)
+TARGET_ISO_GAUSS, TARGET_DIAG_GAUSS, TARGET_DENSE_GAUSS, TARGET_LINREG, TARGET_NORMAL_MODEL, TARGET_FUNNEL = range(6)
 RNG_PHILOX, RNG_MT19937_TAPE, RNG_USER_TAPE = range(3)
 MEM_HOST, MEM_DEVICE = 0, 1
 ARITH_FAST, ARITH_STRICT = 0, 1
@@ -59,7 +59,7 @@ class NutsSettings(ctypes.Structure):
 
 class RmhmcSettings(ctypes.Structure):
     _fields_ = [("n_burnin_draws", c_i64), ("n_keep_draws", c_i64), ("n_leap_steps", c_i64), ("step_size", c_dbl),
-                ("n_fp_steps", c_i64), ("chol_mode", c_i32), ("arith", c_i32)]
+                ("n_fp_steps", c_i64), ("chol_mode", c_i32), ("arith", c_i32), ("metric_id", c_i32), ("reserved0", c_i32)]
 
 
 class Output(ctypes.Structure):
@@ -249,12 +249,12 @@ def nuts(initial_vals, target, step_size=1.0, n_adapt_draws=1000, target_accept_
 
 
 def rmhmc(initial_vals, target, n_leap_steps=1, step_size=1.0, n_fp_steps=5, chol_mode=CHOL_EIGEN_LLT, arith=ARITH_FAST,
-          **kw):
+          metric_id=0, **kw):
     """Many-chain mcmc::rmhmc (src/rmhmc.cpp:298-325); the metric is the one registered with the target."""
     c = _split(kw)
     assert not kw, kw
     run = _Run("rmhmc", initial_vals, target, **c)
-    st = RmhmcSettings(c["n_burnin"], c["n_keep"], int(n_leap_steps), float(step_size), int(n_fp_steps), chol_mode, arith)
+    st = RmhmcSettings(c["n_burnin"], c["n_keep"], int(n_leap_steps), float(step_size), int(n_fp_steps), chol_mode, arith, int(metric_id), 0)
     _check(run.lib.mcmcb200_rmhmc_run(ctypes.byref(run.problem), ctypes.byref(run.rng), ctypes.byref(st), ctypes.byref(run.out)))
     return run.result()
 

@@ -17,10 +17,10 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcmc_b200.so")
 
-CU_SOURCES = ["engine.cu", "dispatch.cu", "hmc_wide.cu", "mala_wide.cu", "rmhmc.cu", "util_kernels.cu", "summary.cu"]
+CU_SOURCES = ["engine.cu", "dispatch.cu", "hmc_wide.cu", "mala_wide.cu", "rmhmc.cu", "util_kernels.cu", "summary.cu", "rmhmc_general.cu"]
 # compiled once per registered target (-DMCMCB200_TARGET_SLICE=k), so the big template fan-out builds in parallel
 SLICED_SOURCES = ["hmc.cu", "nuts.cu", "mala.cu", "rwmh.cu"]
-N_TARGETS = 5
+N_TARGETS = 6
 CPP_SOURCES = ["host_tape.cpp", "host_linalg.cpp"]
 
 NVCC_FLAGS = [

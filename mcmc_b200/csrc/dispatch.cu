@@ -20,7 +20,7 @@ namespace mcmcb200
     int launch_rwmh_slice##k(const RwmhLaunch& a);
 DECL(0)
 #ifndef MCMCB200_FAST_BUILD
-DECL(1) DECL(2) DECL(3) DECL(4)
+DECL(1) DECL(2) DECL(3) DECL(4) DECL(5)
 #endif
 #undef DECL
 
@@ -31,6 +31,7 @@ DECL(1) DECL(2) DECL(3) DECL(4)
     case 2: return MCMCB200_SLICE_OR_MISSING(fn##_slice2(a));                                         \
     case 3: return MCMCB200_SLICE_OR_MISSING(fn##_slice3(a));                                         \
     case 4: return MCMCB200_SLICE_OR_MISSING(fn##_slice4(a));                                         \
+    case 5: return MCMCB200_SLICE_OR_MISSING(fn##_slice5(a));                                         \
     default:                                                                 \
         set_error(what ": unknown target id %d", a.target_id);               \
         return MCMCB200_ERR_UNKNOWN_TARGET;                                  \

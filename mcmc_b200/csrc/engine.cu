@@ -108,6 +108,7 @@ static int64_t target_data_len(int target_id, int d)
     case MCMCB200_TARGET_DENSE_GAUSS: return (int64_t)d * d;
     case MCMCB200_TARGET_LINREG: return (int64_t)d * d + d;
     case MCMCB200_TARGET_NORMAL_MODEL: return d == 2 ? 3 : -1;
+    case MCMCB200_TARGET_FUNNEL: return d >= 2 ? 0 : -1;
     default: return -1;
     }
 }
@@ -360,6 +361,7 @@ void mcmcb200_rmhmc_settings_default(mcmcb200_rmhmc_settings_t* s)
     s->n_leap_steps = 1;
     s->step_size = 1.0;
     s->n_fp_steps = 5;
+    s->metric_id = 0;
     s->chol_mode = MCMCB200_CHOL_EIGEN_LLT;
     s->arith = MCMCB200_ARITH_FAST;
 }
@@ -549,8 +551,26 @@ int mcmcb200_rmhmc_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, 
     a.eps = st->step_size;
     a.chol_mode = st->chol_mode;
     a.cons_term = (double)(0.5 * (double)(size_t)pr->n_dim * 1.83787706640934548356L);
+    a.metric_id = st->metric_id;
+    a.work = nullptr;
+    a.work_stride = 0;
+    // the 2-parameter Normal model runs thread-per-chain in registers (rmhmc.cu); everything else — and the Normal model
+    // too when MCMCB200_RMHMC_GENERAL=1 (tests compare the two kernels) — runs warp-per-chain with the metric algebra
+    // in a per-chain scratch area (rmhmc_general.cu)
+    bool general = pr->target_id != MCMCB200_TARGET_NORMAL_MODEL;
+    if (const char* e = std::getenv("MCMCB200_RMHMC_GENERAL")) general = general || e[0] == '1';
+    if (general) {
+        if (!rmhmc_general_supported(pr->target_id, st->metric_id, pr->n_dim)) {
+            set_error("rmhmc: target %d has no registered metric %d for n_dim=%d (general kernel: n_dim <= 64)", pr->target_id, st->metric_id, pr->n_dim);
+            return MCMCB200_ERR_UNSUPPORTED;
+        }
+        a.work_stride = rmhmc_general_work_doubles(pr->n_dim);
+        void* wp = nullptr;
+        if ((rc = pool_get(s.scope.dev, SLOT_WORK, (size_t)pr->n_chains * (size_t)a.work_stride * sizeof(double), &wp))) return rc;
+        a.work = static_cast<double*>(wp);
+    }
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
-    if ((rc = launch_rmhmc(a))) return rc;
+    if ((rc = general ? launch_rmhmc_general(a) : launch_rmhmc(a))) return rc;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
     if (out->n_leapfrog_out)
         for (long long c = 0; c < pr->n_chains; ++c) out->n_leapfrog_out[c] = (st->n_burnin_draws + st->n_keep_draws) * st->n_leap_steps;
@@ -565,7 +585,7 @@ int mcmcb200_target_lookup(const char* name)
     static const struct { const char* n; int id; } tbl[] = {
         {"iso_gauss", MCMCB200_TARGET_ISO_GAUSS},     {"diag_gauss", MCMCB200_TARGET_DIAG_GAUSS},
         {"dense_gauss", MCMCB200_TARGET_DENSE_GAUSS}, {"linreg", MCMCB200_TARGET_LINREG},
-        {"normal_model", MCMCB200_TARGET_NORMAL_MODEL}};
+        {"normal_model", MCMCB200_TARGET_NORMAL_MODEL}, {"funnel", MCMCB200_TARGET_FUNNEL}};
     for (const auto& e : tbl)
         if (std::strcmp(e.n, name) == 0) return e.id;
     return -1;

@@ -75,6 +75,9 @@ struct RmhmcLaunch : CommonLaunch {
     double eps;
     int chol_mode;
     double cons_term;  // 0.5 * n_dim * log(2 pi), computed in long double then narrowed (src/rmhmc.cpp:188)
+    int metric_id;     // which of the target's registered metrics (0 = default)
+    double* work;      // general kernel: per-chain scratch for the d x d matrices and the two derivative cubes
+    long long work_stride;
 };
 
 struct EvalLaunch {
@@ -102,6 +105,10 @@ int launch_mala_wide(const MalaLaunch& a, double* work, int* launches);
 int launch_nuts(const NutsLaunch& a);
 int launch_rwmh(const RwmhLaunch& a);
 int launch_rmhmc(const RmhmcLaunch& a);
+// warp-per-chain kernel for general n_dim <= 64 (rmhmc_general.cu)
+bool rmhmc_general_supported(int target_id, int metric_id, int d);
+long long rmhmc_general_work_doubles(int d);
+int launch_rmhmc_general(const RmhmcLaunch& a);
 int launch_target_eval(const EvalLaunch& a);
 int launch_philox_stream(unsigned long long seed, long long chain, long long draw, int d, int n_unif, double* out_dev,
                          cudaStream_t stream);

@@ -159,6 +159,40 @@ struct NormalModel {
     }
 };
 
+// Neal's funnel (BASELINE config 5): x[0] = v ~ N(0, 3^2), x[i] | v ~ N(0, e^v), i >= 1; constants dropped:
+//   log pi = -v^2/18 - (d-1) v/2 - 1/2 e^-v S,  S = sum_{i>=1} x_i^2     (host twin: oracle/host_targets.hpp TGT_FUNNEL)
+struct Funnel {
+    static constexpr bool needs_scratch = false;
+    static constexpr bool dense_matrix = false;
+    static constexpr bool separable = false;
+    static constexpr bool per_element_data = false;
+    template <int EPL, bool STRICT, bool WANT_VALUE, bool WANT_GRAD, bool REDUCE = true, class Ctx = WarpCtx>
+    static __device__ __forceinline__ double eval(const double*, const Ctx& w, const double (&x)[EPL], double (&g)[EPL])
+    {
+        typedef Ar<STRICT> A;
+        const double v = __shfl_sync(FULL, x[0], 0);   // element 0 lives in slot 0 of lane 0
+        const double ev = exp(-v);
+        double xx[EPL];
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) xx[k] = (elem_index(w.lane, k) == 0) ? 0.0 : x[k];
+        const double S = warp_dot<EPL, STRICT>(xx, xx);   // the gradient of v needs the total, so it is always reduced
+        const double dm1 = (double)(w.d - 1);
+        const double hes = A::mul(A::mul(0.5, ev), S);
+        if (WANT_GRAD) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const int j = elem_index(w.lane, k);
+                g[k] = (j == 0) ? A::add(A::sub((-v) / 9.0, dm1 / 2.0), hes) : ((j < w.d) ? -A::mul(ev, x[k]) : 0.0);
+            }
+        }
+        if (WANT_VALUE) {
+            const double val = A::sub(A::sub((-A::mul(v, v)) / 18.0, A::mul(dm1, v) / 2.0), hes);
+            return (REDUCE || w.lane == 0) ? val : 0.0;
+        }
+        return 0.0;
+    }
+};
+
 }  // namespace mcmcb200
 
 // X-macro: (enum id, functor type).  MCMCB200_FAST_BUILD (developer builds for kernel tuning, see
@@ -166,7 +200,7 @@ struct NormalModel {
 // MCMCB200_TARGET_SLICE = k (build.py compiles hmc.cu / mala.cu / nuts.cu once per target, in parallel): the
 // translation unit instantiates the kernels of target k only and exports launch_<sampler>_slice<k>; the
 // by-target dispatch lives in dispatch.cu.
-#define MCMCB200_N_TARGETS 5
+#define MCMCB200_N_TARGETS 6
 #if defined(MCMCB200_TARGET_SLICE)
 #if MCMCB200_TARGET_SLICE == 0
 #define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)
@@ -178,6 +212,8 @@ struct NormalModel {
 #define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_LINREG, LinReg)
 #elif MCMCB200_TARGET_SLICE == 4
 #define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_NORMAL_MODEL, NormalModel)
+#elif MCMCB200_TARGET_SLICE == 5
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_FUNNEL, Funnel)
 #else
 #error "MCMCB200_TARGET_SLICE out of range"
 #endif
@@ -193,6 +229,7 @@ struct NormalModel {
     X(MCMCB200_TARGET_DIAG_GAUSS, DiagGauss) \
     X(MCMCB200_TARGET_DENSE_GAUSS, DenseGauss) \
     X(MCMCB200_TARGET_LINREG, LinReg)        \
-    X(MCMCB200_TARGET_NORMAL_MODEL, NormalModel)
+    X(MCMCB200_TARGET_NORMAL_MODEL, NormalModel) \
+    X(MCMCB200_TARGET_FUNNEL, Funnel)
 #define MCMCB200_SLICED(name) name
 #endif

@@ -31,8 +31,10 @@ enum {
     TGT_DIAG_GAUSS   = 1,  // log pi = -1/2 sum_i w_i x_i^2, data = w[d]
     TGT_DENSE_GAUSS  = 2,  // log pi = -1/2 x' P x, data = P[d*d] row-major     (C4)
     TGT_LINREG       = 3,  // log pi = -1/2 t' A t + b' t, data = A[d*d], b[d]  (C3)
-    TGT_NORMAL_MODEL = 4   // 2-parameter Normal(mu, sigma) likelihood on sufficient statistics
+    TGT_NORMAL_MODEL = 4,  // 2-parameter Normal(mu, sigma) likelihood on sufficient statistics
                            // data = {n, xbar, M2 = sum (x - xbar)^2}  (examples/eigen/*_normal.cpp)
+    TGT_FUNNEL       = 5   // Neal's funnel (C5): x[0] = v ~ N(0, 3^2), x[i] | v ~ N(0, e^v), i >= 1; no data
+                           // log pi = -v^2/18 - (d-1) v/2 - 1/2 e^-v sum_{i>=1} x_i^2   (constants dropped)
 };
 
 inline int lane_of(int j) { return (j % 64) / 2; }
@@ -134,6 +136,19 @@ inline double value_and_grad(int target_id, const double* data, const double* x,
         }
         return ret;
     }
+    case TGT_FUNNEL: {
+        const double v = x[0];
+        const double ev = std::exp(-v);
+        t[0] = 0.0;
+        for (int j = 1; j < d; ++j) t[size_t(j)] = x[j] * x[j];
+        const double S = reduce_sum(t.data(), d, sum_mode);
+        const double dm1 = double(d - 1);
+        if (grad) {
+            grad[0] = ((-v) / 9.0 - dm1 / 2.0) + (0.5 * ev) * S;
+            for (int j = 1; j < d; ++j) grad[j] = -(ev * x[j]);
+        }
+        return ((-(v * v)) / 18.0 - (dm1 * v) / 2.0) - (0.5 * ev) * S;
+    }
     default:
         return std::nan("");
     }
@@ -152,6 +167,28 @@ inline void metric_normal_model(const double* data, const double* x, double* G, 
         for (int k = 0; k < 8; ++k) dG[k] = 0.0;
         for (int k = 0; k < 4; ++k) dG[4 + k] = (-2.0 * G[k]) / sigma;
     }
+}
+
+// Metric for TGT_FUNNEL, id 1 ("funnel_fisher"): minus the expected Hessian over x | v, a diagonal position-dependent
+// metric:  G = diag(1/9 + (d-1)/2, e^-v, ..., e^-v);  dG/dv = diag(0, -e^-v, ..., -e^-v);  dG/dx_i = 0.
+inline void metric_funnel_fisher(const double* x, int d, double* G, double* dG)
+{
+    const double ev = std::exp(-x[0]);
+    for (size_t k = 0; k < size_t(d) * d; ++k) G[k] = 0.0;
+    G[0] = 1.0 / 9.0 + double(d - 1) / 2.0;
+    for (int i = 1; i < d; ++i) G[size_t(i) * d + i] = ev;
+    if (dG) {
+        for (size_t k = 0; k < size_t(d) * d * d; ++k) dG[k] = 0.0;
+        for (int i = 1; i < d; ++i) dG[size_t(i) * d + i] = -ev;   // block 0 = dG/dv
+    }
+}
+
+// metric registered with a target (metric_id 0 = the target's default)
+inline bool metric(int target_id, int metric_id, const double* data, const double* x, int d, double* G, double* dG)
+{
+    if (target_id == TGT_NORMAL_MODEL && d == 2) { metric_normal_model(data, x, G, dG); return true; }
+    if (target_id == TGT_FUNNEL && (metric_id == 0 || metric_id == 1)) { metric_funnel_fisher(x, d, G, dG); return true; }
+    return false;
 }
 
 }  // namespace otgt

@@ -157,6 +157,7 @@ struct Ctx {
     int target_id; const double* tdata; int d; int sum_mode;
     bool identity;            // precond empty -> M = I (src/hmc.cpp:57)
     vec M, Minv, S;           // precond, inverse, "sqrt" factor (CHOL_LOWER semantics per chol_mode)
+    int metric_id = 0;        // RM-HMC: which of the target's registered metrics (0 = default)
     bool bounded;             // algo_settings_t::vals_bound
     std::vector<int> btype;   // determine_bounds_type: 1 none, 2 lower, 3 upper, 4 both
     vec lb, ub;
@@ -470,6 +471,7 @@ struct oracle_cfg_t {
     int mala_exact_dmvnorm;  // 1: two dmvnorm() with LLT log-det + QR solve (mala.ipp:63-64); 0: cancelled form
     double* tape_out; long tape_out_cap;  // optional: every variate consumed, in order
     int vals_bound; const double* lower; const double* upper;   // algo_settings_t::vals_bound / lower_bounds / upper_bounds
+    int metric_id;           // rmhmc: metric registered with the target (0 = default)
 };
 
 struct oracle_res_t {
@@ -859,7 +861,7 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
 }
 
 // ------------------------------------------------------------------ RM-HMC (src/rmhmc.cpp:30-294, Appendix E)
-// only TGT_NORMAL_MODEL carries a metric in this oracle (examples/eigen/rmhmc_normal.cpp)
+// metrics registered with a target: otgt::metric (TGT_NORMAL_MODEL: examples/eigen/rmhmc_normal.cpp; TGT_FUNNEL: C5)
 static void metric(const Ctx& c, const double* v, vec& G, vec* dG)
 {
     // box_tensor_fn (src/rmhmc.cpp:150-161): the metric is evaluated at inv_transform(v) when bounded
@@ -868,7 +870,7 @@ static void metric(const Ctx& c, const double* v, vec& G, vec* dG)
     if (dG) dG->assign(size_t(d) * d * d, 0.0);
     vec x(v, v + d);
     if (c.bounded) box_inv_transform(c, v, x.data());
-    otgt::metric_normal_model(c.tdata, x.data(), G.data(), dG ? dG->data() : nullptr);
+    otgt::metric(c.target_id, c.metric_id, c.tdata, x.data(), d, G.data(), dG ? dG->data() : nullptr);
 }
 
 // returns (eps * F)/2 with F_i = -grad_i + 1/2 (tr(A D_i) - ((A D_i)' q).(A q))   (src/rmhmc.cpp:132-146; Q16 sign)
@@ -897,6 +899,7 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     c.identity = true;   // precond_mat is never read (Q18)
+    c.metric_id = cfg->metric_id;
     setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;

@@ -32,6 +32,7 @@ struct tgt_ctx_t {
     int target_id;
     const double* data;
     int d;
+    int metric_id;
 };
 
 double log_kernel_cb(const mcmc::ColVec_t& vals, mcmc::ColVec_t* grad_out, void* ctx_v)
@@ -58,12 +59,12 @@ mcmc::Mat_t tensor_cb(const mcmc::ColVec_t& vals, mcmc::Cube_t* deriv_out, void*
     mcmc::Mat_t G(d, d);
     if (deriv_out) {
         std::vector<double> dG(size_t(d) * d * d);
-        otgt::metric_normal_model(ctx->data, vals.data(), G.data(), dG.data());
+        otgt::metric(ctx->target_id, ctx->metric_id, ctx->data, vals.data(), d, G.data(), dG.data());
         deriv_out->setZero(d, d, d);
         for (int i = 0; i < d; ++i)
             for (int k = 0; k < d * d; ++k) deriv_out->mat(i).data()[k] = dG[size_t(i) * d * d + k];
     } else {
-        otgt::metric_normal_model(ctx->data, vals.data(), G.data(), nullptr);
+        otgt::metric(ctx->target_id, ctx->metric_id, ctx->data, vals.data(), d, G.data(), nullptr);
     }
     return G;
 }
@@ -103,12 +104,13 @@ struct ref_settings_t {
     int vals_bound;        // algo_settings_t::vals_bound
     const double* lower;   // d entries (+-inf = unbounded side) when vals_bound
     const double* upper;
+    int metric_id;         // rmhmc: metric registered with the target (0 = default)
 };
 
 int ref_run_chain(int sampler, int target_id, const double* tdata, int d, const double* x0, const ref_settings_t* st,
                   unsigned long seed, double* draws_out, long* n_accept)
 {
-    tgt_ctx_t ctx = {target_id, tdata, d};
+    tgt_ctx_t ctx = {target_id, tdata, d, st->metric_id};
     mcmc::ColVec_t init(d);
     for (int j = 0; j < d; ++j) init(j) = x0[j];
 

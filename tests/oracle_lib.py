@@ -19,7 +19,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 HMC, MALA, NUTS, RMHMC, RWMH = 0, 1, 2, 3, 4
 RNG_MT, RNG_TAPE, RNG_PHILOX = 0, 1, 2
 SUM_SEQ, SUM_WARP = 0, 1
-TGT_ISO_GAUSS, TGT_DIAG_GAUSS, TGT_DENSE_GAUSS, TGT_LINREG, TGT_NORMAL_MODEL = 0, 1, 2, 3, 4
+TGT_ISO_GAUSS, TGT_DIAG_GAUSS, TGT_DENSE_GAUSS, TGT_LINREG, TGT_NORMAL_MODEL, TGT_FUNNEL = 0, 1, 2, 3, 4, 5
 
 _dp = ctypes.POINTER(ctypes.c_double)
 
@@ -41,6 +41,7 @@ class _RefSettings(ctypes.Structure):
         ("n_adapt_draws", ctypes.c_long), ("target_accept_rate", ctypes.c_double), ("gamma_val", ctypes.c_double),
         ("t0_val", ctypes.c_double), ("kappa_val", ctypes.c_double), ("max_tree_depth", ctypes.c_long),
         ("use_nuts_defaults", ctypes.c_int), ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p),
+        ("metric_id", ctypes.c_int),
     ]
 
 
@@ -55,7 +56,7 @@ class _OracleCfg(ctypes.Structure):
         ("rng_mode", ctypes.c_int), ("seed", ctypes.c_ulong), ("tape", ctypes.c_void_p), ("tape_len", ctypes.c_long),
         ("chain_id", ctypes.c_long), ("sum_mode", ctypes.c_int), ("mala_exact_dmvnorm", ctypes.c_int),
         ("tape_out", ctypes.c_void_p), ("tape_out_cap", ctypes.c_long),
-        ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p),
+        ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p), ("metric_id", ctypes.c_int),
     ]
 
 
@@ -69,7 +70,7 @@ class Settings(dict):
 
     DEFAULTS = dict(n_burnin=1000, n_keep=1000, n_leap_steps=1, step_size=1.0, precond=None, n_fp_steps=5,
                     n_adapt_draws=1000, target_accept_rate=0.55, gamma_val=0.05, t0_val=10.0, kappa_val=0.75,
-                    max_tree_depth=10, lower_bounds=None, upper_bounds=None)
+                    max_tree_depth=10, lower_bounds=None, upper_bounds=None, metric_id=0)
 
     def __init__(self, **kw):
         super().__init__(self.DEFAULTS)
@@ -116,7 +117,7 @@ class Reference:
         vb, lo, hi = _bounds(st, d, keep)
         return _RefSettings(st["n_burnin"], st["n_keep"], st["n_leap_steps"], st["step_size"], _ptr(pc),
                             st["n_fp_steps"], st["n_adapt_draws"], st["target_accept_rate"], st["gamma_val"],
-                            st["t0_val"], st["kappa_val"], st["max_tree_depth"], 0, vb, lo, hi)
+                            st["t0_val"], st["kappa_val"], st["max_tree_depth"], 0, vb, lo, hi, st["metric_id"])
 
     def run_chain(self, sampler, target_id, tdata, x0, st, seed):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
@@ -179,7 +180,7 @@ class Oracle:
                          st["target_accept_rate"], st["gamma_val"], st["t0_val"], st["kappa_val"],
                          st["max_tree_depth"], rng_mode, ctypes.c_ulong(seed), _ptr(tape_a),
                          0 if tape_a is None else tape_a.size, chain_id, sum_mode, mala_exact, _ptr(rec),
-                         record_tape, vb, lo, hi)
+                         record_tape, vb, lo, hi, st["metric_id"])
         draws = np.zeros((st["n_keep"], d))
         logp = np.zeros(st["n_keep"]) if want_logp else None
         res = _OracleRes()

@@ -49,12 +49,13 @@ def test_defaults_match_reference_structs(api):
 
 def test_target_registry(api):
     lib = api.load()
-    names = ["iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model"]
-    assert [lib.mcmcb200_target_lookup(n.encode()) for n in names] == [0, 1, 2, 3, 4]
+    names = ["iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model", "funnel"]
+    assert [lib.mcmcb200_target_lookup(n.encode()) for n in names] == [0, 1, 2, 3, 4, 5]
     assert lib.mcmcb200_target_lookup(b"nope") == -1
     f = lib.mcmcb200_target_data_len
     assert [f(t, 16) for t in range(4)] == [0, 16, 256, 272]
     assert f(4, 2) == 3 and f(4, 3) == -1 and f(9, 4) == -1
+    assert f(5, 64) == 0 and f(5, 1) == -1
 
 
 def test_host_side_reference_stream(api, oracle):

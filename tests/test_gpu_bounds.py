@@ -15,7 +15,7 @@ from test_gpu_nuts import _run_pair
 
 pytestmark = pytest.mark.gpu
 
-TNAME = {ol.TGT_ISO_GAUSS: "iso_gauss", ol.TGT_DIAG_GAUSS: "diag_gauss", ol.TGT_DENSE_GAUSS: "dense_gauss", ol.TGT_LINREG: "linreg",
+TNAME = {ol.TGT_FUNNEL: "funnel", ol.TGT_ISO_GAUSS: "iso_gauss", ol.TGT_DIAG_GAUSS: "diag_gauss", ol.TGT_DENSE_GAUSS: "dense_gauss", ol.TGT_LINREG: "linreg",
          ol.TGT_NORMAL_MODEL: "normal_model"}
 
 

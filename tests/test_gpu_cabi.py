@@ -29,7 +29,8 @@ def test_error_codes(engine):
     assert r["draws"].shape == (2, 0, 4)
 
 
-@pytest.mark.parametrize("tname,tid", [("iso_gauss", 0), ("diag_gauss", 1), ("dense_gauss", 2), ("linreg", 3), ("normal_model", 4)])
+@pytest.mark.parametrize("tname,tid", [("iso_gauss", 0), ("diag_gauss", 1), ("dense_gauss", 2), ("linreg", 3), ("normal_model", 4),
+                                       ("funnel", 5)])
 def test_device_functors_match_host_callbacks(engine, oracle, tname, tid):
     rng = np.random.default_rng(tid)
     d = 2 if tid == 4 else 37
@@ -47,7 +48,7 @@ def test_device_functors_match_host_callbacks(engine, oracle, tname, tid):
     val, grad = engine.api.target_eval(tname, td, x, arith=engine.api.ARITH_STRICT)
     for i in range(x.shape[0]):
         v, g = oracle.target(tid, td, x[i], sum_mode=ol.SUM_WARP)
-        if tid == 4:  # device log() vs glibc log(): last-bit differences allowed
+        if tid in (4, 5):  # device log() / exp() vs glibc: last-bit differences allowed
             assert abs(val[i] - v) <= 1e-12 * abs(v) and np.abs(grad[i] - g).max() <= 1e-12 * np.abs(g).max()
         else:
             assert val[i] == v and np.array_equal(grad[i], g)

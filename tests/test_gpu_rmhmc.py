@@ -78,3 +78,94 @@ def test_moments_track_reference_and_unsupported_target(engine, reference):
     with pytest.raises(engine.McmcB200Error) as ei:
         engine.rmhmc(np.zeros((2, 4)), "iso_gauss", n_burnin=1, n_keep=1)
     assert ei.value.code == engine.api.ERR_UNSUPPORTED
+
+
+# ---- the warp-per-chain kernel for general n_dim <= 64 (rmhmc_general.cu) and Neal's funnel (BASELINE config 5) -------
+
+def test_general_kernel_reproduces_thread_per_chain_kernel_and_goldens(engine, reference, monkeypatch):
+    """MCMCB200_RMHMC_GENERAL=1 routes the 2-parameter Normal model through the general kernel (LU inverse, Cholesky and
+    log-det on matrices in global scratch): it must give what the register kernel gives, and the reference's G4 golden."""
+    td = _data()
+    rng = np.random.default_rng(4)
+    x0 = np.array([3.0, 3.0]) + 0.2 * rng.normal(size=(24, 2))
+    kw = dict(target_data=td, n_leap_steps=2, step_size=0.15, n_burnin=5, n_keep=60, want_logp=True)
+    for mode, seed in ((engine.api.RNG_MT19937_TAPE, 77), (engine.api.RNG_PHILOX, 78)):
+        for arith in (engine.api.ARITH_STRICT, engine.api.ARITH_FAST):
+            a = engine.rmhmc(x0, "normal_model", rng_mode=mode, seed=seed, arith=arith, **kw)
+            monkeypatch.setenv("MCMCB200_RMHMC_GENERAL", "1")
+            b = engine.rmhmc(x0, "normal_model", rng_mode=mode, seed=seed, arith=arith, **kw)
+            monkeypatch.delenv("MCMCB200_RMHMC_GENERAL")
+            if arith == engine.api.ARITH_STRICT:
+                assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["logp"], b["logp"])
+            else:
+                assert np.abs(a["draws"] - b["draws"]).max() <= TOL
+            assert np.array_equal(a["n_accept"], b["n_accept"])
+    st = ol.Settings(n_burnin=0, n_keep=5, n_leap_steps=1, step_size=0.2)
+    ref, acc = reference.run_chain(ol.RMHMC, ol.TGT_NORMAL_MODEL, td, [3, 3], st, 1)
+    monkeypatch.setenv("MCMCB200_RMHMC_GENERAL", "1")
+    r = engine.rmhmc(np.array([[3.0, 3.0]]), "normal_model", target_data=td, n_leap_steps=1, step_size=0.2, n_burnin=0, n_keep=5,
+                     rng_mode=engine.api.RNG_MT19937_TAPE, seed=1, arith=engine.api.ARITH_STRICT)
+    assert np.abs(r["draws"][0] - ref).max() <= TOL and r["n_accept"][0] == acc
+
+
+def _funnel_start(C, d, rng):
+    x0 = rng.normal(size=(C, d)) * 0.6
+    x0[:, 0] = rng.uniform(-0.5, 0.8, size=C)
+    return x0
+
+
+@pytest.mark.parametrize("d,L,eps", [(2, 2, 0.1), (3, 3, 0.1), (5, 2, 0.15), (8, 3, 0.08), (17, 2, 0.1), (33, 2, 0.08), (64, 2, 0.06)])
+def test_funnel_rmhmc_vs_oracle_and_reference(engine, oracle, reference, d, L, eps):
+    """C5-shaped runs: Neal's funnel with its registered position-dependent metric, general n_dim up to 64.  STRICT on the
+    reference's stream and FAST on Philox against the oracle (SUM_WARP), and against the unmodified reference where its
+    O(d^4) momentum updates are affordable.  exp/log/sqrt are the CUDA library's, so the tolerance is 1e-10, not bits; as
+    for the Normal model a rounding-level difference may flip one accept decision and decorrelate one chain."""
+    rng = np.random.default_rng(d)
+    C = 6
+    x0 = _funnel_start(C, d, rng)
+    nk = 30 if d <= 17 else 12
+    st = ol.Settings(n_burnin=2, n_keep=nk, n_leap_steps=L, step_size=eps, n_fp_steps=4)
+    kw = dict(n_leap_steps=L, step_size=eps, n_fp_steps=4, n_burnin=2, n_keep=nk, want_logp=True)
+    r = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_MT19937_TAPE, seed=900, arith=engine.api.ARITH_STRICT, **kw)
+    bad = 0
+    for c in range(C):
+        o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=900 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP, want_logp=True)
+        ok = np.abs(r["draws"][c] - o["draws"]).max() <= TOL and r["n_accept"][c] == o["n_accept"] and np.abs(r["logp"][c] - o["logp"]).max() <= 1e-9
+        bad += 0 if ok else 1
+    assert bad <= 1
+    assert 0 < r["n_accept"].sum() < C * nk or d == 2
+    if d <= 8:
+        ref, acc, _ = reference.run_chains(ol.RMHMC, ol.TGT_FUNNEL, None, x0, st, 900)
+        linf = np.abs(r["draws"] - ref).max(axis=(1, 2))
+        assert (linf <= TOL).sum() >= C - 1 and (r["n_accept"] == acc).sum() >= C - 1
+    rf = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_PHILOX, seed=901, chain_offset=11, arith=engine.api.ARITH_FAST, **kw)
+    bad = 0
+    for c in range(C):
+        o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=901, rng_mode=ol.RNG_PHILOX, chain_id=11 + c, sum_mode=ol.SUM_WARP)
+        bad += 0 if (np.abs(rf["draws"][c] - o["draws"]).max() <= TOL and rf["n_accept"][c] == o["n_accept"]) else 1
+    assert bad <= 1
+
+
+def test_funnel_other_samplers_and_unsupported_combinations(engine, oracle):
+    """The funnel functor under HMC / MALA / RWMH / NUTS (Philox, FAST) against the oracle; RM-HMC refuses n_dim > 64."""
+    rng = np.random.default_rng(12)
+    for d in (2, 9, 64, 100):
+        C = 5
+        x0 = _funnel_start(C, d, rng)
+        for smp, call, st in (
+                (ol.HMC, lambda: engine.hmc(x0, "funnel", n_leap_steps=4, step_size=0.05, n_burnin=2, n_keep=20, rng_mode=engine.api.RNG_PHILOX, seed=5),
+                 ol.Settings(n_burnin=2, n_keep=20, n_leap_steps=4, step_size=0.05)),
+                (ol.MALA, lambda: engine.mala(x0, "funnel", step_size=0.05, n_burnin=2, n_keep=20, rng_mode=engine.api.RNG_PHILOX, seed=5),
+                 ol.Settings(n_burnin=2, n_keep=20, step_size=0.05)),
+                (ol.RWMH, lambda: engine.rwmh(x0, "funnel", par_scale=0.05, n_burnin=2, n_keep=20, rng_mode=engine.api.RNG_PHILOX, seed=5),
+                 ol.Settings(n_burnin=2, n_keep=20, step_size=0.05))):
+            r = call()
+            for c in range(C):
+                o = oracle.run_chain(smp, ol.TGT_FUNNEL, None, x0[c], st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=c, sum_mode=ol.SUM_WARP)
+                assert np.abs(r["draws"][c] - o["draws"]).max() <= TOL and r["n_accept"][c] == o["n_accept"], (smp, d, c)
+    with pytest.raises(engine.McmcB200Error) as ei:
+        engine.rmhmc(np.zeros((2, 65)), "funnel", n_burnin=1, n_keep=1)
+    assert ei.value.code == engine.api.ERR_UNSUPPORTED
+    with pytest.raises(engine.McmcB200Error) as ei:
+        engine.rmhmc(np.zeros((2, 8)), "funnel", n_burnin=1, n_keep=1, metric_id=7)
+    assert ei.value.code == engine.api.ERR_UNSUPPORTED
