@@ -69,7 +69,8 @@ typedef enum {
                                         carries the Fisher metric used by mcmcb200_rmhmc_run */
     MCMCB200_TARGET_FUNNEL = 5       /* Neal's funnel (BASELINE config 5): x[0] = v ~ N(0, 3^2), x[i] | v ~ N(0, e^v);
                                         n_dim >= 2, no data; metrics for mcmcb200_rmhmc_run (n_dim <= 64):
-                                        1 = "funnel_fisher" diag(1/9 + (n_dim-1)/2, e^-v, ..., e^-v) (default) */
+                                        1 = "funnel_fisher" diag(1/9 + (n_dim-1)/2, e^-v, ..., e^-v) (default),
+                                        2 = "funnel_softabs" SoftAbs of the Hessian, alpha = 1e6 (closed form) */
 } mcmcb200_target_t;
 
 typedef enum {

@@ -206,6 +206,7 @@ struct b200_settings_t {
     int arith = MCMCB200_ARITH_FAST;
     int chol_mode = b200_detail::default_chol;
     int device = -1;
+    int rmhmc_metric_id = 0;  // which of the kernel's registered metrics plays tensor_fn in mcmc::rmhmc (0 = its default)
     // many-chain calls: CUDA ordinals to shard the chains over (contiguous shards, one host thread per device, each
     // shard with its global chain offset, so the result does not depend on the list); empty = `device` alone
     std::vector<int> devices;
@@ -558,6 +559,7 @@ inline bool rmhmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_ker
                                 r.n_fp_steps = static_cast<int64_t>(static_cast<uint_t>(st.rmhmc_settings.n_fp_steps));
                                 r.chol_mode = st.b200.chol_mode;
                                 r.arith = st.b200.arith;
+                                r.metric_id = st.b200.rmhmc_metric_id;
                                 return mcmcb200_rmhmc_run(&pr, &rng, &r, &out);
                             });
 }

@@ -13,8 +13,8 @@
 // Linear algebra in the oracle's order (so STRICT arithmetic reproduces it bit for bit up to libm's log/exp/sqrt):
 // LU inverse with partial pivoting (first maximum wins), column Cholesky with the Eigen matrixLLT storage quirk
 // selectable (Q8), log-det from the Cholesky diagonal, products accumulated over the inner index in increasing order.
-// Work per momentum update is the reference's O(d^4) (d products of d x d matrices); a contraction form
-// (tr(A D_i), (Aq)' D_i (Aq): O(d^3)) is the next step for the FAST mode.
+// STRICT arithmetic performs the reference's O(d^4) momentum update literally (d products of d x d matrices); FAST
+// arithmetic contracts it to O(d^3): one d x d matrix per update, then one Frobenius product with each dG/dx_i.
 //
 // Scratch per chain (doubles): 9 d^2 (G_new, G_prev, G_w, inv_new, inv_prev, sumM, LU, Lchol, T) + 2 d^3 (dG_new,
 // dG_prev; the metric functors only write their fixed sparsity pattern into zero-initialised cubes).
@@ -60,6 +60,102 @@ struct FunnelFisherMetric {   // minus the expected Hessian of Neal's funnel ove
         if (dG)
             for (int i = lane; i < d; i += 32)
                 if (i > 0) dG[(size_t)i * d + i] = -ev;   // block 0 = dG/dv; everything else stays zero
+    }
+};
+
+// SoftAbs metric of Neal's funnel, alpha = 1e6 (BASELINE config 5): G = Q f(Lambda) Q' for the Hessian of log pi,
+// f(l) = l coth(alpha l).  The Hessian is an arrow matrix, so the spectrum is closed-form (no eigensolver): see
+// oracle/host_targets.hpp metric_funnel_softabs for the derivation; this functor repeats the same operations in the
+// same order with forward-mode dual numbers (value, d/dv, d/dS), S = sum_{i>=1} x_i^2.
+template <bool STRICT> struct Dual2Ops {
+    typedef Ar<STRICT> A;
+    struct D2 { double v, dv, ds; };
+    static __device__ __forceinline__ D2 mk(double v, double dv = 0.0, double ds = 0.0) { D2 r = {v, dv, ds}; return r; }
+    static __device__ __forceinline__ D2 add(D2 a, D2 b) { return mk(A::add(a.v, b.v), A::add(a.dv, b.dv), A::add(a.ds, b.ds)); }
+    static __device__ __forceinline__ D2 sub(D2 a, D2 b) { return mk(A::sub(a.v, b.v), A::sub(a.dv, b.dv), A::sub(a.ds, b.ds)); }
+    static __device__ __forceinline__ D2 mul(D2 a, D2 b)
+    {
+        return mk(A::mul(a.v, b.v), A::add(A::mul(a.dv, b.v), A::mul(a.v, b.dv)), A::add(A::mul(a.ds, b.v), A::mul(a.v, b.ds)));
+    }
+    static __device__ __forceinline__ D2 scale(D2 a, double c) { return mk(A::mul(a.v, c), A::mul(a.dv, c), A::mul(a.ds, c)); }
+    static __device__ __forceinline__ D2 div(D2 a, D2 b)
+    {
+        const double q = a.v / b.v;
+        return mk(q, A::sub(a.dv, A::mul(q, b.dv)) / b.v, A::sub(a.ds, A::mul(q, b.ds)) / b.v);
+    }
+    static __device__ __forceinline__ D2 sqrt_(D2 a)
+    {
+        const double r = sqrt(a.v);
+        return mk(r, a.dv / A::mul(2.0, r), a.ds / A::mul(2.0, r));
+    }
+    static __device__ __forceinline__ D2 softabs(D2 l, double alpha)
+    {
+        const double z = A::mul(alpha, l.v);
+        double f, fp;
+        if (fabs(z) < 1e-4) {
+            f = A::add(1.0 / alpha, A::mul(z, l.v) / 3.0);
+            fp = A::mul(2.0, z) / 3.0;
+        } else if (fabs(z) > 300.0) {
+            f = fabs(l.v);
+            fp = (l.v > 0.0) ? 1.0 : -1.0;
+        } else {
+            const double ct = 1.0 / tanh(z), sh = sinh(z);
+            f = A::mul(l.v, ct);
+            fp = A::sub(ct, z / A::mul(sh, sh));
+        }
+        return mk(f, A::mul(fp, l.dv), A::mul(fp, l.ds));
+    }
+};
+struct FunnelSoftabsMetric {
+    template <bool STRICT> static __device__ __forceinline__ void eval(const double* __restrict__, int d, int lane, const double* xs, double* G,
+                                                                        double* dG)
+    {
+        typedef Ar<STRICT> A;
+        typedef Dual2Ops<STRICT> O;
+        typedef typename O::D2 D2;
+        const double alpha = 1e6;
+        double S = 0.0;
+        for (int i = 1; i < d; ++i) S = A::add(S, A::mul(xs[i], xs[i]));
+        const double e = exp(-xs[0]);
+        const D2 ev = O::mk(e, -e, 0.0), Sd = O::mk(S, 0.0, 1.0);
+        const D2 h = O::sub(O::mk(-1.0 / 9.0), O::scale(O::mul(ev, Sd), 0.5));
+        const D2 a = O::mk(-ev.v, -ev.dv, 0.0);
+        const D2 beta2 = O::mul(O::mul(ev, ev), Sd);
+        const D2 delta = O::scale(O::sub(h, a), 0.5), mu = O::scale(O::add(h, a), 0.5);
+        const D2 r = O::sqrt_(O::add(O::mul(delta, delta), beta2));
+        const D2 f1 = O::softabs(O::add(mu, r), alpha), f2 = O::softabs(O::sub(mu, r), alpha), fa = O::softabs(a, alpha);
+        const D2 Sig = O::scale(O::add(f1, f2), 0.5);
+        const D2 Del = O::div(O::sub(f1, f2), O::scale(r, 2.0));
+        const D2 Dd = O::mul(Del, delta);
+        const D2 g11 = O::add(Sig, Dd), w = O::mul(Del, ev), P = O::div(O::sub(O::sub(Sig, Dd), fa), Sd);
+        for (int j = 0; j < d; ++j)
+            for (int i = lane; i < d; i += 32) {
+                double g;
+                if (i == 0 && j == 0) g = g11.v;
+                else if (i == 0 || j == 0) g = A::mul(w.v, xs[i + j]);
+                else g = A::add((i == j) ? fa.v : 0.0, A::mul(A::mul(P.v, xs[i]), xs[j]));
+                G[(size_t)j * d + i] = g;
+            }
+        if (!dG) return;
+        const size_t dd = (size_t)d * d;
+        for (int k = 0; k < d; ++k) {
+            const double s2 = A::mul(2.0, xs[k]);
+            for (int j = 0; j < d; ++j)
+                for (int i = lane; i < d; i += 32) {
+                    double g;
+                    if (k == 0) {
+                        if (i == 0 && j == 0) g = g11.dv;
+                        else if (i == 0 || j == 0) g = A::mul(w.dv, xs[i + j]);
+                        else g = A::add((i == j) ? fa.dv : 0.0, A::mul(A::mul(P.dv, xs[i]), xs[j]));
+                    } else {
+                        if (i == 0 && j == 0) g = A::mul(g11.ds, s2);
+                        else if (i == 0 || j == 0) g = A::add(A::mul(A::mul(w.ds, s2), xs[i + j]), (i + j == k) ? w.v : 0.0);
+                        else g = A::add(A::mul(A::mul(A::mul(P.ds, s2), xs[i]), xs[j]),
+                                        A::add((i == k) ? A::mul(P.v, xs[j]) : 0.0, (j == k) ? A::mul(P.v, xs[i]) : 0.0));
+                    }
+                    dG[(size_t)k * dd + (size_t)j * d + i] = g;
+                }
+        }
     }
 };
 
@@ -205,9 +301,11 @@ __global__ void __launch_bounds__(RG_WARPS * 32) rmhmc_general_kernel(const __gr
     if (chain >= a.n_chains) return;
     const int d = a.d;
     const int dp = (d + 1) & ~1;
-    double* vs = smem + (size_t)warp * 3 * dp;   // staged vector for products
+    double* vs = smem + (size_t)warp * 5 * dp;   // staged vector for products
     double* xs = vs + dp;                         // staged position for the functors
     double* tscr = xs + dp;                       // target functor scratch
+    double* us = tscr + dp;                       // FAST momentum update: u = A q
+    double* ups = us + dp;                        //                       u' = A' q
     const WarpCtx w{lane, d, tscr};
     int* piv = pivs[warp];
 
@@ -231,6 +329,38 @@ __global__ void __launch_bounds__(RG_WARPS * 32) rmhmc_general_kernel(const __gr
         T::template eval<RG_EPL, STRICT, false, true, true>(a.tdata, w, y, g);
         LA::stage(vs, d, lane, q);
         LA::gemv(Ainv, d, lane, vs, 1.0, Aq);
+        if constexpr (!STRICT) {
+            // FAST: tr(A D_i) - ((A D_i)' q).(A q) = sum_{a,b} D_i[b,a] (A[a,b] - u'_b u_a) with u = A q, u' = A' q: one d x d
+            // matrix Mt built once per update, then one Frobenius product per i — O(d^3) instead of the reference's O(d^4),
+            // and the cube is streamed exactly once, coalesced
+            double up[RG_EPL];
+            up[0] = 0.0; up[1] = 0.0;
+            for (int b = 0; b < d; ++b) {   // u'_a = sum_b A[b,a] q_b: column a of A is contiguous
+                const double qb = vs[b];
+                if (2 * lane < d) up[0] = fma(Ainv[(size_t)(2 * lane) * d + b], qb, up[0]);
+                if (2 * lane + 1 < d) up[1] = fma(Ainv[(size_t)(2 * lane + 1) * d + b], qb, up[1]);
+            }
+            LA::stage(us, d, lane, Aq);
+            LA::stage(ups, d, lane, up);
+            for (int aa = 0; aa < d; ++aa) {
+                const double ua = us[aa];
+                for (int b = lane; b < d; b += 32) Tm[(size_t)aa * d + b] = fma(-ups[b], ua, Ainv[(size_t)b * d + aa]);
+            }
+            __syncwarp();
+            for (int i = 0; i < d; ++i) {
+                const double* Di = dG + (size_t)i * dd2;
+                double s0 = 0.0, s1 = 0.0;
+                int k = lane;
+                for (; k + 32 < (int)dd2; k += 64) {
+                    s0 = fma(Di[k], Tm[k], s0);
+                    s1 = fma(Di[k + 32], Tm[k + 32], s1);
+                }
+                if (k < (int)dd2) s0 = fma(Di[k], Tm[k], s0);
+                const double sft = warp_sum<false>(s0 + s1);
+                if (lane == i / 2) g[i & 1] = fma(0.5, sft, -g[i & 1]);
+            }
+            __syncwarp();
+        } else {
         for (int i = 0; i < d; ++i) {
             const double* Di = dG + (size_t)i * dd2;
             // Tm = Ainv * D_i, one column at a time (inner index increasing)
@@ -254,6 +384,7 @@ __global__ void __launch_bounds__(RG_WARPS * 32) rmhmc_general_kernel(const __gr
             const double gi = A::mul(0.5, A::sub(tr, dpv));
             if (lane == i / 2) g[i & 1] = A::add(-g[i & 1], gi);
             __syncwarp();
+        }
         }
 #pragma unroll
         for (int k = 0; k < RG_EPL; ++k) out[k] = A::mul(A::mul(a.eps, g[k]), 0.5);
@@ -356,7 +487,7 @@ template <class T, class M> static int launch_tm(const RmhmcLaunch& a)
 {
     const long long blocks = (a.n_chains + RG_WARPS - 1) / RG_WARPS;
     const int dp = (a.d + 1) & ~1;
-    const size_t smem = (size_t)RG_WARPS * 3 * dp * sizeof(double);
+    const size_t smem = (size_t)RG_WARPS * 5 * dp * sizeof(double);
 #define RG_LAUNCH(S, R)                                                                        \
     do {                                                                                       \
         rmhmc_general_kernel<T, M, S, R><<<(unsigned)blocks, RG_WARPS * 32, smem, a.stream>>>(a); \
@@ -372,7 +503,7 @@ bool rmhmc_general_supported(int target_id, int metric_id, int d)
 {
     if (d < 1 || d > 32 * RG_EPL) return false;
     if (target_id == MCMCB200_TARGET_NORMAL_MODEL) return d == 2 && metric_id <= 0;
-    if (target_id == MCMCB200_TARGET_FUNNEL) return d >= 2 && (metric_id == 0 || metric_id == 1);
+    if (target_id == MCMCB200_TARGET_FUNNEL) return d >= 2 && metric_id >= 0 && metric_id <= 2;
     return false;
 }
 
@@ -383,7 +514,8 @@ int launch_rmhmc_general(const RmhmcLaunch& a)
         return MCMCB200_ERR_UNSUPPORTED;
     }
     if (a.target_id == MCMCB200_TARGET_NORMAL_MODEL) return launch_tm<NormalModel, NormalModelMetric>(a);
-    if (a.target_id == MCMCB200_TARGET_FUNNEL) return launch_tm<Funnel, FunnelFisherMetric>(a);
+    if (a.target_id == MCMCB200_TARGET_FUNNEL)
+        return a.metric_id == 2 ? launch_tm<Funnel, FunnelSoftabsMetric>(a) : launch_tm<Funnel, FunnelFisherMetric>(a);
     set_error("rmhmc: target %d has no registered metric", a.target_id);
     return MCMCB200_ERR_UNSUPPORTED;
 }

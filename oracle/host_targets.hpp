@@ -183,11 +183,119 @@ inline void metric_funnel_fisher(const double* x, int d, double* G, double* dG)
     }
 }
 
+// ---- SoftAbs metric for TGT_FUNNEL, id 2 ("funnel_softabs", BASELINE config 5) -------------------------------------
+// G = Q f(Lambda) Q' for the Hessian H = Q Lambda Q' of log pi, f(l) = l coth(alpha l), alpha = 1e6 (Betancourt 2013).
+// The funnel's Hessian is an arrow matrix — H_vv = h = -1/9 - e^-v S/2, H_vi = e^-v x_i, H_ij = a delta_ij, a = -e^-v,
+// S = sum x_i^2 — so its spectrum is closed-form: eigenvalue a on the complement of span{e_v, x/|x|} and the two
+// eigenvalues mu +- r of [[h, beta], [beta, a]] (beta = e^-v sqrt S, mu = (h+a)/2, delta = (h-a)/2, r = sqrt(delta^2 +
+// beta^2)).  With Sig = (f1+f2)/2 and Del = (f1-f2)/(2r):
+//   G_vv = Sig + Del delta,   G_vi = (Del e^-v) x_i,   G_ij = f(a) delta_ij + P x_i x_j,   P = (Sig - Del delta - f(a))/S.
+// The scalars are functions of (v, S); their partial derivatives come from forward-mode dual numbers (value, d/dv, d/dS),
+// and dG/dx_k follows from dS/dx_k = 2 x_k.  The device functor (mcmc_b200/csrc/rmhmc_general.cu) repeats the same
+// operations in the same order.
+struct Dual2 {
+    double v, dv, ds;
+};
+inline Dual2 d2(double v, double dv = 0.0, double ds = 0.0) { Dual2 r = {v, dv, ds}; return r; }
+inline Dual2 d2_add(Dual2 a, Dual2 b) { return d2(a.v + b.v, a.dv + b.dv, a.ds + b.ds); }
+inline Dual2 d2_sub(Dual2 a, Dual2 b) { return d2(a.v - b.v, a.dv - b.dv, a.ds - b.ds); }
+inline Dual2 d2_mul(Dual2 a, Dual2 b) { return d2(a.v * b.v, a.dv * b.v + a.v * b.dv, a.ds * b.v + a.v * b.ds); }
+inline Dual2 d2_scale(Dual2 a, double c) { return d2(a.v * c, a.dv * c, a.ds * c); }
+inline Dual2 d2_div(Dual2 a, Dual2 b)
+{
+    const double q = a.v / b.v;
+    return d2(q, (a.dv - q * b.dv) / b.v, (a.ds - q * b.ds) / b.v);
+}
+inline Dual2 d2_sqrt(Dual2 a)
+{
+    const double r = std::sqrt(a.v);
+    return d2(r, a.dv / (2.0 * r), a.ds / (2.0 * r));
+}
+// f(l) = l coth(alpha l) and f'(l) = coth(alpha l) - alpha l / sinh^2(alpha l); series near 0, saturated for |alpha l| > 300
+inline void softabs_f(double l, double alpha, double* f, double* fp)
+{
+    const double z = alpha * l;
+    if (std::fabs(z) < 1e-4) {
+        *f = 1.0 / alpha + (z * l) / 3.0;
+        *fp = (2.0 * z) / 3.0;
+    } else if (std::fabs(z) > 300.0) {
+        *f = std::fabs(l);
+        *fp = (l > 0.0) ? 1.0 : -1.0;
+    } else {
+        const double ct = 1.0 / std::tanh(z), sh = std::sinh(z);
+        *f = l * ct;
+        *fp = ct - z / (sh * sh);
+    }
+}
+inline Dual2 d2_softabs(Dual2 l, double alpha)
+{
+    double f, fp;
+    softabs_f(l.v, alpha, &f, &fp);
+    return d2(f, fp * l.dv, fp * l.ds);
+}
+struct FunnelSoftabsScalars {
+    Dual2 g11, w, fa, P;
+};
+inline FunnelSoftabsScalars funnel_softabs_scalars(double v, double S, double alpha)
+{
+    const double e = std::exp(-v);
+    const Dual2 ev = d2(e, -e, 0.0), Sd = d2(S, 0.0, 1.0);
+    const Dual2 h = d2_sub(d2(-1.0 / 9.0), d2_scale(d2_mul(ev, Sd), 0.5));
+    const Dual2 a = d2(-ev.v, -ev.dv, 0.0);
+    const Dual2 beta2 = d2_mul(d2_mul(ev, ev), Sd);
+    const Dual2 delta = d2_scale(d2_sub(h, a), 0.5), mu = d2_scale(d2_add(h, a), 0.5);
+    const Dual2 r = d2_sqrt(d2_add(d2_mul(delta, delta), beta2));
+    const Dual2 f1 = d2_softabs(d2_add(mu, r), alpha), f2 = d2_softabs(d2_sub(mu, r), alpha), fa = d2_softabs(a, alpha);
+    const Dual2 Sig = d2_scale(d2_add(f1, f2), 0.5);
+    const Dual2 Del = d2_div(d2_sub(f1, f2), d2_scale(r, 2.0));
+    const Dual2 Dd = d2_mul(Del, delta);
+    FunnelSoftabsScalars o;
+    o.g11 = d2_add(Sig, Dd);
+    o.w = d2_mul(Del, ev);
+    o.fa = fa;
+    o.P = d2_div(d2_sub(d2_sub(Sig, Dd), fa), Sd);
+    return o;
+}
+inline void metric_funnel_softabs(const double* x, int d, double* G, double* dG)
+{
+    const double alpha = 1e6;
+    double S = 0.0;
+    for (int i = 1; i < d; ++i) S = S + x[i] * x[i];
+    const FunnelSoftabsScalars c = funnel_softabs_scalars(x[0], S, alpha);
+    const size_t dd = size_t(d) * d;
+    for (int j = 0; j < d; ++j)
+        for (int i = 0; i < d; ++i) {
+            double g;
+            if (i == 0 && j == 0) g = c.g11.v;
+            else if (i == 0 || j == 0) g = c.w.v * x[i + j];
+            else g = ((i == j) ? c.fa.v : 0.0) + (c.P.v * x[i]) * x[j];
+            G[size_t(j) * d + i] = g;
+        }
+    if (!dG) return;
+    for (int k = 0; k < d; ++k)
+        for (int j = 0; j < d; ++j)
+            for (int i = 0; i < d; ++i) {
+                double g;
+                if (k == 0) {   // d/dv
+                    if (i == 0 && j == 0) g = c.g11.dv;
+                    else if (i == 0 || j == 0) g = c.w.dv * x[i + j];
+                    else g = ((i == j) ? c.fa.dv : 0.0) + (c.P.dv * x[i]) * x[j];
+                } else {        // d/dx_k = (d/dS) 2 x_k + explicit dependence on x_k
+                    const double s2 = 2.0 * x[k];
+                    if (i == 0 && j == 0) g = c.g11.ds * s2;
+                    else if (i == 0 || j == 0) g = (c.w.ds * s2) * x[i + j] + ((i + j == k) ? c.w.v : 0.0);
+                    else g = ((c.P.ds * s2) * x[i]) * x[j] + (((i == k) ? c.P.v * x[j] : 0.0) + ((j == k) ? c.P.v * x[i] : 0.0));
+                }
+                dG[size_t(k) * dd + size_t(j) * d + i] = g;
+            }
+}
+
 // metric registered with a target (metric_id 0 = the target's default)
 inline bool metric(int target_id, int metric_id, const double* data, const double* x, int d, double* G, double* dG)
 {
     if (target_id == TGT_NORMAL_MODEL && d == 2) { metric_normal_model(data, x, G, dG); return true; }
     if (target_id == TGT_FUNNEL && (metric_id == 0 || metric_id == 1)) { metric_funnel_fisher(x, d, G, dG); return true; }
+    if (target_id == TGT_FUNNEL && metric_id == 2) { metric_funnel_softabs(x, d, G, dG); return true; }
     return false;
 }
 

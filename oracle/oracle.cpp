@@ -989,6 +989,12 @@ double oracle_target(int target_id, const double* tdata, int d, const double* x,
     return otgt::value_and_grad(target_id, tdata, x, grad, d, sum_mode);
 }
 
+// a target's registered metric and its derivative cube (tests check the closed forms against finite differences)
+int oracle_metric(int target_id, int metric_id, const double* tdata, int d, const double* x, double* G, double* dG)
+{
+    return otgt::metric(target_id, metric_id, tdata, x, d, G, dG) ? 0 : -1;
+}
+
 // raw RNG streams, for checking the engine's host-side tape generator and device Philox
 void oracle_rng_stream(int rng_mode, unsigned long seed, long chain_id, long draw, int d, int n_unif, double* out)
 {

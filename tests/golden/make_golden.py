@@ -86,6 +86,17 @@ def cases():
         dict(name="rwmh_box_d4", sampler=ol.RWMH, target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 0.5, 2.0, 1.5], x0=[0.3, 0.7, 0.4, 0.2], seed=35,
              st=dict(n_burnin=5, n_keep=50, step_size=0.6), lower=lo4, upper=hi4),
     ]
+    # Neal's funnel (BASELINE config 5's density) under RM-HMC with its two registered metrics (st.metric_id: 1 = Fisher-type
+    # diagonal, 2 = closed-form SoftAbs, alpha = 1e6) and under HMC; appended last like the rwmh cases
+    xf = [0.3] + (0.7 * rng.normal(size=5)).tolist()
+    out += [
+        dict(name="rmhmc_funnel_fisher_d6", sampler=ol.RMHMC, target=ol.TGT_FUNNEL, tdata=None, x0=xf, seed=51,
+             st=dict(n_burnin=3, n_keep=40, n_leap_steps=3, step_size=0.1, n_fp_steps=4, metric_id=1)),
+        dict(name="rmhmc_funnel_softabs_d6", sampler=ol.RMHMC, target=ol.TGT_FUNNEL, tdata=None, x0=xf, seed=52,
+             st=dict(n_burnin=3, n_keep=40, n_leap_steps=3, step_size=0.08, n_fp_steps=5, metric_id=2)),
+        dict(name="hmc_funnel_d6", sampler=ol.HMC, target=ol.TGT_FUNNEL, tdata=None, x0=xf, seed=53,
+             st=dict(n_burnin=3, n_keep=40, n_leap_steps=5, step_size=0.1)),
+    ]
     return out
 
 

@@ -201,6 +201,16 @@ class Oracle:
         v = self.lib.oracle_target(target_id, _ptr(tdata), x.size, _ptr(x), _ptr(g), sum_mode)
         return v, g
 
+    def metric(self, target_id, metric_id, tdata, x, want_deriv=True):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        d = x.size
+        tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
+        G = np.zeros((d, d))
+        dG = np.zeros((d, d, d)) if want_deriv else None
+        rc = self.lib.oracle_metric(target_id, metric_id, _ptr(tdata), d, _ptr(x), _ptr(G), _ptr(dG))
+        assert rc == 0, rc
+        return G.T.copy(), (None if dG is None else dG.transpose(0, 2, 1).copy())   # column-major -> [i][j]
+
     def rng_stream(self, rng_mode, seed, chain_id, draw, d, n_unif):
         out = np.zeros(d + n_unif)
         self.lib.oracle_rng_stream(rng_mode, ctypes.c_ulong(seed), ctypes.c_long(chain_id), ctypes.c_long(draw), d,

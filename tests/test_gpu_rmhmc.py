@@ -108,41 +108,51 @@ def test_general_kernel_reproduces_thread_per_chain_kernel_and_goldens(engine, r
     assert np.abs(r["draws"][0] - ref).max() <= TOL and r["n_accept"][0] == acc
 
 
+def _close(a, b, tol=TOL):
+    """L-inf agreement where both are finite, identical NaN pattern elsewhere: the reference ACCEPTS a proposal whose energy
+    is NaN (std::min(0.01, NaN) = 0.01, src/rmhmc.cpp:250), so an unstable chain turns NaN — in the reference, the oracle and
+    the kernel at the same draw."""
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.allclose(a, b, rtol=0, atol=tol, equal_nan=True)
+
+
 def _funnel_start(C, d, rng):
     x0 = rng.normal(size=(C, d)) * 0.6
     x0[:, 0] = rng.uniform(-0.5, 0.8, size=C)
     return x0
 
 
+@pytest.mark.parametrize("metric_id", [1, 2])
 @pytest.mark.parametrize("d,L,eps", [(2, 2, 0.1), (3, 3, 0.1), (5, 2, 0.15), (8, 3, 0.08), (17, 2, 0.1), (33, 2, 0.08), (64, 2, 0.06)])
-def test_funnel_rmhmc_vs_oracle_and_reference(engine, oracle, reference, d, L, eps):
+def test_funnel_rmhmc_vs_oracle_and_reference(engine, oracle, reference, d, L, eps, metric_id):
     """C5-shaped runs: Neal's funnel with its registered position-dependent metric, general n_dim up to 64.  STRICT on the
     reference's stream and FAST on Philox against the oracle (SUM_WARP), and against the unmodified reference where its
     O(d^4) momentum updates are affordable.  exp/log/sqrt are the CUDA library's, so the tolerance is 1e-10, not bits; as
-    for the Normal model a rounding-level difference may flip one accept decision and decorrelate one chain."""
+    for the Normal model a rounding-level difference may flip one accept decision and decorrelate one chain.
+    metric_id 1 = the Fisher-type diagonal metric, 2 = the closed-form SoftAbs metric (alpha = 1e6) of BASELINE config 5."""
     rng = np.random.default_rng(d)
     C = 6
+    if metric_id == 2 and d >= 17:
+        eps = 0.02   # the reference's RM-HMC (Q16/Q17) with SoftAbs needs small steps at this size to accept anything
     x0 = _funnel_start(C, d, rng)
     nk = 30 if d <= 17 else 12
-    st = ol.Settings(n_burnin=2, n_keep=nk, n_leap_steps=L, step_size=eps, n_fp_steps=4)
-    kw = dict(n_leap_steps=L, step_size=eps, n_fp_steps=4, n_burnin=2, n_keep=nk, want_logp=True)
+    st = ol.Settings(n_burnin=2, n_keep=nk, n_leap_steps=L, step_size=eps, n_fp_steps=4, metric_id=metric_id)
+    kw = dict(n_leap_steps=L, step_size=eps, n_fp_steps=4, n_burnin=2, n_keep=nk, want_logp=True, metric_id=metric_id)
     r = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_MT19937_TAPE, seed=900, arith=engine.api.ARITH_STRICT, **kw)
     bad = 0
     for c in range(C):
         o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=900 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP, want_logp=True)
-        ok = np.abs(r["draws"][c] - o["draws"]).max() <= TOL and r["n_accept"][c] == o["n_accept"] and np.abs(r["logp"][c] - o["logp"]).max() <= 1e-9
+        ok = _close(r["draws"][c], o["draws"]) and r["n_accept"][c] == o["n_accept"] and _close(r["logp"][c], o["logp"], 1e-9)
         bad += 0 if ok else 1
     assert bad <= 1
-    assert 0 < r["n_accept"].sum() < C * nk or d == 2
+    assert 0 < r["n_accept"].sum()
     if d <= 8:
         ref, acc, _ = reference.run_chains(ol.RMHMC, ol.TGT_FUNNEL, None, x0, st, 900)
-        linf = np.abs(r["draws"] - ref).max(axis=(1, 2))
-        assert (linf <= TOL).sum() >= C - 1 and (r["n_accept"] == acc).sum() >= C - 1
+        assert sum(_close(r["draws"][c], ref[c]) for c in range(C)) >= C - 1 and (r["n_accept"] == acc).sum() >= C - 1
     rf = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_PHILOX, seed=901, chain_offset=11, arith=engine.api.ARITH_FAST, **kw)
     bad = 0
     for c in range(C):
         o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=901, rng_mode=ol.RNG_PHILOX, chain_id=11 + c, sum_mode=ol.SUM_WARP)
-        bad += 0 if (np.abs(rf["draws"][c] - o["draws"]).max() <= TOL and rf["n_accept"][c] == o["n_accept"]) else 1
+        bad += 0 if (_close(rf["draws"][c], o["draws"]) and rf["n_accept"][c] == o["n_accept"]) else 1
     assert bad <= 1
 
 
@@ -169,3 +179,25 @@ def test_funnel_other_samplers_and_unsupported_combinations(engine, oracle):
     with pytest.raises(engine.McmcB200Error) as ei:
         engine.rmhmc(np.zeros((2, 8)), "funnel", n_burnin=1, n_keep=1, metric_id=7)
     assert ei.value.code == engine.api.ERR_UNSUPPORTED
+
+
+def test_funnel_goldens(engine):
+    """Committed fixtures from the unmodified reference: rmhmc_funnel_{fisher,softabs}_d6 and hmc_funnel_d6."""
+    import golden_util
+
+    seen = 0
+    for c in golden_util.load()["cases"]:
+        if c["target"] != ol.TGT_FUNNEL:
+            continue
+        st = c["settings"]
+        x0 = np.array([c["x0"]], dtype=np.float64)
+        common = dict(n_burnin=st["n_burnin"], n_keep=st["n_keep"], rng_mode=engine.api.RNG_MT19937_TAPE, seed=c["seed"], arith=engine.api.ARITH_STRICT)
+        if c["sampler"] == ol.RMHMC:
+            r = engine.rmhmc(x0, "funnel", n_leap_steps=st["n_leap_steps"], step_size=st["step_size"], n_fp_steps=st["n_fp_steps"],
+                             metric_id=st["metric_id"], **common)
+        else:
+            r = engine.hmc(x0, "funnel", n_leap_steps=st["n_leap_steps"], step_size=st["step_size"], **common)
+        assert np.abs(r["draws"][0] - c["draws"]).max() <= TOL, c["name"]
+        assert r["n_accept"][0] == c["n_accept"], c["name"]
+        seen += 1
+    assert seen == 3

@@ -30,7 +30,7 @@ def test_golden_rng_stream(oracle, golden):
 
 
 def test_oracle_reproduces_every_golden_case(oracle, golden):
-    assert len(golden["cases"]) >= 20
+    assert len(golden["cases"]) >= 23
     for c in golden["cases"]:
         o = oracle.run_chain(c["sampler"], c["target"], c["tdata"], c["x0"], c["settings"], seed=c["seed"], rng_mode=ol.RNG_MT,
                              sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1)
@@ -81,6 +81,15 @@ def _rand_cases():
         ("rwmh dense cov", ol.RWMH, ol.TGT_DENSE_GAUSS, P.ravel(), rng.normal(size=7), ol.Settings(n_burnin=5, n_keep=80, step_size=0.5, precond=M), 18),
         ("rwmh linreg", ol.RWMH, ol.TGT_LINREG, np.concatenate([A.ravel(), b]), rng.normal(size=7), ol.Settings(n_burnin=0, n_keep=80, step_size=0.3), 19),
         ("rwmh normal model", ol.RWMH, ol.TGT_NORMAL_MODEL, nm, [3, 3], ol.Settings(n_burnin=10, n_keep=100, step_size=0.1), 20),
+        # Neal's funnel (BASELINE config 5) with its registered metrics: general-d RM-HMC (d^3 derivative cube, LU inverse, ...)
+        ("rmhmc funnel fisher d=9", ol.RMHMC, ol.TGT_FUNNEL, None, np.concatenate([[0.2], 0.6 * rng.normal(size=8)]),
+         ol.Settings(n_burnin=3, n_keep=30, n_leap_steps=3, step_size=0.08, n_fp_steps=4, metric_id=1), 21),
+        ("rmhmc funnel softabs d=7", ol.RMHMC, ol.TGT_FUNNEL, None, np.concatenate([[-0.1], 0.6 * rng.normal(size=6)]),
+         ol.Settings(n_burnin=3, n_keep=30, n_leap_steps=2, step_size=0.1, n_fp_steps=5, metric_id=2), 22),
+        ("nuts funnel d=5", ol.NUTS, ol.TGT_FUNNEL, None, np.concatenate([[0.2], 0.6 * rng.normal(size=4)]),
+         ol.Settings(n_burnin=20, n_keep=20, n_adapt_draws=20), 23),
+        ("mala funnel d=12", ol.MALA, ol.TGT_FUNNEL, None, np.concatenate([[0.2], 0.6 * rng.normal(size=11)]),
+         ol.Settings(n_burnin=3, n_keep=40, step_size=0.1), 24),
     ]
 
 
@@ -198,3 +207,34 @@ def test_philox_stream_is_sharding_invariant(oracle):
     assert not np.array_equal(a["draws"], b["draws"])
     c = oracle.run_chain(ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=77)
     assert np.array_equal(a["draws"], c["draws"])
+
+
+def test_funnel_softabs_metric_closed_form(oracle):
+    """The closed-form SoftAbs metric of Neal's funnel (alpha = 1e6: G = |H| up to 1e-6) against a numerical
+    eigendecomposition of the Hessian, and its derivative cube against central differences."""
+    rng = np.random.default_rng(1)
+    for d in (2, 3, 6, 9, 17):
+        x = rng.normal(size=d) * 0.8
+        x[0] = rng.uniform(-1.0, 1.0)
+        G, dG = oracle.metric(ol.TGT_FUNNEL, 2, None, x)
+        v, xs = x[0], x[1:]
+        e, S = np.exp(-v), (xs ** 2).sum()
+        H = np.zeros((d, d))
+        H[0, 0] = -1 / 9 - 0.5 * e * S
+        H[0, 1:] = H[1:, 0] = e * xs
+        H[1:, 1:] = -e * np.eye(d - 1)
+        lam, Q = np.linalg.eigh(H)
+        assert np.abs(G - (Q * np.abs(lam)) @ Q.T).max() <= 1e-13
+        assert np.abs(G - G.T).max() <= 1e-15 and np.linalg.eigvalsh(G).min() > 0
+        for k in range(d):
+            h = 1e-6
+            xp, xm = x.copy(), x.copy()
+            xp[k] += h
+            xm[k] -= h
+            Gp, _ = oracle.metric(ol.TGT_FUNNEL, 2, None, xp, False)
+            Gm, _ = oracle.metric(ol.TGT_FUNNEL, 2, None, xm, False)
+            assert np.abs((Gp - Gm) / (2 * h) - dG[k]).max() <= 2e-8 * max(1.0, np.abs(dG[k]).max())
+        # the Fisher-type metric: diagonal, derivative only with respect to v
+        G1, dG1 = oracle.metric(ol.TGT_FUNNEL, 1, None, x)
+        assert np.allclose(np.diag(G1), [1 / 9 + (d - 1) / 2] + [e] * (d - 1)) and np.abs(G1 - np.diag(np.diag(G1))).max() == 0
+        assert np.abs(dG1[1:]).max() == 0 and np.allclose(np.diag(dG1[0]), [0] + [-e] * (d - 1))

@@ -28,3 +28,17 @@ if "sweep" in which:
         ms = r["kernel_ms"]
         print("HMC iso d=%d: 4096 chains x 300 draws: kernel %.2f ms, %.3e draws/s, %.1f GB/s algorithmic (2*d*8 B/draw), acc %.3f"
               % (d, ms, C * 300 / ms * 1e3, C * 300 * 2 * d * 8 / ms * 1e-6, r["n_accept"].mean() / 200))
+if "c5" in which:
+    # BASELINE config 5: RM-HMC, Neal's funnel d = 64, 2048 chains, SoftAbs metric (alpha = 1e6, closed form), n_fp = 5, L = 5;
+    # eps = 0.01: the reference's RM-HMC (Q16/Q17 semantics) accepts ~70 % there, nothing at 0.1
+    rng = np.random.default_rng(5)
+    d, C = 64, 2048
+    x0 = rng.normal(size=(C, d)) * 0.6
+    x0[:, 0] = rng.uniform(-0.5, 0.8, size=C)
+    for metric, name in ((2, "funnel_softabs"), (1, "funnel_fisher")):
+        for nb, nk in ((1, 2), (5, 15)):
+            t0 = time.time()
+            r = mcmc_b200.rmhmc(x0, "funnel", n_leap_steps=5, step_size=0.01, n_fp_steps=5, n_burnin=nb, n_keep=nk, rng_mode=api.RNG_PHILOX, seed=5,
+                                metric_id=metric)
+            print("C5 RM-HMC funnel d=64 (%s): %d chains x %d draws, L=5, n_fp=5: kernel %.1f ms (%.1f ms/draw), acc %.2f, finite %.3f, wall %.1fs"
+                  % (name, C, nb + nk, r["kernel_ms"], r["kernel_ms"] / (nb + nk), r["n_accept"].mean() / nk, np.isfinite(r["draws"]).all(axis=(1, 2)).mean(), time.time() - t0))
