@@ -11,8 +11,8 @@
 // thread's registers, so chains map to threads (32 chains per warp) instead of warps.
 //
 // Registered metric: the Fisher information of the 2-parameter Normal(mu, sigma) model of
-// examples/eigen/rmhmc_normal.cpp:82-111 (target MCMCB200_TARGET_NORMAL_MODEL).  The SoftAbs metric for the
-// funnel (BASELINE config 5) is not built yet ("what comes next").
+// examples/eigen/rmhmc_normal.cpp:82-111 (target MCMCB200_TARGET_NORMAL_MODEL).  Larger metrics — Neal's funnel with
+// its Fisher-type or SoftAbs metric up to n_dim = 64 (BASELINE config 5) — run warp-per-chain in rmhmc_general.cu.
 #include "engine.h"
 #include "rng.cuh"
 #include "box.cuh"
