@@ -349,13 +349,19 @@ __global__ void __launch_bounds__(RG_WARPS * 32) rmhmc_general_kernel(const __gr
             __syncwarp();
             for (int i = 0; i < d; ++i) {
                 const double* Di = dG + (size_t)i * dd2;
-                double s0 = 0.0, s1 = 0.0;
+                // eight independent loads in flight per lane and array: the cube is streamed from L2/HBM and a dependent
+                // two-term loop left the warp waiting one memory latency per 64 elements
+                double acc[4] = {0.0, 0.0, 0.0, 0.0};
                 int k = lane;
-                for (; k + 32 < (int)dd2; k += 64) {
-                    s0 = fma(Di[k], Tm[k], s0);
-                    s1 = fma(Di[k + 32], Tm[k + 32], s1);
+                for (; k + 7 * 32 < (int)dd2; k += 8 * 32) {
+                    double dv[8], tv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { dv[u] = Di[k + 32 * u]; tv[u] = Tm[k + 32 * u]; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[u & 3] = fma(dv[u], tv[u], acc[u & 3]);
                 }
-                if (k < (int)dd2) s0 = fma(Di[k], Tm[k], s0);
+                for (; k < (int)dd2; k += 32) acc[0] = fma(Di[k], Tm[k], acc[0]);
+                const double s0 = acc[0] + acc[1], s1 = acc[2] + acc[3];
                 const double sft = warp_sum<false>(s0 + s1);
                 if (lane == i / 2) g[i & 1] = fma(0.5, sft, -g[i & 1]);
             }

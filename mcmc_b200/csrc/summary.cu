@@ -4,7 +4,7 @@
 //   (each lane a 16-byte vector per row, 512 contiguous bytes per warp instruction, 8 rows in flight) and accumulates
 //   sum (x - s) and sum (x - s)^2 with s = the chain's first kept draw, so large means do not cancel.  HBM-bound: the
 //   draws are read exactly once (8 B per element), everything else is O(n_chains * n_dim).
-// combine_kernel: one thread per element j over the per-chain statistics: pooled mean, pooled variance, R-hat.
+// combine_kernel: per tile of 32 elements, 32 x 32 threads over (element, chain slice): pooled mean, pooled variance, R-hat.
 #include <vector>
 
 #include "engine.h"
@@ -74,30 +74,41 @@ __global__ void __launch_bounds__(SUM_WARPS * 32) chain_stats_kernel(const doubl
     }
 }
 
-__global__ void combine_kernel(const double* __restrict__ cmean, const double* __restrict__ cvar, long long n_chains, long long n_keep, int d,
-                               double* __restrict__ mean, double* __restrict__ var, double* __restrict__ rhat)
+// one block per tile of 32 elements, 32 x 32 threads: thread (tx, ty) reduces chains ty, ty + 32, ... of element j = tile*32 + tx
+// (coalesced across tx), then the 32 partials per element are combined in shared memory.  Sums of the chain means are shifted
+// by chain 0's mean so that the between-chain variance does not cancel.
+__global__ void __launch_bounds__(1024) combine_kernel(const double* __restrict__ cmean, const double* __restrict__ cvar, long long n_chains,
+                                                       long long n_keep, int d, double* __restrict__ mean, double* __restrict__ var,
+                                                       double* __restrict__ rhat)
 {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d) return;
-    const double C = (double)n_chains, n = (double)n_keep;
-    const double nan = __longlong_as_double(0x7ff8000000000000ll);
-    double sm = 0.0, sw = 0.0;
-    for (long long c = 0; c < n_chains; ++c) {   // consecutive threads read consecutive j: coalesced
-        sm += cmean[(size_t)c * d + j];
-        sw += cvar[(size_t)c * d + j];
+    __shared__ double s1[32][33], s2[32][33], sw[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int j = blockIdx.x * 32 + tx;
+    double a1 = 0.0, a2 = 0.0, aw = 0.0;
+    const double shift = (j < d) ? cmean[j] : 0.0;
+    if (j < d)
+        for (long long c = ty; c < n_chains; c += 32) {
+            const double e = cmean[(size_t)c * d + j] - shift;
+            a1 += e;
+            a2 = fma(e, e, a2);
+            aw += cvar[(size_t)c * d + j];
+        }
+    s1[ty][tx] = a1; s2[ty][tx] = a2; sw[ty][tx] = aw;
+    __syncthreads();
+    if (ty == 0 && j < d) {
+        double t1 = 0.0, t2 = 0.0, tw = 0.0;
+        for (int r = 0; r < 32; ++r) { t1 += s1[r][tx]; t2 += s2[r][tx]; tw += sw[r][tx]; }
+        const double C = (double)n_chains, n = (double)n_keep;
+        const double nan = __longlong_as_double(0x7ff8000000000000ll);
+        const double m = shift + t1 / C;
+        const double sb = fmax(0.0, t2 - t1 * (t1 / C));          // sum_c (m_c - m)^2
+        mean[j] = m;
+        const double W = tw / C;                                   // mean within-chain variance
+        const double Bn = n_chains > 1 ? sb / (C - 1.0) : nan;     // B/n: variance of the chain means
+        // pooled sample variance of all C*n draws: [(n-1) sum_c s_c^2 + n sum_c (m_c - m)^2] / (C n - 1)
+        var[j] = (n_keep > 1 || n_chains > 1) ? ((n_keep > 1 ? (n - 1.0) * tw : 0.0) + n * sb) / (C * n - 1.0) : nan;
+        rhat[j] = (n_chains > 1 && n_keep > 1) ? sqrt(((n - 1.0) / n * W + Bn) / W) : nan;
     }
-    const double m = sm / C;
-    double sb = 0.0;
-    for (long long c = 0; c < n_chains; ++c) {
-        const double e = cmean[(size_t)c * d + j] - m;
-        sb = fma(e, e, sb);
-    }
-    mean[j] = m;
-    const double W = sw / C;                                  // mean within-chain variance
-    const double Bn = n_chains > 1 ? sb / (C - 1.0) : nan;    // B/n: variance of the chain means
-    // pooled sample variance of all C*n draws: [(n-1) sum_c s_c^2 + n sum_c (m_c - m)^2] / (C n - 1)
-    var[j] = (n_keep > 1 || n_chains > 1) ? ((n_keep > 1 ? (n - 1.0) * sw : 0.0) + n * sb) / (C * n - 1.0) : nan;
-    rhat[j] = (n_chains > 1 && n_keep > 1) ? sqrt(((n - 1.0) / n * W + Bn) / W) : nan;
 }
 
 }  // namespace mcmcb200
@@ -170,7 +181,7 @@ extern "C" int mcmcb200_summarize_draws(const double* draws, int32_t draws_mem, 
     MCMCB200_CUDA_TRY(cudaEventRecord(e0, st));
     chain_stats_kernel<<<(unsigned)blocks, SUM_WARPS * 32, 0, st>>>(d_draws, n_chains, n_keep, n_dim, bpr, cmean, cvar);
     MCMCB200_CUDA_TRY(cudaGetLastError());
-    combine_kernel<<<(n_dim + 127) / 128, 128, 0, st>>>(cmean, cvar, n_chains, n_keep, n_dim, r, r + n_dim, r + 2 * n_dim);
+    combine_kernel<<<(n_dim + 31) / 32, dim3(32, 32), 0, st>>>(cmean, cvar, n_chains, n_keep, n_dim, r, r + n_dim, r + 2 * n_dim);
     MCMCB200_CUDA_TRY(cudaGetLastError());
     MCMCB200_CUDA_TRY(cudaEventRecord(e1, st));
     MCMCB200_CUDA_TRY(cudaMemcpyAsync(out->mean, r, (size_t)n_dim * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -168,7 +168,10 @@ def test_funnel_other_samplers_and_unsupported_combinations(engine, oracle):
                 (ol.MALA, lambda: engine.mala(x0, "funnel", step_size=0.05, n_burnin=2, n_keep=20, rng_mode=engine.api.RNG_PHILOX, seed=5),
                  ol.Settings(n_burnin=2, n_keep=20, step_size=0.05)),
                 (ol.RWMH, lambda: engine.rwmh(x0, "funnel", par_scale=0.05, n_burnin=2, n_keep=20, rng_mode=engine.api.RNG_PHILOX, seed=5),
-                 ol.Settings(n_burnin=2, n_keep=20, step_size=0.05))):
+                 ol.Settings(n_burnin=2, n_keep=20, step_size=0.05)),
+                (ol.NUTS, lambda: engine.nuts(x0, "funnel", step_size=0.05, n_adapt_draws=0, max_tree_depth=6, n_burnin=2, n_keep=8,
+                                              rng_mode=engine.api.RNG_PHILOX, seed=5),
+                 ol.Settings(n_burnin=2, n_keep=8, step_size=0.05, n_adapt_draws=0, max_tree_depth=6))):
             r = call()
             for c in range(C):
                 o = oracle.run_chain(smp, ol.TGT_FUNNEL, None, x0[c], st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=c, sum_mode=ol.SUM_WARP)
