@@ -222,12 +222,72 @@ template <bool STRICT> struct RG {
             for (int i = 2 * lane; i < 2 * lane + 2; ++i)
                 if (i > k && i < d) lu[(size_t)k * d + i] = lu[(size_t)k * d + i] / dd;
             __syncwarp();
-            for (int j = k + 1; j < d; ++j) {
-                const double t = lu[(size_t)j * d + k];
-                for (int i = 2 * lane; i < 2 * lane + 2; ++i)
-                    if (i > k && i < d) lu[(size_t)j * d + i] = A::sub(lu[(size_t)j * d + i], A::mul(lu[(size_t)k * d + i], t));
+            // trailing update, four columns in flight per lane (row k of those columns is not modified in this step, and
+            // every element receives exactly one update, so the grouping does not change any result)
+            for (int j = k + 1; j < d; j += 4) {
+                double t[4], v[4][2];
+                const double lk0 = (2 * lane > k && 2 * lane < d) ? lu[(size_t)k * d + 2 * lane] : 0.0;
+                const double lk1 = (2 * lane + 1 > k && 2 * lane + 1 < d) ? lu[(size_t)k * d + 2 * lane + 1] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int jj = (j + u < d) ? j + u : d - 1;
+                    t[u] = lu[(size_t)jj * d + k];
+                    v[u][0] = (2 * lane < d) ? lu[(size_t)jj * d + 2 * lane] : 0.0;
+                    v[u][1] = (2 * lane + 1 < d) ? lu[(size_t)jj * d + 2 * lane + 1] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (j + u < d) {
+                        if (2 * lane > k && 2 * lane < d) lu[(size_t)(j + u) * d + 2 * lane] = A::sub(v[u][0], A::mul(lk0, t[u]));
+                        if (2 * lane + 1 > k && 2 * lane + 1 < d) lu[(size_t)(j + u) * d + 2 * lane + 1] = A::sub(v[u][1], A::mul(lk1, t[u]));
+                    }
             }
             __syncwarp();
+        }
+        if constexpr (!STRICT) {
+            // FAST: lanes over ROWS, four right-hand sides at a time in registers, column-oriented (axpy) substitution.  The
+            // forward sweep applies the same operations in the same order as the oracle; the backward sweep applies the terms
+            // of a row in decreasing instead of increasing column order (rounding-level difference, FAST mode only).
+            const int i0 = 2 * lane, i1 = 2 * lane + 1;
+            for (int c0 = 0; c0 < d; c0 += 4) {
+                double y[4][2];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    y[cc][0] = (i0 < d && piv[i0] == c0 + cc) ? 1.0 : 0.0;
+                    y[cc][1] = (i1 < d && piv[i1] == c0 + cc) ? 1.0 : 0.0;
+                }
+                for (int j = 0; j < d; ++j) {   // L y = P e_c, unit lower triangle
+                    const double l0 = (i0 > j && i0 < d) ? lu[(size_t)j * d + i0] : 0.0;
+                    const double l1 = (i1 > j && i1 < d) ? lu[(size_t)j * d + i1] : 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const double yj = __shfl_sync(FULL, (j & 1) ? y[cc][1] : y[cc][0], j >> 1);
+                        y[cc][0] = fma(-l0, yj, y[cc][0]);
+                        y[cc][1] = fma(-l1, yj, y[cc][1]);
+                    }
+                }
+                for (int j = d - 1; j >= 0; --j) {   // U x = y
+                    const double ujj = lu[(size_t)j * d + j];
+                    const double u0 = (i0 < j) ? lu[(size_t)j * d + i0] : 0.0;
+                    const double u1 = (i1 < j) ? lu[(size_t)j * d + i1] : 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const double xj = __shfl_sync(FULL, (j & 1) ? y[cc][1] : y[cc][0], j >> 1) / ujj;
+                        if (i0 == j) y[cc][0] = xj;
+                        if (i1 == j) y[cc][1] = xj;
+                        y[cc][0] = fma(-u0, xj, y[cc][0]);
+                        y[cc][1] = fma(-u1, xj, y[cc][1]);
+                    }
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    if (c0 + cc < d) {
+                        if (i0 < d) inv[(size_t)(c0 + cc) * d + i0] = y[cc][0];
+                        if (i1 < d) inv[(size_t)(c0 + cc) * d + i1] = y[cc][1];
+                    }
+            }
+            __syncwarp();
+            return;
         }
         // one right-hand side (column of the identity) per lane slot, substitution in the oracle's order
         for (int cc = 0; cc < 2; ++cc) {
