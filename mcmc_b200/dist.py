@@ -38,3 +38,24 @@ def all_reduce_max(value, device, group=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def all_gather_summary(chain_mean, chain_var, n_keep, n_chains_total, group=None):
+    """Posterior summaries over ALL ranks' chains without gathering any draws ("summary reductions fused
+    into the all-gather epilogue"): every rank passes the per-chain means / sample variances of its shard ([count_r, d] each,
+    e.g. from ``api.summarize(..., per_chain=True)``, which reduces the device-resident draws_out where it lies); the
+    O(n_chains * d) statistics are all-gathered and combined the same way the single-GPU kernel does.  Returns
+    (mean[d], var[d], rhat[d]) of the n_chains_total * n_keep draws on every rank."""
+    cm = all_gather_draws(chain_mean.contiguous(), n_chains_total, group=group).to(torch.float64)
+    cv = all_gather_draws(chain_var.contiguous(), n_chains_total, group=group).to(torch.float64)
+    C, n = float(n_chains_total), float(n_keep)
+    shift = cm[0]
+    e = cm - shift
+    t1, t2, tw = e.sum(dim=0), (e * e).sum(dim=0), cv.sum(dim=0)
+    mean = shift + t1 / C
+    sb = torch.clamp(t2 - t1 * (t1 / C), min=0.0)                 # sum_c (m_c - m)^2
+    W = tw / C
+    Bn = sb / (C - 1.0) if n_chains_total > 1 else torch.full_like(W, float("nan"))
+    var = ((n - 1.0) * tw + n * sb) / (C * n - 1.0)
+    rhat = torch.sqrt(((n - 1.0) / n * W + Bn) / W)
+    return mean, var, rhat

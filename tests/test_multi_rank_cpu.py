@@ -30,13 +30,15 @@ def _run_chains(first, count):
 def _worker(rank, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
     dist.init_process_group("gloo", rank=rank, world_size=WORLD)
-    from mcmc_b200.dist import all_gather_draws, all_reduce_max, chain_shard
+    from mcmc_b200.dist import all_gather_draws, all_gather_summary, all_reduce_max, chain_shard
 
     first, count = chain_shard(N_CHAINS, rank, WORLD)
     local = torch.from_numpy(_run_chains(first, count))
     full = all_gather_draws(local, N_CHAINS)
     t = all_reduce_max(1.0 + rank, "cpu")
-    q.put((rank, first, count, full.numpy(), t))
+    # summaries of all ranks' chains from per-chain statistics only (what api.summarize(per_chain=True) returns on a GPU)
+    m, v, rh = all_gather_summary(local.mean(dim=1), local.var(dim=1, unbiased=True), local.shape[1], N_CHAINS)
+    q.put((rank, first, count, full.numpy(), t, m.numpy(), v.numpy(), rh.numpy()))
     dist.destroy_process_group()
 
 
@@ -56,7 +58,13 @@ def test_sharded_runs_assemble_to_single_process_result():
         p.join(timeout=60)
         assert p.exitcode == 0
     want = _run_chains(0, N_CHAINS)
-    for rank, first, count, full, tmax in res:
+    T = want.shape[1]
+    cm, cv = want.mean(axis=1), want.var(axis=1, ddof=1)
+    W, Bn = cv.mean(axis=0), cm.var(axis=0, ddof=1)
+    for rank, first, count, full, tmax, m, v, rh in res:
         assert full.shape == (N_CHAINS, 5, D)
         assert np.array_equal(full, want)
         assert tmax == 2.0
+        assert np.allclose(m, want.reshape(-1, D).mean(axis=0), rtol=1e-13, atol=1e-15)
+        assert np.allclose(v, want.reshape(-1, D).var(axis=0, ddof=1), rtol=1e-12)
+        assert np.allclose(rh, np.sqrt(((T - 1) / T * W + Bn) / W), rtol=1e-12)
