@@ -64,7 +64,7 @@ typedef enum {
     MCMCB200_TARGET_DIAG_GAUSS = 1,  /* log pi = -1/2 sum_i w_i x_i^2 ; data = w[n_dim]                  */
     MCMCB200_TARGET_DENSE_GAUSS = 2, /* log pi = -1/2 x' P x ; data = P[n_dim^2], symmetric             */
     MCMCB200_TARGET_LINREG = 3,      /* log pi = -1/2 t' A t + b' t ; data = A[n_dim^2] (sym), b[n_dim]  */
-    MCMCB200_TARGET_NORMAL_MODEL = 4, /* Normal(mu, sigma) likelihood of examples/eigen/*_normal.cpp on
+    MCMCB200_TARGET_NORMAL_MODEL = 4, /* Normal(mu, sigma) likelihood of the examples/eigen/..._normal.cpp programs on
                                         sufficient statistics; n_dim = 2, data = {n, xbar, sum (x-xbar)^2};
                                         carries the Fisher metric used by mcmcb200_rmhmc_run */
     MCMCB200_TARGET_FUNNEL = 5       /* Neal's funnel (BASELINE config 5): x[0] = v ~ N(0, 3^2), x[i] | v ~ N(0, e^v);

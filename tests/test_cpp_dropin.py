@@ -29,6 +29,7 @@ def _build(src, out, std="c++14"):
 def test_header_and_examples_compile_and_link():
     _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
     _build(os.path.join(ROOT, "examples", "hmc_normal.cpp"), os.path.join(BIN, "hmc_normal"))
+    _build(os.path.join(ROOT, "examples", "rmhmc_funnel.cpp"), os.path.join(BIN, "rmhmc_funnel"))
 
 
 @pytest.mark.gpu
@@ -68,3 +69,13 @@ def test_example_runs(engine):
     assert r.returncode == 0, r.stderr
     mean = [float(v) for v in r.stdout.splitlines()[0].split(":")[1].split("(")[0].split()]
     assert abs(mean[0] - 2.0) < 0.3 and abs(mean[1] - 2.0) < 0.3, r.stdout
+
+
+@pytest.mark.gpu
+def test_funnel_example_runs(engine):
+    """BASELINE config 5 written like reference user code: RM-HMC, Neal's funnel d = 64, SoftAbs metric, many chains per call."""
+    exe = _build(os.path.join(ROOT, "examples", "rmhmc_funnel.cpp"), os.path.join(BIN, "rmhmc_funnel"))
+    r = subprocess.run([exe, "64"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    acc = float(r.stdout.strip().split("acceptance rate")[1])
+    assert 0.2 < acc < 0.9, r.stdout

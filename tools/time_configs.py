@@ -19,6 +19,28 @@ if "c4" in which:
         nlf = r["n_leapfrog"].sum()
         print("C4 NUTS d=256 dense cond 1e3: %d chains x 400 draws: kernel %.1f ms, %.3e draws/s, %.3e leapfrogs/s (%.1f leapfrogs/draw), eps=%.3f, wall %.1fs"
               % (C, r["kernel_ms"], C * 400 / r["kernel_ms"] * 1e3, nlf / r["kernel_ms"] * 1e3, nlf / (C * 400), r["step_size"].mean(), time.time() - t0))
+if "c3" in which:
+    # BASELINE config 3: MALA, d = 1024 Bayesian linear regression on sufficient statistics, 16384 chains, 20 + 100 draws;
+    # draws_out (13.4 GB) stays on the device
+    import torch
+    rng = np.random.default_rng(7)
+    d, C, n = 1024, 16384, 4096
+    X = rng.normal(size=(n, d))
+    beta = np.sin(np.arange(d))
+    yv = X @ beta + 0.5 * rng.normal(size=n)
+    A = X.T @ X / 0.25 + np.eye(d) / 100.0
+    A = (A + A.T) / 2
+    b = X.T @ yv / 0.25
+    eps = 0.5 / np.sqrt(np.linalg.eigvalsh(A).max())
+    td = np.concatenate([A.ravel(), b])
+    x0 = torch.from_numpy(rng.normal(size=(C, d)) * 0.01 + np.linalg.solve(A, b)).cuda()
+    draws = torch.empty((C, 100, d), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        r = mcmc_b200.mala(None, "linreg", target_data=td, step_size=eps, n_burnin=20, n_keep=100, rng_mode=api.RNG_PHILOX, seed=3,
+                           initial_dev_ptr=x0.data_ptr(), n_chains=C, n_dim=d, draws_dev_ptr=draws.data_ptr(),
+                           stream=torch.cuda.current_stream().cuda_stream)
+    print("C3 MALA d=1024 linreg: %d chains x 120 draws: kernel %.1f ms (%.3f ms/draw, %d launches), acc %.2f, gradient GEMM %.1f TFLOP/s-equivalent"
+          % (C, r["kernel_ms"], r["kernel_ms"] / 120, r["kernel_launches"], r["n_accept"].mean() / 100, 2.0 * d * d * C * 121 / r["kernel_ms"] * 1e-9))
 if "sweep" in which:
     for d in (32, 128, 512, 2048):
         C = 4096
