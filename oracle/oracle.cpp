@@ -989,6 +989,125 @@ double oracle_target(int target_id, const double* tdata, int d, const double* x,
     return otgt::value_and_grad(target_id, tdata, x, grad, d, sum_mode);
 }
 
+// ------------------------------------------------------------------ DE (src/de.cpp:30-271), SURVEY §8f item 4
+// Differential evolution MCMC (ter Braak): ONE population of n_pop members per call; in every generation member i proposes
+// X_i + gamma (X_c1 - X_c2) + U(-b, b)^d with two other members chosen at random.  The member loop updates X in place, so
+// member i sees the NEW rows of members < i (the reference's OpenMP loop races on exactly that; its single-threaded order is
+// the deterministic semantics restated here).  Random stream (single thread): engine(seed) -> one runif -> thread engine
+// seed = size_t((u + 0 + 1) * 1000) (stats/seed_values.hpp:27); per member and generation: c1 (redrawn while == i), c2
+// (redrawn while == i or == c1), d uniforms in (-b, b), one uniform z; rind(0, n-1) = size_t(U(nextafter(0, n), n))
+// (stats/rind.hpp:36).  tape_out (optional) records the variates a device kernel needs, in order: the n_pop*d initial
+// uniforms, then per generation and member {c1, c2, d proposal uniforms, z} (indices as doubles, rejected index draws are
+// not recorded); rng_mode RNG_TAPE replays such a tape.
+struct de_cfg_t {
+    int target_id;
+    const double* tdata;
+    int d;
+    long n_pop, n_burnin, n_keep;
+    int jumps;
+    double par_b, par_gamma_jump;
+    const double* init_lb;
+    const double* init_ub;
+    int vals_bound;
+    const double* lower;
+    const double* upper;
+    int rng_mode;             // RNG_MT or RNG_TAPE
+    unsigned long seed;
+    const double* tape; long tape_len;
+    int sum_mode;
+    double* tape_out; long tape_out_cap;
+};
+
+static double de_runif(std::mt19937_64& eng, double a, double b)
+{
+    const double a_adj = std::nextafter(a, b);   // runif.hpp:60
+    std::uniform_real_distribution<double> ud(a_adj, b);
+    return ud(eng);
+}
+
+int oracle_run_de(const de_cfg_t* cfg, const double* x0, double* draws, oracle_res_t* res)
+{
+    Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode; c.identity = true;
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    const int d = c.d;
+    const long n_pop = cfg->n_pop, n_total = cfg->n_burnin + cfg->n_keep;
+    const double par_b = cfg->par_b;
+    const double par_gamma = 2.38 / std::sqrt(2.0 * double(size_t(d)));   // :59 (settings.par_gamma is never read)
+    vec lb(d), ub(d);
+    for (int j = 0; j < d; ++j) {   // :70-71
+        lb[j] = cfg->init_lb ? cfg->init_lb[j] : x0[j] + (-0.5);
+        ub[j] = cfg->init_ub ? cfg->init_ub[j] : x0[j] + 0.5;
+    }
+    if (c.bounded)   // sampling_bounds_check, misc/bounds_check.hpp:27-57
+        for (int j = 0; j < d; ++j) {
+            if (c.btype[j] == 4 || c.btype[j] == 2) lb[j] = std::max(c.lb[j], lb[j]);
+            if (c.btype[j] == 4 || c.btype[j] == 3) ub[j] = std::min(c.ub[j], ub[j]);
+        }
+    std::mt19937_64 master(cfg->seed), eng;
+    long cursor = 0, rec_n = 0;
+    auto record = [&](double v) { if (cfg->tape_out && rec_n < cfg->tape_out_cap) cfg->tape_out[rec_n] = v; ++rec_n; };
+    auto from_tape = [&]() { return (cursor < cfg->tape_len) ? cfg->tape[cursor++] : std::nan(""); };
+    if (cfg->rng_mode == RNG_MT) {
+        const double u0 = de_runif(master, 0.0, 1.0);
+        eng.seed(static_cast<size_t>((u0 + 0 + 1) * 1000));   // generate_seed_value(0, 1, rand_engine)
+    }
+    auto unif = [&](double a, double b) {
+        const double v = (cfg->rng_mode == RNG_MT) ? de_runif(eng, a, b) : from_tape();
+        record(v);
+        return v;
+    };
+    auto index_other = [&](long i, long c1) -> long {   // do { c = rind(0, n_pop-1) } while (c == i [|| c == c1])
+        long cidx;
+        if (cfg->rng_mode == RNG_MT) {
+            do { cidx = long(static_cast<size_t>(de_runif(eng, 0.0, double(n_pop - 1) + 1.0))); } while (cidx == i || cidx == c1);
+        } else {
+            cidx = long(from_tape());
+        }
+        record(double(cidx));
+        return cidx;
+    };
+
+    vec X(size_t(n_pop) * d), tv(n_pop), prop(d), rv(d);
+    for (long i = 0; i < n_pop; ++i) {   // :118-137
+        for (int j = 0; j < d; ++j) rv[j] = unif(0.0, 1.0);
+        for (int j = 0; j < d; ++j) X[size_t(i) * d + j] = lb[j] + (ub[j] - lb[j]) * rv[j];
+        double v = box_logp(c, &X[size_t(i) * d]);
+        if (!std::isfinite(v)) v = -std::numeric_limits<double>::infinity();
+        tv[i] = v;
+    }
+    long n_accept = 0;
+    double gamma_run = par_gamma;
+    for (long g = 0; g < n_total; ++g) {
+        const double temperature = 1.0;   // de_cooling_schedule, de.hpp:86-89
+        if (cfg->jumps && ((g + 1) % 10 == 0)) gamma_run = cfg->par_gamma_jump;   // :147-149
+        for (long i = 0; i < n_pop; ++i) {
+            const long c1 = index_other(i, -1);          // :166-168
+            const long c2 = index_other(i, c1);          // :170-172
+            for (int j = 0; j < d; ++j) rv[j] = unif(-par_b, par_b);   // :177
+            for (int j = 0; j < d; ++j)                  // :179: (X_i + (X_c1 - X_c2) * gamma) + rand
+                prop[j] = (X[size_t(i) * d + j] + (X[size_t(c1) * d + j] - X[size_t(c2) * d + j]) * gamma_run) + rv[j];
+            double pv = box_logp(c, prop.data());        // :181
+            if (!std::isfinite(pv)) pv = -std::numeric_limits<double>::infinity();
+            const double comp = pv - tv[i];              // :189
+            const double z = unif(0.0, 1.0);             // :190
+            if (comp > temperature * std::log(z)) {      // :192
+                for (int j = 0; j < d; ++j) X[size_t(i) * d + j] = prop[j];
+                tv[i] = pv;
+                if (g >= cfg->n_burnin) ++n_accept;
+            }
+        }
+        if (g >= cfg->n_burnin) {                        // :210-212
+            double* out = draws + size_t(g - cfg->n_burnin) * size_t(n_pop) * d;
+            for (size_t k = 0; k < size_t(n_pop) * d; ++k) out[k] = X[k];
+        }
+        if (cfg->jumps && ((g + 1) % 10 == 0)) gamma_run = par_gamma;   // :214-216
+    }
+    if (c.bounded)   // :223-232
+        for (long r = 0; r < cfg->n_keep * n_pop; ++r) { vec tmp(draws + r * d, draws + (r + 1) * d); box_inv_transform(c, tmp.data(), draws + r * d); }
+    res->n_accept = n_accept; res->tape_used = rec_n; res->final_step = par_gamma; res->n_leapfrog = 0;
+    return 0;
+}
+
 // a target's registered metric and its derivative cube (tests check the closed forms against finite differences)
 int oracle_metric(int target_id, int metric_id, const double* tdata, int d, const double* x, double* G, double* dG)
 {

@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY (oracle/).  Thin extern "C" driver around the
 // UNMODIFIED reference samplers.  It is compiled together with
-// /root/reference/src/{hmc,mala,nuts,rmhmc,rwmh}.cpp (where they lie; nothing is copied
+// /root/reference/src/{hmc,mala,nuts,rmhmc,rwmh,de}.cpp (where they lie; nothing is copied
 // into this repo) against the stand-in Eigen header — see oracle/Makefile —
 // into oracle/_ref/libmcmc_ref_{strict,fast}.so.
 //
@@ -213,6 +213,53 @@ int ref_run_chains(int sampler, int target_id, const double* tdata, int d, long 
     const auto t1 = std::chrono::steady_clock::now();
     if (elapsed_s) *elapsed_s = std::chrono::duration<double>(t1 - t0).count();
     return bad;
+}
+
+// mcmc::de (src/de.cpp:30-271): one population of n_pop members, single-threaded (omp_n_threads = 1: the member loop updates X
+// in place, so its sequential semantics are the deterministic ones).  draws_out: [n_keep][n_pop][d] (Cube_t: one n_pop x d
+// matrix per kept generation).  init_lb / init_ub: d entries or null (defaults initial_vals -+ 0.5, src/de.cpp:70-71).
+struct ref_de_settings_t {
+    long n_pop, n_burnin, n_keep;
+    int jumps;
+    double par_b, par_gamma_jump;
+    const double* init_lb;
+    const double* init_ub;
+    int vals_bound;
+    const double* lower;
+    const double* upper;
+};
+
+int ref_run_de(int target_id, const double* tdata, int d, const double* x0, const ref_de_settings_t* st, unsigned long seed,
+               double* draws_out, long* n_accept)
+{
+    tgt_ctx_t ctx = {target_id, tdata, d, 0};
+    mcmc::ColVec_t init(d);
+    for (int j = 0; j < d; ++j) init(j) = x0[j];
+    mcmc::algo_settings_t s;
+    s.rng_seed_value = seed;
+    if (st->vals_bound) {
+        s.vals_bound = true;
+        s.lower_bounds.resize(d);
+        s.upper_bounds.resize(d);
+        for (int j = 0; j < d; ++j) { s.lower_bounds(j) = st->lower[j]; s.upper_bounds(j) = st->upper[j]; }
+    }
+    s.de_settings.n_pop = size_t(st->n_pop);
+    s.de_settings.n_burnin_draws = size_t(st->n_burnin);
+    s.de_settings.n_keep_draws = size_t(st->n_keep);
+    s.de_settings.jumps = st->jumps != 0;
+    s.de_settings.par_b = st->par_b;
+    s.de_settings.par_gamma_jump = st->par_gamma_jump;
+    s.de_settings.omp_n_threads = 1;
+    if (st->init_lb) { s.de_settings.initial_lb.resize(d); for (int j = 0; j < d; ++j) s.de_settings.initial_lb(j) = st->init_lb[j]; }
+    if (st->init_ub) { s.de_settings.initial_ub.resize(d); for (int j = 0; j < d; ++j) s.de_settings.initial_ub(j) = st->init_ub[j]; }
+    mcmc::Cube_t draws;
+    const bool ok = mcmc::de(init, log_kernel_val_cb, draws, &ctx, s);
+    if (draws_out)
+        for (long t = 0; t < st->n_keep; ++t)
+            for (long i = 0; i < st->n_pop; ++i)
+                for (int j = 0; j < d; ++j) draws_out[(size_t(t) * st->n_pop + i) * d + j] = draws.mat(t)(i, j);
+    if (n_accept) *n_accept = long(s.de_settings.n_accept_draws);
+    return ok ? 0 : 1;
 }
 
 int ref_max_threads(void)

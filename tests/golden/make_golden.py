@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Generate tests/golden/reference_golden.json from the UNMODIFIED reference (oracle/_ref/libmcmc_ref_strict.so:
-/root/reference/src/{hmc,mala,nuts,rmhmc,rwmh}.cpp compiled against the stand-in Eigen, -O2 -ffp-contract=off).
+/root/reference/src/{hmc,mala,nuts,rmhmc,rwmh,de}.cpp compiled against the stand-in Eigen, -O2 -ffp-contract=off).
 
 Run in the build container (where /root/reference exists):   python tests/golden/make_golden.py
 The reference ships no golden vectors of its own, so these fixtures pin the oracle — and through it
@@ -117,10 +117,31 @@ def main():
         e["draws_hex"] = hexlist(draws)
         e["n_accept"] = int(acc)
         golden["cases"].append(e)
+    # mcmc::de (src/de.cpp): one population per case, single-threaded member loop; draws [n_keep][n_pop][d]
+    inf = float("inf")
+    golden["de_cases"] = []
+    for c in [
+        dict(name="de_iso_d3", target=ol.TGT_ISO_GAUSS, tdata=None, x0=[0.5, -0.5, 1.0], seed=11, st=dict(n_pop=12, n_burnin=5, n_keep=20)),
+        dict(name="de_diag_d6_jumps", target=ol.TGT_DIAG_GAUSS, tdata=np.linspace(0.5, 2, 6).tolist(), x0=[0.1, -0.2, 0.3, 0.0, 0.5, -0.4], seed=12,
+             st=dict(n_pop=20, n_burnin=15, n_keep=25, jumps=True, par_b=1e-3)),
+        dict(name="de_box_d4", target=ol.TGT_DIAG_GAUSS, tdata=[1.0, 0.5, 2.0, 1.5], x0=[0.3, 0.7, 0.4, 0.2], seed=13,
+             st=dict(n_pop=10, n_burnin=5, n_keep=30), lower=[-inf, 0.0, -inf, -1.0], upper=[inf, inf, 2.0, 1.5]),
+    ]:
+        st = ol.DeSettings(**c["st"])
+        if "lower" in c:
+            st["lower_bounds"], st["upper_bounds"] = c["lower"], c["upper"]
+        draws, acc = ref.run_de(c["target"], c["tdata"], c["x0"], st, c["seed"])
+        e = dict(c)
+        if "lower" in c:
+            e["lower"], e["upper"] = hexlist(c["lower"]), hexlist(c["upper"])
+        e["draws_shape"] = list(draws.shape)
+        e["draws_hex"] = hexlist(draws)
+        e["n_accept"] = int(acc)
+        golden["de_cases"].append(e)
     path = os.path.join(HERE, "reference_golden.json")
     with open(path, "w") as f:
         json.dump(golden, f, indent=0)
-    print("wrote", path, os.path.getsize(path), "bytes,", len(golden["cases"]), "cases")
+    print("wrote", path, os.path.getsize(path), "bytes,", len(golden["cases"]), "cases +", len(golden["de_cases"]), "de cases")
 
 
 if __name__ == "__main__":

@@ -60,6 +60,35 @@ class _OracleCfg(ctypes.Structure):
     ]
 
 
+class _RefDeSettings(ctypes.Structure):
+    _fields_ = [("n_pop", ctypes.c_long), ("n_burnin", ctypes.c_long), ("n_keep", ctypes.c_long), ("jumps", ctypes.c_int),
+                ("par_b", ctypes.c_double), ("par_gamma_jump", ctypes.c_double), ("init_lb", ctypes.c_void_p),
+                ("init_ub", ctypes.c_void_p), ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p)]
+
+
+class _DeCfg(ctypes.Structure):
+    _fields_ = [("target_id", ctypes.c_int), ("tdata", ctypes.c_void_p), ("d", ctypes.c_int), ("n_pop", ctypes.c_long),
+                ("n_burnin", ctypes.c_long), ("n_keep", ctypes.c_long), ("jumps", ctypes.c_int), ("par_b", ctypes.c_double),
+                ("par_gamma_jump", ctypes.c_double), ("init_lb", ctypes.c_void_p), ("init_ub", ctypes.c_void_p),
+                ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p), ("rng_mode", ctypes.c_int),
+                ("seed", ctypes.c_ulong), ("tape", ctypes.c_void_p), ("tape_len", ctypes.c_long), ("sum_mode", ctypes.c_int),
+                ("tape_out", ctypes.c_void_p), ("tape_out_cap", ctypes.c_long)]
+
+
+class DeSettings(dict):
+    """de_settings_t with the reference's defaults (include/misc/mcmc_structs.hpp:44-62)."""
+
+    DEFAULTS = dict(n_pop=100, n_burnin=1000, n_keep=1000, jumps=False, par_b=1e-4, par_gamma_jump=2.0, initial_lb=None, initial_ub=None,
+                    lower_bounds=None, upper_bounds=None)
+
+    def __init__(self, **kw):
+        super().__init__(self.DEFAULTS)
+        for k in kw:
+            if k not in self.DEFAULTS:
+                raise KeyError(k)
+        self.update(kw)
+
+
 class _OracleRes(ctypes.Structure):
     _fields_ = [("n_accept", ctypes.c_long), ("tape_used", ctypes.c_long), ("final_step", ctypes.c_double),
                 ("n_leapfrog", ctypes.c_long)]
@@ -147,6 +176,24 @@ class Reference:
         assert rc == 0, rc
         return draws, acc, el.value
 
+    def run_de(self, target_id, tdata, x0, st, seed):
+        """mcmc::de, one population, single-threaded member loop -> (draws [n_keep][n_pop][d], n_accept)."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        d = x0.size
+        tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
+        keep = []
+        vb, lo, hi = _bounds(st, d, keep)
+        ilb = None if st["initial_lb"] is None else np.ascontiguousarray(st["initial_lb"], dtype=np.float64)
+        iub = None if st["initial_ub"] is None else np.ascontiguousarray(st["initial_ub"], dtype=np.float64)
+        rs = _RefDeSettings(st["n_pop"], st["n_burnin"], st["n_keep"], int(st["jumps"]), st["par_b"], st["par_gamma_jump"], _ptr(ilb),
+                            _ptr(iub), vb, lo, hi)
+        draws = np.zeros((st["n_keep"], st["n_pop"], d))
+        acc = ctypes.c_long(0)
+        self.lib.ref_run_de.restype = ctypes.c_int
+        rc = self.lib.ref_run_de(target_id, _ptr(tdata), d, _ptr(x0), ctypes.byref(rs), ctypes.c_ulong(seed), _ptr(draws), ctypes.byref(acc))
+        assert rc == 0, rc
+        return draws, acc.value
+
     def max_threads(self):
         return self.lib.ref_max_threads()
 
@@ -190,6 +237,30 @@ class Oracle:
                    n_leapfrog=res.n_leapfrog)
         if want_logp:
             out["logp"] = logp
+        if record_tape:
+            out["tape"] = rec[:min(record_tape, res.tape_used)]
+        return out
+
+    def run_de(self, target_id, tdata, x0, st, seed=0, rng_mode=RNG_MT, tape=None, sum_mode=SUM_SEQ, record_tape=0):
+        """The restated mcmc::de (oracle.cpp oracle_run_de): draws [n_keep][n_pop][d], n_accept, optionally the variate tape."""
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        d = x0.size
+        tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
+        keep = []
+        vb, lo, hi = _bounds(st, d, keep)
+        ilb = None if st["initial_lb"] is None else np.ascontiguousarray(st["initial_lb"], dtype=np.float64)
+        iub = None if st["initial_ub"] is None else np.ascontiguousarray(st["initial_ub"], dtype=np.float64)
+        tape_a = None if tape is None else np.ascontiguousarray(tape, dtype=np.float64)
+        rec = np.zeros(record_tape) if record_tape else None
+        cfg = _DeCfg(target_id, _ptr(tdata), d, st["n_pop"], st["n_burnin"], st["n_keep"], int(st["jumps"]), st["par_b"],
+                     st["par_gamma_jump"], _ptr(ilb), _ptr(iub), vb, lo, hi, rng_mode, ctypes.c_ulong(seed), _ptr(tape_a),
+                     0 if tape_a is None else tape_a.size, sum_mode, _ptr(rec), record_tape)
+        draws = np.zeros((st["n_keep"], st["n_pop"], d))
+        res = _OracleRes()
+        self.lib.oracle_run_de.restype = ctypes.c_int
+        rc = self.lib.oracle_run_de(ctypes.byref(cfg), _ptr(x0), _ptr(draws), ctypes.byref(res))
+        assert rc == 0, rc
+        out = dict(draws=draws, n_accept=res.n_accept, tape_used=res.tape_used)
         if record_tape:
             out["tape"] = rec[:min(record_tape, res.tape_used)]
         return out

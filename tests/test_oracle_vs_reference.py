@@ -238,3 +238,52 @@ def test_funnel_softabs_metric_closed_form(oracle):
         G1, dG1 = oracle.metric(ol.TGT_FUNNEL, 1, None, x)
         assert np.allclose(np.diag(G1), [1 / 9 + (d - 1) / 2] + [e] * (d - 1)) and np.abs(G1 - np.diag(np.diag(G1))).max() == 0
         assert np.abs(dG1[1:]).max() == 0 and np.allclose(np.diag(dG1[0]), [0] + [-e] * (d - 1))
+
+
+# ---- mcmc::de: the oracle restatement and the tape a device kernel will consume ---------------------
+
+def _de_cases():
+    rng = np.random.default_rng(9)
+    inf = np.inf
+    return [
+        ("iso d=3", ol.TGT_ISO_GAUSS, None, [0.5, -0.5, 1.0], ol.DeSettings(n_pop=12, n_burnin=5, n_keep=20), 11),
+        ("diag d=6 jumps", ol.TGT_DIAG_GAUSS, np.linspace(0.5, 2, 6), rng.normal(size=6), ol.DeSettings(n_pop=20, n_burnin=15, n_keep=25, jumps=True, par_b=1e-3), 12),
+        ("funnel d=5 initial bounds", ol.TGT_FUNNEL, None, np.zeros(5),
+         ol.DeSettings(n_pop=16, n_burnin=10, n_keep=20, initial_lb=-np.ones(5), initial_ub=np.ones(5)), 13),
+        ("box diag d=4", ol.TGT_DIAG_GAUSS, [1.0, 0.5, 2.0, 1.5], [0.3, 0.7, 0.4, 0.2],
+         ol.DeSettings(n_pop=10, n_burnin=5, n_keep=30, lower_bounds=[-inf, 0.0, -inf, -1.0], upper_bounds=[inf, inf, 2.0, 1.5]), 14),
+        ("normal model", ol.TGT_NORMAL_MODEL, [100.0, 2.0, 400.0], [2.5, 2.5], ol.DeSettings(n_pop=8, n_burnin=10, n_keep=40, par_b=1e-2), 15),
+        ("dense d=7 default population", ol.TGT_DENSE_GAUSS, (lambda a: (a @ a.T / 7 + np.eye(7)).ravel())(rng.normal(size=(7, 7))), rng.normal(size=7),
+         ol.DeSettings(n_burnin=3, n_keep=6), 16),
+    ]
+
+
+def test_de_oracle_bit_equal_to_live_reference_and_tape_replay(oracle, reference):
+    """The restated differential-evolution sampler reproduces the unmodified src/de.cpp (single-threaded member loop) bit for bit;
+    the recorded variate tape (what a device kernel will consume) replays to the same draws."""
+    for name, tid, tdata, x0, st, seed in _de_cases():
+        ref, acc = reference.run_de(tid, tdata, x0, st, seed)
+        o = oracle.run_de(tid, tdata, x0, st, seed=seed, record_tape=2_000_000)
+        assert np.array_equal(o["draws"], ref), name
+        assert o["n_accept"] == acc, name
+        d, n_pop, n_total = len(x0), st["n_pop"], st["n_burnin"] + st["n_keep"]
+        assert o["tape_used"] == n_pop * d + n_total * n_pop * (d + 3), name      # static layout: a tape-driven kernel is possible
+        rp = oracle.run_de(tid, tdata, x0, st, rng_mode=ol.RNG_TAPE, tape=o["tape"])
+        assert np.array_equal(rp["draws"], o["draws"]) and rp["n_accept"] == o["n_accept"], name
+        tp = o["tape"][n_pop * d:].reshape(n_total, n_pop, d + 3)
+        i = np.arange(n_pop)[None, :]
+        assert ((tp[..., 0] != i) & (tp[..., 1] != i) & (tp[..., 0] != tp[..., 1])).all(), name   # c1, c2, i pairwise distinct
+        assert (np.abs(tp[..., 2:2 + d]) < st["par_b"]).all() and ((tp[..., -1] > 0) & (tp[..., -1] < 1)).all(), name
+
+
+def test_de_golden_cases(oracle, golden):
+    assert len(golden["de_cases"]) == 3
+    for c in golden["de_cases"]:
+        st = ol.DeSettings(**c["st"])
+        if "lower" in c:
+            st["lower_bounds"] = np.array([float.fromhex(h) for h in c["lower"]])
+            st["upper_bounds"] = np.array([float.fromhex(h) for h in c["upper"]])
+        want = np.array([float.fromhex(h) for h in c["draws_hex"]]).reshape(c["draws_shape"])
+        o = oracle.run_de(c["target"], c["tdata"], c["x0"], st, seed=c["seed"])
+        assert np.array_equal(o["draws"], want), c["name"]
+        assert o["n_accept"] == c["n_accept"], c["name"]
