@@ -26,6 +26,25 @@ def _build(src, out, std="c++14"):
     return out
 
 
+def test_c_abi_header_is_plain_c_and_fails_loudly_without_a_gpu():
+    """include/mcmc_b200.h + mcmc_b200_summary.h compile as C99 (what a cgo / JNI / ctypes binding sees); the example runs the
+    hot path through the C ABI and, on a machine without a CUDA device, stops with the library's error — never a CPU result."""
+    from mcmc_b200 import api
+
+    os.makedirs(BIN, exist_ok=True)
+    exe = os.path.join(BIN, "c_abi_hmc")
+    libdir = os.path.dirname(api.LIB_PATH)
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    r = subprocess.run([cc, "-std=c99", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "c_abi_hmc.c"),
+                        "-o", exe, "-L", libdir, "-lmcmc_b200", "-Wl,-rpath," + libdir, "-lm"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    if api.device_count() > 0:
+        assert r.returncode == 0 and "acceptance rate" in r.stdout, (r.stdout, r.stderr)
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr, (r.stdout, r.stderr)
+
+
 def test_header_and_examples_compile_and_link():
     _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
     _build(os.path.join(ROOT, "examples", "hmc_normal.cpp"), os.path.join(BIN, "hmc_normal"))
