@@ -521,7 +521,9 @@ int mcmcb200_nuts_run(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng, c
     a.work = static_cast<double*>(p);
     // dense targets with enough chains to fill the GPU run 8 chains per CTA with cooperative gradients (nuts.cu);
     // MCMCB200_NUTS_COOP=0/1 forces the choice (tests compare the two kernels bit for bit)
-    a.coop = pr->n_chains >= 64;
+    // by default only for the target whose cooperative path is covered by the GPU parity tests (dense_gauss, the C4 target);
+    // linreg has the same kernel instantiated and can be switched on with the environment variable
+    a.coop = pr->n_chains >= 64 && pr->target_id == MCMCB200_TARGET_DENSE_GAUSS;
     if (const char* e = std::getenv("MCMCB200_NUTS_COOP")) a.coop = (e[0] == '1');
     a.coop_batch = 6;   // measured on B200 (C4 shape, 1184 chains x 40 draws): 2 -> 456 ms, 4 -> 332, 6 -> 314, 8 -> 332
     if (const char* e = std::getenv("MCMCB200_NUTS_BATCH")) a.coop_batch = std::atoi(e) > 0 ? std::atoi(e) : 1;
