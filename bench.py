@@ -12,6 +12,9 @@ across ranks with no data-path collective (weak scaling: 4096 chains per GPU, gl
   roofline algorithmic bytes (2*d*8 B per transition) / CUDA-event kernel time vs the measured HBM peak
   cpu_baseline / --impl reference: the UNMODIFIED reference (oracle/_ref, OpenMP loop over chains, one mcmc::hmc
            call per chain) on the host cores, bounded sample of the same workload.
+  e2e_summary (informational, not the reference's output format): the same call chain when the caller only needs
+           posterior summaries — draws_out stays in HBM and mcmcb200_summarize_draws reduces it there.
+With --gpus N > 1 every rank first binds itself to the host cores of its GPU's NUMA node (best effort).
 """
 import argparse
 import json
