@@ -269,18 +269,38 @@ inline void fill_problem(mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, const fp_t
     rng.seed = s.rng_seed_value;
 }
 
-// [C][n_keep][d] chain-major -> per-chain n_keep x d column-major matrices
+// [C][n_keep][d] chain-major -> per-chain n_keep x d column-major matrices (the reference's Mat_t layout).
+// A 32 x 32-tiled transpose per chain; chains are spread over host threads once the output is large (the whole C2 job is
+// 4.2 GB: a naive single-threaded transpose would cost more than the sampling call itself).
+inline void transpose_chain(const fp_t* in, fp_t* out, size_t n_keep, size_t d)
+{
+    const size_t B = 32;
+    for (size_t t0 = 0; t0 < n_keep; t0 += B)
+        for (size_t j0 = 0; j0 < d; j0 += B) {
+            const size_t t1 = t0 + B < n_keep ? t0 + B : n_keep, j1 = j0 + B < d ? j0 + B : d;
+            for (size_t j = j0; j < j1; ++j)
+                for (size_t t = t0; t < t1; ++t) out[j * n_keep + t] = in[t * d + j];
+        }
+}
 inline void unpack(const std::vector<fp_t>& buf, size_t n_chains, size_t n_keep, size_t d, Mat_t* single, Cube_t* cube)
 {
     if (cube) cube->set_n_mat(n_chains);
-    for (size_t c = 0; c < n_chains; ++c) {
-        Mat_t& m = cube ? cube->mat(c) : *single;
-        mresize(m, n_keep, d);
-        fp_t* out = mdata(m);
-        const fp_t* in = buf.data() + c * n_keep * d;
-        for (size_t t = 0; t < n_keep; ++t)
-            for (size_t j = 0; j < d; ++j) out[j * n_keep + t] = in[t * d + j];
+    for (size_t c = 0; c < n_chains; ++c) mresize(cube ? cube->mat(c) : *single, n_keep, d);
+    auto work = [&](size_t c_begin, size_t c_end) {
+        for (size_t c = c_begin; c < c_end; ++c)
+            transpose_chain(buf.data() + c * n_keep * d, mdata(cube ? cube->mat(c) : *single), n_keep, d);
+    };
+    size_t n_thr = 1;
+    if (n_chains > 1 && n_chains * n_keep * d >= (size_t(1) << 22)) {
+        n_thr = std::thread::hardware_concurrency();
+        if (n_thr == 0) n_thr = 1;
+        if (n_thr > 16) n_thr = 16;
+        if (n_thr > n_chains) n_thr = n_chains;
     }
+    if (n_thr <= 1) { work(0, n_chains); return; }
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < n_thr; ++g) th.emplace_back(work, n_chains * g / n_thr, n_chains * (g + 1) / n_thr);
+    for (auto& t : th) t.join();
 }
 
 inline const fp_t* precond_or_null(const Mat_t& m, size_t d) { return (msize(m) == d * d) ? cdata(m) : nullptr; }  // src/hmc.cpp:57

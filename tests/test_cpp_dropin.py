@@ -45,6 +45,13 @@ def test_c_abi_header_is_plain_c_and_fails_loudly_without_a_gpu():
         assert r.returncode == 1 and "no CPU fallback" in r.stderr, (r.stdout, r.stderr)
 
 
+def test_draws_out_adapter_on_the_cpu():
+    """b200_detail::unpack (chain-major device layout -> the reference's column-major Mat_t per chain, tiled + threaded)."""
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "unpack_check.cpp"), os.path.join(BIN, "unpack_check"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "unpack ok" in r.stdout, (r.stdout, r.stderr)
+
+
 def test_header_and_examples_compile_and_link():
     _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
     _build(os.path.join(ROOT, "examples", "hmc_normal.cpp"), os.path.join(BIN, "hmc_normal"))
