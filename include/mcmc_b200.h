@@ -14,7 +14,9 @@
  *                          include/mcmc/rmhmc.hpp:47-86, src/rmhmc.cpp:30-325
  *   mcmcb200_rwmh_run   <- bool mcmc::rwmh (initial_vals, target_log_kernel (value only), draws_out, target_data, settings)
  *                          include/mcmc/rwmh.hpp:43-72, src/rwmh.cpp:30-199   (the gradient-free sibling)
- *   mcmcb200_*_settings <- hmc_/mala_/nuts_/rmhmc_/rwmh_settings_t + algo_settings_t
+ *   mcmcb200_de_run     <- bool mcmc::de   (initial_vals, target_log_kernel (value only), Cube_t& draws_out, target_data, settings)
+ *                          include/mcmc/de.hpp:43-72, src/de.cpp:30-271   (the population sampler)
+ *   mcmcb200_*_settings <- hmc_/mala_/nuts_/rmhmc_/rwmh_/de_settings_t + algo_settings_t
  *                          include/misc/mcmc_structs.hpp:66-134,151-184 (same field names and defaults)
  *
  * Differences forced by the device boundary:
@@ -179,10 +181,34 @@ typedef struct mcmcb200_rwmh_settings {
     int32_t arith;          /* mcmcb200_arith_t */
 } mcmcb200_rwmh_settings_t;
 
+/* de_settings_t (mcmc_structs.hpp:44-62).  par_gamma is kept out: the reference never reads it (src/de.cpp:58-59 uses
+   2.38 / sqrt(2 n_vals)).  One call runs problem.n_chains independent POPULATIONS of n_pop members each;
+   problem.initial_vals is [n_chains][n_dim] (the reference's initial_vals of each population);
+   draws_out is [n_chains][n_keep_draws][n_pop][n_dim] (per population the reference's Cube_t: n_keep matrices of
+   n_pop x n_vals, row-major here); n_accept_draws[p] counts accepted member updates after burn-in (src/de.cpp:198).
+   MCMCB200_RNG_USER_TAPE stride per population: n_pop*n_dim + (n_burnin+n_keep)*n_pop*(n_dim+3), see csrc/de.cu. */
+typedef struct mcmcb200_de_settings {
+    int64_t n_burnin_draws; /* default 1000 */
+    int64_t n_keep_draws;   /* default 1000 */
+    int64_t n_pop;          /* default 100; >= 3 */
+    int32_t jumps;          /* default 0 */
+    int32_t arith;          /* mcmcb200_arith_t */
+    double par_b;           /* default 1e-4 */
+    double par_gamma_jump;  /* default 2.0 */
+    const double* initial_lb; /* HOST [n_dim] or NULL -> initial_vals - 0.5 (src/de.cpp:70) */
+    const double* initial_ub; /* HOST [n_dim] or NULL -> initial_vals + 0.5 (src/de.cpp:71) */
+} mcmcb200_de_settings_t;
+
+typedef enum {
+    MCMCB200_LAYOUT_CHAIN_ROWS = 0, /* draws_out[chain][t][j]: each chain a row-major n_keep x n_dim matrix (default)          */
+    MCMCB200_LAYOUT_COLMAJOR = 1    /* draws_out[chain][j][t]: each chain the reference's column-major n_keep x n_dim Mat_t
+                                       (SURVEY Q23), transposed on the device before it is handed back                     */
+} mcmcb200_layout_t;
+
 typedef struct mcmcb200_output {
-    double* draws_out;       /* [n_chains][n_keep_draws][n_dim] */
+    double* draws_out;       /* [n_chains][n_keep_draws][n_dim] (see draws_layout) */
     int32_t draws_mem;       /* mcmcb200_mem_t */
-    int32_t reserved0;
+    int32_t draws_layout;    /* mcmcb200_layout_t */
     int64_t* n_accept_draws; /* HOST, [n_chains]: post-burn-in acceptances per chain (src/hmc.cpp:196-199); may be NULL */
     double* logp_out;        /* optional, same memory space as draws_out: log pi of each kept draw, [n_chains][n_keep] */
     double* step_size_out;   /* optional HOST [n_chains]: NUTS step size after the last draw */
@@ -198,6 +224,7 @@ void mcmcb200_mala_settings_default(mcmcb200_mala_settings_t* s);
 void mcmcb200_nuts_settings_default(mcmcb200_nuts_settings_t* s);
 void mcmcb200_rmhmc_settings_default(mcmcb200_rmhmc_settings_t* s);
 void mcmcb200_rwmh_settings_default(mcmcb200_rwmh_settings_t* s);
+void mcmcb200_de_settings_default(mcmcb200_de_settings_t* s);
 
 int mcmcb200_hmc_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
                      const mcmcb200_hmc_settings_t* settings, mcmcb200_output_t* out);
@@ -211,10 +238,32 @@ int mcmcb200_rmhmc_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* 
 int mcmcb200_rwmh_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
                       const mcmcb200_rwmh_settings_t* settings, mcmcb200_output_t* out);
 
+int mcmcb200_de_run(const mcmcb200_problem_t* problem, const mcmcb200_rng_t* rng,
+                    const mcmcb200_de_settings_t* settings, mcmcb200_output_t* out);
+
 /* Target registry: id by name ("iso_gauss", "diag_gauss", "dense_gauss", "linreg", "normal_model", "funnel"), -1 if unknown;
    number of doubles the target's data blob must hold for a given n_dim (-1 if unknown / n_dim invalid). */
 int mcmcb200_target_lookup(const char* name);
 int64_t mcmcb200_target_data_len(int target_id, int32_t n_dim);
+/* User-defined targets: the reference's log-kernel is an arbitrary callback (include/mcmc/hmc.hpp:43-58); on the device
+   it is a __device__ functor compiled by the USER (include/mcmc_b200_device.cuh shows how: one struct + one macro in the
+   user's own .cu, built into the user's shared library, no rebuild of libmcmc_b200.so).  The macro fills this table with
+   launchers of the sampler kernels instantiated for that functor and calls mcmcb200_register_target() when the user's
+   library is loaded; the returned id (>= MCMCB200_USER_TARGET_BASE) is used like a built-in one.  A NULL launcher means
+   "sampler not instantiated" (the run call then fails with MCMCB200_ERR_UNKNOWN_TARGET). */
+#define MCMCB200_USER_TARGET_BASE 64
+#define MCMCB200_USER_ABI 2u
+typedef struct mcmcb200_user_target {
+    uint32_t abi_version;                   /* MCMCB200_USER_ABI: layout of the internal launch structs */
+    int64_t (*data_len)(int32_t n_dim);      /* minimum doubles of target data for n_dim; < 0 = n_dim not valid for this target */
+    int (*launch[8])(const void* launch_struct); /* hmc, mala, nuts, rwmh, de, target_eval, rmhmc (user metric), reserved */
+} mcmcb200_user_target_t;
+int mcmcb200_register_target(const char* name, const mcmcb200_user_target_t* table); /* id, or -(error code) */
+
+/* Metric registry (the reference's tensor_fn, include/mcmc/rmhmc.hpp:51): "normal_fisher" (normal_model, id 0),
+   "funnel_fisher" (funnel, id 1), "funnel_softabs" (funnel, id 2) -> the target it belongs to and the metric_id for
+   mcmcb200_rmhmc_settings_t.  MCMCB200_ERR_UNKNOWN_TARGET if the name is not registered. */
+int mcmcb200_metric_lookup(const char* name, int* target_id_out, int* metric_id_out);
 
 /* Evaluate a registered functor on the device: x is HOST [n_points][n_dim]; value_out HOST [n_points];
    grad_out HOST [n_points][n_dim] or NULL.  Used to check device functors against host callbacks. */
@@ -226,8 +275,31 @@ int mcmcb200_target_eval(int target_id, const double* target_data, int64_t targe
    written to tape_out[(n_pre_normals + n_draws*(n_dim+1))].  Exposed so tests can compare it with the oracle. */
 int mcmcb200_mt19937_tape(uint64_t seed, int64_t n_pre_normals, int64_t n_draws, int32_t n_dim, double* tape_out);
 
+/* Host side of MCMCB200_RNG_MT19937_TAPE for mcmc::de: the variates one reference population consumes from
+   std::mt19937_64(seed) (src/de.cpp:92-99,118-190), tape_out[n_pop*n_dim + n_gen*n_pop*(n_dim+3)]. */
+int mcmcb200_de_tape(uint64_t seed, int64_t n_pop, int32_t n_dim, int64_t n_gen, double par_b, double* tape_out);
+
 /* Raw device Philox stream (for tests): normals of draw `draw` for `chain`, then n_unif uniforms. HOST out. */
 int mcmcb200_philox_stream(uint64_t seed, int64_t chain, int64_t draw, int32_t n_dim, int32_t n_unif, double* out);
+
+/* Multi-GPU assembly of draws_out: one process (or host thread) per GPU; rank 0 creates a 128-byte id, every
+   rank calls comm_init with it, then allgather_draws puts each rank's chain-major block local_dev[chains_per_rank[rank]]
+   [n_keep][n_dim] into full_dev[sum chains][n_keep][n_dim] (rank order) on every rank, on `stream`, over NCCL / NVLink.
+   NCCL is bound at run time (libnccl.so.2); MCMCB200_ERR_UNSUPPORTED if it is not installed.  All pointers are DEVICE. */
+int mcmcb200_comm_unique_id(void* id_out, size_t id_bytes);
+int mcmcb200_comm_init(const void* id, size_t id_bytes, int32_t world_size, int32_t rank, int32_t device, void** comm_out);
+int mcmcb200_comm_destroy(void* comm);
+int mcmcb200_allgather_draws(void* comm, const double* local_dev, const int64_t* chains_per_rank, int64_t n_keep, int32_t n_dim,
+                             double* full_dev, void* stream);
+
+/* Page-locked host memory for draws_out (cudaHostAlloc / cudaFreeHost): a D2H copy into it runs at the PCIe rate, a copy
+   into pageable memory at a fraction of it.  NULL on failure. */
+void* mcmcb200_host_alloc(size_t bytes);
+void mcmcb200_host_free(void* p);
+
+/* Measured fp64 FMA peak of the device (TFLOP/s, dependent-free DFMA loop on every SM): the roofline denominator of the
+   compute-bound kernels, taken in the same process (bench.py). */
+int mcmcb200_fp64_peak(int32_t device, double* tflops_out);
 
 const char* mcmcb200_last_error(void);
 int mcmcb200_device_count(void);

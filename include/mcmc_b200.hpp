@@ -159,7 +159,8 @@ struct hmc_settings_t {
     size_t n_leap_steps = 1;
     fp_t step_size = 1.0;
     Mat_t precond_mat;
-    size_t n_accept_draws = 0;  // returned: post-burn-in acceptances (of chain 0 in many-chain calls)
+    size_t n_accept_draws = 0;  // returned: post-burn-in acceptances (many-chain calls: the mean over chains, rounded, so that
+                                // n_accept_draws / n_keep_draws stays the acceptance rate; b200.n_accept_per_chain has every chain)
 };
 struct nuts_settings_t {
     size_t n_burnin_draws = 1E03;
@@ -202,7 +203,7 @@ struct rwmh_settings_t {   // mcmc_structs.hpp:138-149
     size_t n_accept_draws = 0;
 };
 struct b200_settings_t {
-    int rng_mode = MCMCB200_RNG_MT19937_TAPE;  // reference-compatible stream by default (NUTS: Philox, see nuts())
+    int rng_mode = MCMCB200_RNG_MT19937_TAPE;  // reference-compatible stream by default (all samplers, NUTS included)
     int arith = MCMCB200_ARITH_FAST;
     int chol_mode = b200_detail::default_chol;
     int device = -1;
@@ -234,6 +235,20 @@ struct kernel_data {  // what `void* target_data` points to
     size_t n;
 };
 inline registered_kernel device_kernel(const char* name) { return registered_kernel{mcmcb200_target_lookup(name)}; }
+// the registered-functor replacement for rmhmc's tensor_fn (include/mcmc/rmhmc.hpp:51): a metric belongs to a log-kernel
+// (it reads the same data blob); metric_id < 0 = "the kernel's default metric, or settings.b200.rmhmc_metric_id"
+struct registered_metric {
+    int target_id;
+    int metric_id;
+    registered_metric(int t, int m) : target_id(t), metric_id(m) {}
+    registered_metric(registered_kernel k) : target_id(k.target_id), metric_id(-1) {}   // old call shape: rmhmc(x0, kernel, kernel, ...)
+};
+inline registered_metric device_metric(const char* name)
+{
+    int t = -1, m = -1;
+    if (mcmcb200_metric_lookup(name, &t, &m) != MCMCB200_OK) return registered_metric(-1, -1);
+    return registered_metric(t, m);
+}
 namespace b200_detail
 {
 inline std::string& wrapper_error()
@@ -269,32 +284,39 @@ inline void fill_problem(mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, const fp_t
     rng.seed = s.rng_seed_value;
 }
 
-// [C][n_keep][d] chain-major -> per-chain n_keep x d column-major matrices (the reference's Mat_t layout).
-// A 32 x 32-tiled transpose per chain; chains are spread over host threads once the output is large (the whole C2 job is
-// 4.2 GB: a naive single-threaded transpose would cost more than the sampling call itself).
-inline void transpose_chain(const fp_t* in, fp_t* out, size_t n_keep, size_t d)
+// The library hands draws_out back as [chain][j][t] (MCMCB200_LAYOUT_COLMAJOR: transposed on the device), i.e. every chain's
+// block already IS the reference's column-major n_keep x d Mat_t: one chain is copied D2H straight into
+// draws_out; many chains arrive in one page-locked staging buffer (the D2H then runs at the PCIe rate) and are copied —
+// plain memcpy, chains spread over host threads — into the Cube_t's matrices.
+struct pinned_buffer {
+    fp_t* p = nullptr;
+    size_t n = 0;
+    bool pinned = false;
+    std::vector<fp_t> fallback;
+    explicit pinned_buffer(size_t count) : n(count)
+    {
+        if (count * sizeof(fp_t) >= (size_t(1) << 24)) p = static_cast<fp_t*>(mcmcb200_host_alloc(count * sizeof(fp_t)));
+        pinned = p != nullptr;
+        if (!p) { fallback.resize(count); p = fallback.data(); }
+    }
+    ~pinned_buffer() { if (pinned) mcmcb200_host_free(p); }
+    pinned_buffer(const pinned_buffer&) = delete;
+    pinned_buffer& operator=(const pinned_buffer&) = delete;
+};
+inline void unpack(const fp_t* buf, size_t n_chains, size_t n_keep, size_t d, Cube_t& cube)
 {
-    const size_t B = 32;
-    for (size_t t0 = 0; t0 < n_keep; t0 += B)
-        for (size_t j0 = 0; j0 < d; j0 += B) {
-            const size_t t1 = t0 + B < n_keep ? t0 + B : n_keep, j1 = j0 + B < d ? j0 + B : d;
-            for (size_t j = j0; j < j1; ++j)
-                for (size_t t = t0; t < t1; ++t) out[j * n_keep + t] = in[t * d + j];
-        }
-}
-inline void unpack(const std::vector<fp_t>& buf, size_t n_chains, size_t n_keep, size_t d, Mat_t* single, Cube_t* cube)
-{
-    if (cube) cube->set_n_mat(n_chains);
-    for (size_t c = 0; c < n_chains; ++c) mresize(cube ? cube->mat(c) : *single, n_keep, d);
+    cube.set_n_mat(n_chains);
     auto work = [&](size_t c_begin, size_t c_end) {
-        for (size_t c = c_begin; c < c_end; ++c)
-            transpose_chain(buf.data() + c * n_keep * d, mdata(cube ? cube->mat(c) : *single), n_keep, d);
+        for (size_t c = c_begin; c < c_end; ++c) {
+            mresize(cube.mat(c), n_keep, d);   // allocation and first touch happen on the copying thread
+            if (n_keep * d) std::memcpy(mdata(cube.mat(c)), buf + c * n_keep * d, n_keep * d * sizeof(fp_t));
+        }
     };
     size_t n_thr = 1;
     if (n_chains > 1 && n_chains * n_keep * d >= (size_t(1) << 22)) {
         n_thr = std::thread::hardware_concurrency();
         if (n_thr == 0) n_thr = 1;
-        if (n_thr > 16) n_thr = 16;
+        if (n_thr > 32) n_thr = 32;
         if (n_thr > n_chains) n_thr = n_chains;
     }
     if (n_thr <= 1) { work(0, n_chains); return; }
@@ -325,12 +347,16 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
         pr.lower_bounds = cdata(s.lower_bounds);
         pr.upper_bounds = cdata(s.upper_bounds);
     }
-    std::vector<fp_t> buf(n_chains * n_keep * d);
+    // one chain: the result lands directly in draws_out; many chains: in a page-locked staging buffer
+    if (single) mresize(*single, n_keep, d);
+    pinned_buffer stage(cube ? n_chains * n_keep * d : 0);
+    fp_t* const buf = cube ? stage.p : mdata(*single);
     std::vector<int64_t> acc(n_chains, 0);
     mcmcb200_output_t out;
     std::memset(&out, 0, sizeof(out));
-    out.draws_out = buf.data();
+    out.draws_out = buf;
     out.draws_mem = MCMCB200_MEM_HOST;
+    out.draws_layout = MCMCB200_LAYOUT_COLMAJOR;
     out.n_accept_draws = acc.data();
     const size_t n_dev = s.b200.devices.size();
     if (n_dev <= 1 || n_chains < 2) {
@@ -351,7 +377,7 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
                 p2.initial_vals = pr.initial_vals + c0 * d;
                 p2.chain_offset = pr.chain_offset + static_cast<int64_t>(c0);
                 p2.device = s.b200.devices[g];
-                o2.draws_out = buf.data() + c0 * n_keep * d;
+                o2.draws_out = buf + c0 * n_keep * d;
                 o2.n_accept_draws = acc.data() + c0;
                 rcs[g] = fn(p2, rng, o2, s);
                 if (rcs[g] != MCMCB200_OK) errs[g] = mcmcb200_last_error();   // the C ABI's error text is per thread
@@ -364,9 +390,11 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
                 return false;
             }
     }
-    unpack(buf, n_chains, n_keep, d, single, cube);
+    if (cube) unpack(buf, n_chains, n_keep, d, *cube);
     if (sp) {  // written back only if a settings object was passed (src/hmc.cpp:220-222)
-        *n_accept_field = static_cast<size_t>(acc[0]);
+        long double tot = 0;
+        for (size_t c = 0; c < n_chains; ++c) tot += static_cast<long double>(acc[c]);
+        *n_accept_field = static_cast<size_t>(tot / static_cast<long double>(n_chains) + 0.5L);   // one chain: its own count
         s.b200.n_accept_per_chain.assign(acc.begin(), acc.end());
     }
     return true;
@@ -505,9 +533,10 @@ inline bool rwmh(const Mat_t& initial_vals, registered_kernel target_log_kernel,
 }
 
 // ================================================= NUTS ======================================================
-// NUTS consumes a data-dependent number of uniforms per draw, so the reference's mt19937 stream cannot be replayed
-// from a precomputed tape: with rng_mode == MCMCB200_RNG_MT19937_TAPE the wrapper switches to in-kernel Philox
-// (seeded by rng_seed_value) instead of failing.
+// NUTS consumes a data-dependent number of uniforms per draw, so the reference's mt19937 stream cannot be laid out in
+// advance: with rng_mode == MCMCB200_RNG_MT19937_TAPE (the drop-in default) the library drives the kernel draw by draw
+// and feeds it the reference stream with a look-ahead pool of uniforms (engine.cu, nuts_run_impl) — same draws as the
+// reference, one kernel launch per draw.  MCMCB200_RNG_PHILOX runs the whole chain in one launch.
 namespace internal
 {
 inline bool nuts_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
@@ -515,8 +544,7 @@ inline bool nuts_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kern
 {
     algo_settings_t local;
     algo_settings_t& s = sp ? *sp : local;
-    const int rng_mode = (s.b200.rng_mode == MCMCB200_RNG_MT19937_TAPE) ? MCMCB200_RNG_PHILOX : s.b200.rng_mode;
-    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.nuts_settings.n_keep_draws, rng_mode, single, cube,
+    return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.nuts_settings.n_keep_draws, s.b200.rng_mode, single, cube,
                             &s.nuts_settings.n_accept_draws,
                             [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
                                 mcmcb200_nuts_settings_t n;
@@ -557,16 +585,26 @@ inline bool nuts(const Mat_t& initial_vals, registered_kernel target_log_kernel,
 }
 
 // ================================================= RM-HMC ====================================================
-// The reference takes tensor_fn and tensor_data as separate arguments (include/mcmc/rmhmc.hpp:47-86); here the
-// metric is registered together with the kernel, so `tensor_fn` must be the same registered_kernel and tensor_data
-// is ignored.
+// The reference takes tensor_fn and tensor_data as separate arguments (include/mcmc/rmhmc.hpp:47-86).  Here tensor_fn
+// names a REGISTERED metric (mcmc::device_metric("funnel_softabs"), ...), which must belong to the log-kernel, and it
+// reads the log-kernel's data blob: tensor_data must be null or the same pointer as target_data.  Anything else makes the
+// call return false with mcmc::last_error() set — nothing is ignored.
 namespace internal
 {
-inline bool rmhmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, Mat_t* single,
-                       Cube_t* cube)
+inline bool rmhmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, registered_metric tensor_fn, void* target_data,
+                       void* tensor_data, algo_settings_t* sp, Mat_t* single, Cube_t* cube)
 {
     algo_settings_t local;
     algo_settings_t& s = sp ? *sp : local;
+    if (tensor_fn.target_id != k.target_id) {
+        b200_detail::wrapper_error() = "mcmc_b200: rmhmc tensor_fn must be a metric registered for the same log-kernel (see mcmc::device_metric)";
+        return false;
+    }
+    if (tensor_data != nullptr && tensor_data != target_data) {
+        b200_detail::wrapper_error() = "mcmc_b200: rmhmc tensor_data must be null or equal to target_data (registered metrics read the kernel's data blob)";
+        return false;
+    }
+    const int metric_id = tensor_fn.metric_id >= 0 ? tensor_fn.metric_id : s.b200.rmhmc_metric_id;
     return b200_detail::run(x0, d, n_chains, k, target_data, sp, s.rmhmc_settings.n_keep_draws, s.b200.rng_mode, single, cube,
                             &s.rmhmc_settings.n_accept_draws,
                             [&](mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, mcmcb200_output_t& out, algo_settings_t& st) {
@@ -579,29 +617,29 @@ inline bool rmhmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_ker
                                 r.n_fp_steps = static_cast<int64_t>(static_cast<uint_t>(st.rmhmc_settings.n_fp_steps));
                                 r.chol_mode = st.b200.chol_mode;
                                 r.arith = st.b200.arith;
-                                r.metric_id = st.b200.rmhmc_metric_id;
+                                r.metric_id = metric_id;
                                 return mcmcb200_rmhmc_run(&pr, &rng, &r, &out);
                             });
 }
 }  // namespace internal
 
-inline bool rmhmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, registered_kernel /*tensor_fn*/, Mat_t& draws_out,
-                  void* target_data, void* /*tensor_data*/)
+inline bool rmhmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, registered_metric tensor_fn, Mat_t& draws_out,
+                  void* target_data, void* tensor_data)
 {
-    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr,
-                                &draws_out, nullptr);
+    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, tensor_fn, target_data,
+                                tensor_data, nullptr, &draws_out, nullptr);
 }
-inline bool rmhmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, registered_kernel /*tensor_fn*/, Mat_t& draws_out,
-                  void* target_data, void* /*tensor_data*/, algo_settings_t& settings)
+inline bool rmhmc(const ColVec_t& initial_vals, registered_kernel target_log_kernel, registered_metric tensor_fn, Mat_t& draws_out,
+                  void* target_data, void* tensor_data, algo_settings_t& settings)
 {
-    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data,
-                                &settings, &draws_out, nullptr);
+    return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, tensor_fn, target_data,
+                                tensor_data, &settings, &draws_out, nullptr);
 }
-inline bool rmhmc(const Mat_t& initial_vals, registered_kernel target_log_kernel, registered_kernel /*tensor_fn*/, Cube_t& draws_out,
-                  void* target_data, void* /*tensor_data*/, algo_settings_t& settings)
+inline bool rmhmc(const Mat_t& initial_vals, registered_kernel target_log_kernel, registered_metric tensor_fn, Cube_t& draws_out,
+                  void* target_data, void* tensor_data, algo_settings_t& settings)
 {
     return internal::rmhmc_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
-                                target_log_kernel, target_data, &settings, nullptr, &draws_out);
+                                target_log_kernel, tensor_fn, target_data, tensor_data, &settings, nullptr, &draws_out);
 }
 
 }  // namespace mcmc

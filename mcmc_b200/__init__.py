@@ -5,4 +5,4 @@ The product is ``libmcmc_b200.so`` (hand-written sm_100a CUDA behind the C ABI o
 ``mcmc_b200.api`` is a thin ctypes binding used by the tests and ``bench.py``.
 """
 from . import api  # noqa: F401
-from .api import McmcB200Error, hmc, mala, nuts, rmhmc, rwmh  # noqa: F401
+from .api import McmcB200Error, de, hmc, mala, nuts, rmhmc, rwmh  # noqa: F401

@@ -20,6 +20,7 @@ TARGET_ISO_GAUSS, TARGET_DIAG_GAUSS, TARGET_DENSE_GAUSS, TARGET_LINREG, TARGET_N
 RNG_PHILOX, RNG_MT19937_TAPE, RNG_USER_TAPE = range(3)
 MEM_HOST, MEM_DEVICE = 0, 1
 ARITH_FAST, ARITH_STRICT = 0, 1
+LAYOUT_CHAIN_ROWS, LAYOUT_COLMAJOR = 0, 1
 CHOL_LOWER, CHOL_EIGEN_LLT = 0, 1
 
 c_i32, c_i64, c_u64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.c_double, ctypes.c_void_p
@@ -62,8 +63,13 @@ class RmhmcSettings(ctypes.Structure):
                 ("n_fp_steps", c_i64), ("chol_mode", c_i32), ("arith", c_i32), ("metric_id", c_i32), ("reserved0", c_i32)]
 
 
+class DeSettings(ctypes.Structure):
+    _fields_ = [("n_burnin_draws", c_i64), ("n_keep_draws", c_i64), ("n_pop", c_i64), ("jumps", c_i32), ("arith", c_i32),
+                ("par_b", c_dbl), ("par_gamma_jump", c_dbl), ("initial_lb", c_vp), ("initial_ub", c_vp)]
+
+
 class Output(ctypes.Structure):
-    _fields_ = [("draws_out", c_vp), ("draws_mem", c_i32), ("reserved0", c_i32), ("n_accept_draws", c_vp),
+    _fields_ = [("draws_out", c_vp), ("draws_mem", c_i32), ("draws_layout", c_i32), ("n_accept_draws", c_vp),
                 ("logp_out", c_vp), ("step_size_out", c_vp), ("n_leapfrog_out", c_vp), ("kernel_ms", ctypes.c_float),
                 ("kernel_launches", c_i32)]
 
@@ -92,10 +98,32 @@ def load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.mcmcb200_last_error.restype = ctypes.c_char_p
     lib.mcmcb200_target_data_len.restype = c_i64
-    for f in ("hmc", "mala", "nuts", "rmhmc", "rwmh"):
+    lib.mcmcb200_register_target.restype = ctypes.c_int
+    for f in ("hmc", "mala", "nuts", "rmhmc", "rwmh", "de"):
         getattr(lib, "mcmcb200_%s_run" % f).restype = ctypes.c_int
     _lib = lib
     return lib
+
+
+_user_libs = {}
+
+
+def load_user_library(path):
+    """dlopen a USER's target library (built per include/mcmc_b200_device.cuh); its static initialiser registers the
+    target with libmcmc_b200.so, after which target_id("<name>") resolves it.  libmcmc_b200.so is loaded first, globally,
+    so the user library binds to this very copy."""
+    path = os.path.abspath(path)
+    if path not in _user_libs:
+        ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        load()
+        _user_libs[path] = ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+    return _user_libs[path]
+
+
+def metric_lookup(name):
+    t, m = ctypes.c_int(-1), ctypes.c_int(-1)
+    _check(load().mcmcb200_metric_lookup(name.encode(), ctypes.byref(t), ctypes.byref(m)))
+    return t.value, m.value
 
 
 def _check(rc):
@@ -128,7 +156,7 @@ class _Run:
 
     def __init__(self, sampler, initial_vals, target, target_data, n_keep, n_burnin, rng_mode, seed, chain_offset,
                  device, stream, tape, draws_out, want_logp, initial_dev_ptr=None, n_chains=None, n_dim=None,
-                 draws_dev_ptr=None, lower_bounds=None, upper_bounds=None):
+                 draws_dev_ptr=None, lower_bounds=None, upper_bounds=None, layout=0):
         lib = load()
         self.lib = lib
         self.keep = []
@@ -171,13 +199,13 @@ class _Run:
         if draws_dev_ptr is not None:
             self.draws = None
             self.logp = None
-            self.out = Output(c_vp(draws_dev_ptr), MEM_DEVICE, 0, _np_ptr(self.n_accept), None, _np_ptr(self.step_out),
+            self.out = Output(c_vp(draws_dev_ptr), MEM_DEVICE, int(layout), _np_ptr(self.n_accept), None, _np_ptr(self.step_out),
                               _np_ptr(self.nlf_out), 0.0, 0)
         else:
             self.draws = draws_out if draws_out is not None else np.empty((C, self.n_keep, d))
             assert self.draws.dtype == np.float64 and self.draws.flags.c_contiguous and self.draws.size == C * self.n_keep * d
             self.logp = np.empty((C, self.n_keep)) if want_logp else None
-            self.out = Output(_np_ptr(self.draws), MEM_HOST, 0, _np_ptr(self.n_accept), _np_ptr(self.logp),
+            self.out = Output(_np_ptr(self.draws), MEM_HOST, int(layout), _np_ptr(self.n_accept), _np_ptr(self.logp),
                               _np_ptr(self.step_out), _np_ptr(self.nlf_out), 0.0, 0)
 
     def result(self):
@@ -190,7 +218,7 @@ class _Run:
 
 _COMMON = dict(target_data=None, n_burnin=1000, n_keep=1000, rng_mode=RNG_PHILOX, seed=0, chain_offset=0, device=-1,
                stream=None, tape=None, draws_out=None, want_logp=False, initial_dev_ptr=None, n_chains=None, n_dim=None,
-               draws_dev_ptr=None, lower_bounds=None, upper_bounds=None)
+               draws_dev_ptr=None, lower_bounds=None, upper_bounds=None, layout=0)
 
 
 def _split(kw):
@@ -259,6 +287,38 @@ def rmhmc(initial_vals, target, n_leap_steps=1, step_size=1.0, n_fp_steps=5, cho
     return run.result()
 
 
+def de(initial_vals, target, n_pop=100, jumps=False, par_b=1e-4, par_gamma_jump=2.0, initial_lb=None, initial_ub=None,
+       arith=ARITH_FAST, **kw):
+    """Many-population mcmc::de (src/de.cpp:30-271).  initial_vals: [n_populations][n_dim]; result draws:
+    [n_populations][n_keep][n_pop][n_dim] (per population the reference's Cube_t, row-major matrices)."""
+    c = _split(kw)
+    assert not kw, kw
+    x0 = np.ascontiguousarray(initial_vals, dtype=np.float64)
+    if x0.ndim == 1:
+        x0 = x0[None, :]
+    P, d = x0.shape
+    n_keep = int(c["n_keep"])
+    if c["draws_out"] is None:
+        c["draws_out"] = np.empty((P, n_keep * int(n_pop), d))
+    c2 = dict(c)
+    c2["n_keep"] = n_keep * int(n_pop)   # _Run sizes the output per "kept draw"; a population's kept draw is n_pop rows
+    run = _Run("de", x0, target, **c2)
+    lo = None if initial_lb is None else np.ascontiguousarray(initial_lb, dtype=np.float64)
+    hi = None if initial_ub is None else np.ascontiguousarray(initial_ub, dtype=np.float64)
+    st = DeSettings(c["n_burnin"], n_keep, int(n_pop), 1 if jumps else 0, arith, float(par_b), float(par_gamma_jump), _np_ptr(lo), _np_ptr(hi))
+    _check(run.lib.mcmcb200_de_run(ctypes.byref(run.problem), ctypes.byref(run.rng), ctypes.byref(st), ctypes.byref(run.out)))
+    r = run.result()
+    if r["draws"] is not None:
+        r["draws"] = r["draws"].reshape(P, n_keep, int(n_pop), d)
+    return r
+
+
+def de_tape(seed, n_pop, n_dim, n_gen, par_b):
+    out = np.empty(n_pop * n_dim + n_gen * n_pop * (n_dim + 3))
+    _check(load().mcmcb200_de_tape(c_u64(seed), c_i64(n_pop), n_dim, c_i64(n_gen), c_dbl(par_b), _np_ptr(out)))
+    return out
+
+
 def target_eval(target, target_data, x, want_grad=True, arith=ARITH_FAST):
     lib = load()
     x = np.ascontiguousarray(x, dtype=np.float64)
@@ -309,6 +369,38 @@ def summarize(draws=None, draws_dev_ptr=None, n_chains=None, n_keep=None, n_dim=
     return r
 
 
+class Comm:
+    """NCCL communicator owned by the library (include/mcmc_b200.h, csrc/gather.cu).  `exchange_id(id_bytes_or_None)` is the
+    caller's out-of-band broadcast of rank 0's 128-byte id (bench.py uses torch.distributed for that plumbing)."""
+
+    def __init__(self, world_size, rank, device, exchange_id):
+        lib = load()
+        buf = (ctypes.c_ubyte * 128)()
+        if rank == 0:
+            _check(lib.mcmcb200_comm_unique_id(buf, ctypes.c_size_t(128)))
+        raw = exchange_id(bytes(buf) if rank == 0 else None)
+        idb = (ctypes.c_ubyte * 128).from_buffer_copy(raw)
+        self.h = c_vp()
+        self.world, self.rank = int(world_size), int(rank)
+        _check(lib.mcmcb200_comm_init(idb, ctypes.c_size_t(128), self.world, self.rank, int(device), ctypes.byref(self.h)))
+
+    def allgather_draws(self, local_dev_ptr, chains_per_rank, n_keep, n_dim, full_dev_ptr, stream=None):
+        cpr = (c_i64 * self.world)(*[int(c) for c in chains_per_rank])
+        _check(load().mcmcb200_allgather_draws(self.h, c_vp(local_dev_ptr), cpr, c_i64(n_keep), int(n_dim), c_vp(full_dev_ptr),
+                                               c_vp(stream) if stream else None))
+
+    def destroy(self):
+        if self.h:
+            load().mcmcb200_comm_destroy(self.h)
+            self.h = c_vp()
+
+
+def fp64_peak(device=-1):
+    out = ctypes.c_double(0.0)
+    _check(load().mcmcb200_fp64_peak(int(device), ctypes.byref(out)))
+    return out.value
+
+
 def device_count():
     return load().mcmcb200_device_count()
 
@@ -318,5 +410,7 @@ EXPORTED_SYMBOLS = [
     "mcmcb200_rmhmc_settings_default", "mcmcb200_hmc_run", "mcmcb200_mala_run", "mcmcb200_nuts_run",
     "mcmcb200_rmhmc_run", "mcmcb200_rwmh_settings_default", "mcmcb200_rwmh_run", "mcmcb200_target_lookup", "mcmcb200_target_data_len", "mcmcb200_target_eval",
     "mcmcb200_mt19937_tape", "mcmcb200_philox_stream", "mcmcb200_last_error", "mcmcb200_device_count",
-    "mcmcb200_release_workspace", "mcmcb200_summarize_draws",
+    "mcmcb200_release_workspace", "mcmcb200_summarize_draws", "mcmcb200_de_settings_default", "mcmcb200_de_run", "mcmcb200_de_tape",
+    "mcmcb200_metric_lookup", "mcmcb200_register_target", "mcmcb200_allgather_draws", "mcmcb200_comm_unique_id", "mcmcb200_comm_init",
+    "mcmcb200_comm_destroy", "mcmcb200_fp64_peak", "mcmcb200_host_alloc", "mcmcb200_host_free",
 ]

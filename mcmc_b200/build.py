@@ -7,6 +7,7 @@ whatever libcudart a host process already has loaded.
 """
 import hashlib
 import os
+import re
 import shutil
 import subprocess
 import sys
@@ -17,9 +18,12 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcmc_b200.so")
 
-CU_SOURCES = ["engine.cu", "dispatch.cu", "hmc_wide.cu", "mala_wide.cu", "rmhmc.cu", "util_kernels.cu", "summary.cu", "rmhmc_general.cu"]
+CU_SOURCES = ["engine.cu", "dispatch.cu", "hmc_wide.cu", "mala_wide.cu", "rmhmc.cu", "util_kernels.cu", "summary.cu", "rmhmc_general.cu",
+              "hmc_batched.cu", "gather.cu", "transpose.cu", "rmhmc_cta.cu"]
 # compiled once per registered target (-DMCMCB200_TARGET_SLICE=k), so the big template fan-out builds in parallel
-SLICED_SOURCES = ["hmc.cu", "nuts.cu", "mala.cu", "rwmh.cu"]
+SLICED_SOURCES = ["nuts.cu", "hmc.cu", "mala.cu", "rwmh.cu", "de.cu"]
+# translation units that take longest (dense targets in the NUTS kernel: ~9 min each) start first
+SLOW_FIRST = ["nuts.cu.t2.o", "nuts.cu.t3.o", "hmc.cu.t2.o", "hmc.cu.t3.o"]
 N_TARGETS = 6
 CPP_SOURCES = ["host_tape.cpp", "host_linalg.cpp"]
 
@@ -28,6 +32,8 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3",
     "--expt-relaxed-constexpr",
+    "--compress-mode=size",   # the template fan-out is ~190 MB of SASS otherwise; the .so travels to every GPU box
+    "-diag-suppress", "128",
 ]
 
 
@@ -52,10 +58,23 @@ def _stamp(paths, extra):
     return h.hexdigest()
 
 
-def _headers():
-    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    hs.append(os.path.join(os.path.dirname(HERE), "include", "mcmc_b200.h"))
-    return hs
+_INC = re.compile(r'^\s*#\s*include\s+"([^"]+)"', re.M)
+
+
+def _deps(path, seen=None):
+    """The source and every project header it includes, transitively (so that touching one header only rebuilds its users)."""
+    seen = set() if seen is None else seen
+    path = os.path.normpath(path)
+    if path in seen or not os.path.exists(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        for inc in _INC.findall(f.read()):
+            for base in (os.path.dirname(path), os.path.join(os.path.dirname(HERE), "include"), CSRC):
+                if os.path.exists(os.path.join(base, inc)):
+                    _deps(os.path.join(base, inc), seen)
+                    break
+    return seen
 
 
 def build(verbose=False, force=False):
@@ -63,13 +82,13 @@ def build(verbose=False, force=False):
     the default builds every registered target and is what __graft_entry__.build() and the tests use."""
     os.makedirs(OBJ, exist_ok=True)
     nvcc = _nvcc()
-    headers = _headers()
     fast = os.environ.get("MCMCB200_FAST_BUILD") == "1"
     units = []  # (source, object name, extra flags); the slowest translation units first
     for src in SLICED_SOURCES:
         for k in ([0] if fast else range(N_TARGETS)):
             units.append((src, "%s.t%d.o" % (src, k), ["-DMCMCB200_TARGET_SLICE=%d" % k]))
-    units += [(src, src + ".o", []) for src in CU_SOURCES + CPP_SOURCES]
+    units += [(src, src + ".o", []) for src in CU_SOURCES + CPP_SOURCES if os.path.exists(os.path.join(CSRC, src))]
+    units.sort(key=lambda u: SLOW_FIRST.index(u[1]) if u[1] in SLOW_FIRST else len(SLOW_FIRST))
     base = NVCC_FLAGS + (["-DMCMCB200_FAST_BUILD"] if fast else [])
     jobs, objs = [], []
     for src, oname, extra in units:
@@ -78,7 +97,7 @@ def build(verbose=False, force=False):
         objs.append(obj)
         flags = base + extra
         stamp_file = obj + ".stamp"
-        stamp = _stamp([path] + headers, flags)
+        stamp = _stamp(sorted(_deps(path)), flags)
         if not force and os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
             continue
         cmd = [nvcc, "-ccbin", _host_cxx()] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
@@ -100,11 +119,38 @@ def build(verbose=False, force=False):
 
     if jobs or not os.path.exists(LIB):
         cmd = [nvcc, "-ccbin", _host_cxx(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static",
-               "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-lpthread"]
+               "-Xcompiler", "-fPIC", "-o", LIB] + objs + ["-lpthread", "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    build_user_example(verbose=verbose, force=force)
     return LIB
+
+
+USER_EXAMPLE_SRC = os.path.join(os.path.dirname(HERE), "examples", "user_target", "normal_raw.cu")
+USER_EXAMPLE_LIB = os.path.join(os.path.dirname(HERE), "examples", "user_target", "libnormal_raw.so")
+
+
+def build_user_example(verbose=False, force=False):
+    """examples/user_target/normal_raw.cu -> libnormal_raw.so: a USER-defined target built the way include/mcmc_b200_device.cuh
+    documents (its own shared library next to libmcmc_b200.so; the library itself is not rebuilt)."""
+    if not os.path.exists(USER_EXAMPLE_SRC):
+        return None
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--expt-relaxed-constexpr", "--compress-mode=size",
+             "-diag-suppress", "128", "-shared", "-cudart", "static", "-Xcompiler", "-fPIC", "-I" + inc, "-I" + CSRC]
+    stamp_file = USER_EXAMPLE_LIB + ".stamp"
+    stamp = _stamp(sorted(_deps(USER_EXAMPLE_SRC) | _deps(os.path.join(inc, "mcmc_b200_register.cuh"))), flags)
+    if not force and os.path.exists(USER_EXAMPLE_LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return USER_EXAMPLE_LIB
+    cmd = [_nvcc(), "-ccbin", _host_cxx()] + flags + [USER_EXAMPLE_SRC, "-L" + HERE, "-lmcmc_b200", "-Xlinker", "-rpath=$ORIGIN/../../mcmc_b200",
+                                                       "-o", USER_EXAMPLE_LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("user-target example failed to build:\n%s\n%s" % (r.stdout[-4000:], r.stderr[-8000:]))
+    with open(stamp_file, "w") as f:
+        f.write(stamp)
+    return USER_EXAMPLE_LIB
 
 
 if __name__ == "__main__":

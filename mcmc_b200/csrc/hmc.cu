@@ -57,7 +57,7 @@ __device__ __forceinline__ void kick_full(double (&p)[EPL], const double (&g)[EP
 constexpr int hmc_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 4 : 2); }
 
 // FT ("full tile"): n_dim == 32*EPL and 16-byte aligned rows, so no padding predicates anywhere.
-// BOX: box constraints (vals_bound), see box.cuh; available with M = I on the generic (runtime-L) kernels.
+// BOX: box constraints (vals_bound), see box.cuh; on the generic (runtime-L) kernels, with or without a dense mass matrix.
 template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, bool BOX = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_kernel(const __grid_constant__ HmcLaunch a)
 {
@@ -173,10 +173,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
         } else {
             // dH = (U0 + K0) - (U1 + K1) in one butterfly.  u < exp(min(0.01, dH)) holds trivially for dH >= 0 (u < 1)
             // and whenever u < 1 + dH (<= exp(dH)), so exp() is evaluated only in the thin band 1 + dH <= u: the
-            // decision is always that of the exact test.  A non-finite energy rejects (src/hmc.cpp:180-182).
+            // decision is always that of the exact test.  A non-finite proposal energy rejects (dH = -inf or NaN,
+            // src/hmc.cpp:180-182); a chain that starts where log pi = -inf (U0 = +inf, dH = +inf) accepts its first
+            // finite proposal like the reference (min(0.01, +inf) = 0.01).  Same rule in every FAST kernel.
             const double dH = warp_sum<false>((U + K0) - (U1 + K1));
-            acc = false;
-            if (fabs(dH) <= 1.7976931348623157e308) acc = (u < 1.0 + dH) ? true : (u < exp(dH));
+            acc = u < 1.0 + dH;
+            if (!acc) acc = (fabs(dH) <= 1.7976931348623157e308) && (u < exp(dH));
         }
         if (acc) {
             U = U1;
@@ -379,14 +381,10 @@ template <class T, int EPL, int LS> static int launch_pipe(const HmcLaunch& a)
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch& a)
 {
-    if (a.lb != nullptr) {   // box constraints: generic kernels, M = I
-        if (DENSE_M) {
-            set_error("hmc: vals_bound together with precond_mat is not supported on the device path");
-            return MCMCB200_ERR_UNSUPPORTED;
-        }
+    if (a.lb != nullptr) {   // box constraints: generic kernels; the kick uses J o grad, the drift (eps M^-1) p (src/hmc.cpp:107-122,171)
         if (a.rng.mode == RNG_PHILOX)
-            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, false, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, false, true>(a);
-        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, false, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, false, true>(a);
+            return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, false, true>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, false, true>(a);
+        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE, false, true>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE, false, true>(a);
     }
     if (a.rng.mode == RNG_PHILOX) {
         // the unpredicated full-tile kernels exist for the production configuration: Philox, identity mass
@@ -410,10 +408,10 @@ template <class T, int EPL> static int launch_epl(const HmcLaunch& a)
 template <class T> static int launch_target(const HmcLaunch& a)
 {
     switch (epl_for_dim(a.d)) {
-    case 2: return launch_epl<T, 2>(a);
-    case 4: return launch_epl<T, 4>(a);
-    case 8: return launch_epl<T, 8>(a);
-    case 16: return launch_epl<T, 16>(a);
+    MCMCB200_EPL_CASE(2, (launch_epl<T, 2>(a)))
+    MCMCB200_EPL_CASE(4, (launch_epl<T, 4>(a)))
+    MCMCB200_EPL_CASE(8, (launch_epl<T, 8>(a)))
+    MCMCB200_EPL_CASE(16, (launch_epl<T, 16>(a)))
     default:
         set_error("hmc: n_dim=%d exceeds the register-resident kernels (max %d)", a.d, 32 * MAX_EPL);
         return MCMCB200_ERR_UNSUPPORTED;

@@ -112,8 +112,8 @@ __global__ void __launch_bounds__(128) hmc_wide_kernel(const __grid_constant__ H
             const double part = chain_sum(K0 - (L > 0 ? U1 : 0.0) - K1);
             if (RNGM == RNG_PHILOX) u = u_sh;
             const double dH = (L > 0) ? (U + part) : part;   // with L == 0 the position did not move: U1 = U
-            acc = false;
-            if (fabs(dH) <= 1.7976931348623157e308) acc = (u < 1.0 + dH) ? true : (u < exp(dH));
+            acc = u < 1.0 + dH;   // same rule as hmc.cu (dH = +inf accepts, NaN / -inf reject)
+            if (!acc) acc = (fabs(dH) <= 1.7976931348623157e308) && (u < exp(dH));
             const double U1r = chain_sum(L > 0 ? U1 : 0.0);
             if (acc && L > 0) U = U1r;
         }

@@ -25,8 +25,10 @@ namespace mcmcb200
 
 constexpr int mala_min_blocks(int epl) { return epl <= 4 ? 7 : (epl == 8 ? 3 : 1); }
 
-// BOX: box constraints with M = I (src/mala.cpp:104-118,152-157, mala.ipp:50-56): drift eps^2 J grad / 2, noise
-// eps sqrt(J) z, and BOTH proposal densities use the covariance eps^2 J(proposal).
+// BOX: box constraints (src/mala.cpp:104-118,152-157, mala.ipp:50-56): drift ((eps^2 J) M) grad / 2, noise
+// ((eps sqrt(J)) sqrtM) z, and BOTH proposal densities use the covariance eps^2 J(proposal) M (not symmetric
+// for a dense M — the reference's dmvnorm takes it as it is, and so does the cancelled form: Sigma^-1 r = M^-1 (r / (J eps^2)),
+// the two log-dets are the same number).  With DENSE_M the launch's SigInv_cm holds M^-1 (not (eps^2 M)^-1).
 template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) mala_kernel(const __grid_constant__ MalaLaunch a)
 {
@@ -52,7 +54,13 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
     if (BOX) bx.load(a.lb, a.ub, d, lane);
     // mean = v + ((eps^2 M) g)/2 ; bounded (M = I): v + ((J eps^2) g)/2
     auto mala_mean = [&](const double (&v)[EPL], const double (&g)[EPL], const double (&Jv)[EPL], double (&out)[EPL]) {
-        if (BOX) {
+        if (BOX && DENSE_M) {
+            double t[EPL];
+            stage_vec<EPL>(mscr, d, lane, g);
+            gemv_cm_rowscaled<EPL, STRICT>(a.M_cm, d, lane, mscr, Jv, e2, t);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) out[k] = A::add(v[k], A::mul(t[k], 0.5));
+        } else if (BOX) {
 #pragma unroll
             for (int k = 0; k < EPL; ++k) out[k] = A::add(v[k], A::mul(A::mul(A::mul(Jv[k], e2), g[k]), 0.5));
         } else if (DENSE_M) {
@@ -72,6 +80,12 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
             double t[EPL];
 #pragma unroll
             for (int k = 0; k < EPL; ++k) t[k] = r[k] / A::mul(Jp[k], e2);
+            if (DENSE_M) {
+                double s2[EPL];
+                stage_vec<EPL>(mscr, d, lane, t);
+                gemv_cm<EPL, STRICT>(a.SigInv_cm, d, lane, mscr, 1.0, s2);   // M^-1 (r / (J eps^2))
+                return lane_dot<EPL, STRICT>(r, s2);
+            }
             return lane_dot<EPL, STRICT>(r, t);
         }
         if (DENSE_M) {
@@ -103,7 +117,15 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
 
     for (int t = 0; t < n_total; ++t) {
         rng.template normals<EPL, false>(a.rng, t, d, lane, rng_tab, r);  // z
-        if (BOX) {   // mean + ((eps chol(J)) sqrtM) z with chol of the diagonal J = sqrt(J_ii), sqrtM = I
+        if (BOX && DENSE_M) {   // mean + ((eps chol(J)) sqrtM) z: rows of sqrtM scaled by sqrt(J_ii), then by eps
+            double tz[EPL], sj[EPL];
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) sj[k] = sqrt(Jx[k]);
+            stage_vec<EPL>(mscr, d, lane, r);
+            gemv_cm_rowscaled<EPL, STRICT>(a.S_cm, d, lane, mscr, sj, eps, tz);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) y[k] = A::add(mx[k], tz[k]);
+        } else if (BOX) {   // mean + ((eps chol(J)) sqrtM) z with chol of the diagonal J = sqrt(J_ii), sqrtM = I
 #pragma unroll
             for (int k = 0; k < EPL; ++k) y[k] = A::mad(A::mul(sqrt(Jx[k]), eps), r[k], mx[k]);
         } else if (DENSE_M) {
@@ -143,8 +165,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, mala_min_blocks(EPL)) ma
         } else {
             const double qs = (DENSE_M || BOX) ? 1.0 : 1.0 / e2;
             const double dl = warp_sum<false>((LP1 - LP) - 0.5 * qs * (q1 - q2));
-            acc = false;
-            if (fabs(dl) <= 1.7976931348623157e308) acc = (u < 1.0 + dl) ? true : (u < exp(dl));
+            acc = u < 1.0 + dl;   // dl = +inf (chain started where log pi = -inf) accepts like the reference; NaN / -inf reject
+            if (!acc) acc = (fabs(dl) <= 1.7976931348623157e308) && (u < exp(dl));
         }
         if (acc) {
             LP = LP1;
@@ -189,14 +211,10 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const MalaLaunch& a)
 {
-    if (a.lb != nullptr) {   // box constraints: M = I only (a dense M would need an O(d^3) factorisation of J M per draw)
-        if (DENSE_M) {
-            set_error("mala: vals_bound together with precond_mat is not supported on the device path");
-            return MCMCB200_ERR_UNSUPPORTED;
-        }
+    if (a.lb != nullptr) {   // box constraints, with or without a dense precond_mat
         if (a.rng.mode == RNG_PHILOX)
-            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
-        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, true>(a);
+            return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, true>(a);
+        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE, true>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE, true>(a);
     }
     if (a.rng.mode == RNG_PHILOX)
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
@@ -207,10 +225,10 @@ template <class T> static int launch_target(const MalaLaunch& a)
 {
     const bool dense = a.S_cm != nullptr;
     switch (epl_for_dim(a.d)) {
-    case 2: return dense ? launch_mass<T, 2, true>(a) : launch_mass<T, 2, false>(a);
-    case 4: return dense ? launch_mass<T, 4, true>(a) : launch_mass<T, 4, false>(a);
-    case 8: return dense ? launch_mass<T, 8, true>(a) : launch_mass<T, 8, false>(a);
-    case 16: return dense ? launch_mass<T, 16, true>(a) : launch_mass<T, 16, false>(a);
+    MCMCB200_EPL_CASE(2, (dense ? launch_mass<T, 2, true>(a) : launch_mass<T, 2, false>(a)))
+    MCMCB200_EPL_CASE(4, (dense ? launch_mass<T, 4, true>(a) : launch_mass<T, 4, false>(a)))
+    MCMCB200_EPL_CASE(8, (dense ? launch_mass<T, 8, true>(a) : launch_mass<T, 8, false>(a)))
+    MCMCB200_EPL_CASE(16, (dense ? launch_mass<T, 16, true>(a) : launch_mass<T, 16, false>(a)))
     default:
         set_error("mala: n_dim=%d exceeds the register-resident kernels (max %d)", a.d, 32 * MAX_EPL);
         return MCMCB200_ERR_UNSUPPORTED;

@@ -18,6 +18,7 @@
 // 1e-10 contract tolerance, not to bit-exactness.
 #include "engine.h"
 #include "rng.cuh"
+#include "dgemm.h"
 #include <math_constants.h>
 #include <cstdio>
 #include <cstdlib>
@@ -303,8 +304,11 @@ __global__ void __launch_bounds__(R_THREADS) mala_rows_kernel(const __grid_const
         } else {
             u = a.rng.tape[chain * a.rng.tape_stride + t * tape_stride_per_draw + d];
         }
-        bool acc = false;
-        if (fabs(dl) <= 1.7976931348623157e308 && isfinite(lp1_tot)) acc = (u < 1.0 + dl) ? true : (u < exp(dl));
+        bool acc = false;   // a non-finite proposal density rejects (src/mala.cpp:164-166); dl = +inf accepts (same rule as mala.cu)
+        if (isfinite(lp1_tot)) {
+            acc = u < 1.0 + dl;
+            if (!acc) acc = (fabs(dl) <= 1.7976931348623157e308) && (u < exp(dl));
+        }
         if (acc) {
 #pragma unroll
             for (int k = 0; k < EPT; ++k) { x[k] = y[k]; mx[k] = my[k]; }
@@ -346,6 +350,27 @@ template <int RNGM> static int launch_rows_ept(const WideArgs& a, long long t, b
     case 6: case 8: return launch_rows<8, RNGM>(a, t, init, st);
     default: return launch_rows<16, RNGM>(a, t, init, st);
     }
+}
+
+// C[M x d] = Y[M x d] * A[d x d] (row-major) on `stream`: the fp64 tensor-core GEMM above, for the other chain-batched paths
+int launch_dgemm_dmma(const double* Y, const double* Amat, double* Cout, long long M, int d, cudaStream_t stream)
+{
+    if ((d & 1) || ((reinterpret_cast<uintptr_t>(Y) | reinterpret_cast<uintptr_t>(Amat) | reinterpret_cast<uintptr_t>(Cout)) & 15)) {
+        set_error("dgemm: n_dim must be even and the operands 16-byte aligned");
+        return MCMCB200_ERR_UNSUPPORTED;
+    }
+    const size_t gsmem = (size_t)G_STAGES * G_STAGE_DOUBLES * sizeof(double);
+    static bool attr_set[64] = {};   // per device, once: the call may sit inside a stream capture
+    int dev = 0;
+    MCMCB200_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        MCMCB200_CUDA_TRY(cudaFuncSetAttribute(dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const dim3 ggrid((d + GN - 1) / GN, (unsigned)((M + GM - 1) / GM));
+    dgemm_dmma_kernel<<<ggrid, G_THREADS, gsmem, stream>>>(Y, Amat, Cout, (int)M, d);
+    MCMCB200_CUDA_TRY(cudaGetLastError());
+    return MCMCB200_OK;
 }
 
 long long mala_wide_work_doubles(long long n_chains, int d) { return 4 * n_chains * (long long)d + n_chains; }

@@ -8,14 +8,24 @@
 // v*eps): the leaf list of T(j, a) is o_j = o_{j-1} ++ (j + o_{j-1}) offset by a, its "near" slot is offset a+1 and
 // its "far" slot is a+j+1 when the first half did not stop (else the first half's far slot).  So instead of the
 // reference's 2^j leapfrogs per doubling the kernel computes each distinct state once (at most 1 + j(j+1)/2),
-// keeps (x_k, r_k, U_k, K_k) in a per-chain work area and replays the merge logic — slice counts, the uniform
-// draws in post-order, the theta' selection, alpha statistics and U-turn tests — on scalars and on dot products of
-// stored states, with an explicit stack instead of recursion.  Results are those of the literal recursion
-// (oracle.cpp build_tree restates it literally; tests compare the two).
+// keeps (x_k, r_k, U_k, K_k) in a per-chain work area and evaluates the merge logic — slice counts, alpha statistics,
+// stop flags and U-turn tests — on scalars and on dot products of stored states.
+//
+// Subtree summaries instead of a replay.  Within one doubling the subtree T(j, a) is a pure function of (j, a) except for
+// WHICH leaf its theta' selection picks: (n, s, alpha, n_alpha, far slot) do not depend on the uniforms.  The 2^j - 1
+// merges of a depth-j doubling touch only O(j^3) distinct (j, a) pairs (172 of 511 at j = 9), so the kernel memoises the
+// summary of every T(j, a) it has built (per warp, tagged with the doubling's epoch) and walks the DAG with an explicit
+// stack: each distinct subtree is merged — and U-turn-tested — once per doubling.  The recursion draws its uniforms in
+// post-order, one per merge, so a built subtree consumes exactly n_alpha - 1 of them and the uniform of a merge sits at a
+// known offset of the draw's stream (Philox is counter-based; the tape is read at cursor + offset).  theta' is therefore
+// resolved lazily: only when the doubling's proposal is accepted (src/nuts.cpp:261-267) does the kernel descend from the
+// root, drawing the one uniform of each merge on the path (O(j) instead of 2^j - 1 Philox blocks).  Results are those of
+// the literal recursion (oracle.cpp build_tree restates it literally; tests compare the two).
 //
 // Per-chain work area (doubles, dp = n_dim rounded up to even):
 //   [0,dp) prev_draw  [dp,2dp) draw momentum  [2dp,3dp) theta+  [3dp,4dp) theta-  [4dp,5dp) r+  [5dp,6dp) r-
-//   then for k = 1..m_max: x_k, r_k (2 dp each), then U_k[m_max], K_k[m_max].
+//   then for k = 1..m_max: x_k, r_k (2 dp each), then U_k[m_max], K_k[m_max], 8 doubles of saved chain state (segmented
+//   runs, see NutsLaunch::t_begin) and — only for max_tree_depth > 10 — the summary table (2 doubles per entry).
 #include "engine.h"
 #include "rng.cuh"
 #include "targets.cuh"
@@ -32,27 +42,40 @@ static __host__ __device__ int nuts_m_max(int max_depth)
     return 1 + j * (j + 1) / 2;
 }
 
-#if !defined(MCMCB200_TARGET_SLICE) || MCMCB200_TARGET_SLICE == 0   // one definition across the per-target translation units
+// Summary table: one entry per (j, a), 1 <= j <= Jm = max_depth - 1, 0 <= a <= a_max(j) = (Jm (Jm + 1) - j (j + 1)) / 2
+// (a is a subset sum of {j + 1, ..., Jm}); level j starts at off(j) = sum_{i > j} (a_max(i) + 1).
+static __host__ __device__ int nuts_memo_entries(int max_depth)
+{
+    const int Jm = max_depth - 1;
+    int n = 0;
+    for (int j = 1; j <= Jm; ++j) n += (Jm * (Jm + 1) - j * (j + 1)) / 2 + 1;
+    return n;
+}
+constexpr int NUTS_TAB_SMEM = 256;   // entries per warp kept in shared memory: covers max_tree_depth <= 10 (249 entries)
+constexpr int NUTS_STATE_DOUBLES = 8;
+
+#if (!defined(MCMCB200_TARGET_SLICE) || MCMCB200_TARGET_SLICE == 0) && !defined(MCMCB200_USER_TARGET_TYPE)   // one definition across the per-target translation units (the library's)
 long long nuts_work_doubles_per_chain(int d, int max_depth)
 {
     const long long dp = (d + 1) & ~1;
     const long long m = nuts_m_max(max_depth);
-    return 6 * dp + 2 * dp * m + 2 * m + 2;
+    const long long e = nuts_memo_entries(max_depth);
+    return 6 * dp + 2 * dp * m + 2 * m + 2 + NUTS_STATE_DOUBLES + (e > NUTS_TAB_SMEM ? 2 * e : 0);
 }
 #endif
 
 constexpr int NUTS_MAX_LEVELS = 22;
 
-struct NutsStack {  // per-warp recursion stack (shared memory)
-    int j[NUTS_MAX_LEVELS], a[NUTS_MAX_LEVELS], phase[NUTS_MAX_LEVELS], sel[NUTS_MAX_LEVELS], nalpha[NUTS_MAX_LEVELS];
-    long long n[NUTS_MAX_LEVELS];
+struct NutsStack {  // per-warp traversal stack (shared memory): frame = (j, a, phase) + the first half's summary while the second is built
+    int j[NUTS_MAX_LEVELS], a[NUTS_MAX_LEVELS], phase[NUTS_MAX_LEVELS], n[NUTS_MAX_LEVELS], nalpha[NUTS_MAX_LEVELS];
     double alpha[NUTS_MAX_LEVELS];
+    int lvl_off[NUTS_MAX_LEVELS];   // off(j) of the summary table
 };
 
-// U-turn results of the subtrees T(j, a) of the current doubling, per warp: within one doubling the 2^j - 1 merges of
-// the replay touch far fewer distinct (j, a) pairs (172 of 511 at j = 9), and the four state vectors + two dot products
-// of a repeated pair give the same answer.  Entry = (epoch << 1) | result; the epoch changes with every doubling.
-constexpr int NUTS_UC_J = 10, NUTS_UC_A = 46;   // covers the default max_tree_depth = 10; larger trees compute directly
+// summary of a built subtree: alpha statistic + two packed words
+//   w0 = n (21 bits) | far slot << 21 (8 bits) | s << 29        w1 = n_alpha (21 bits) | epoch << 21 (11 bits, 0 = empty)
+struct NutsSummary { double alpha; unsigned w0, w1; };
+constexpr unsigned NUTS_EPOCH_MAX = 2047u;
 
 constexpr int nuts_min_blocks(int epl) { return epl <= 4 ? 4 : (epl == 8 ? 2 : 1); }
 
@@ -69,12 +92,14 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     extern __shared__ double smem[];
     __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
     __shared__ NutsStack stacks[NW];
-    __shared__ int ucache[NW][NUTS_UC_J][NUTS_UC_A];
     __shared__ int n_active;   // COOP: chains of this CTA still running
     __shared__ int coop_want;  // COOP: products requested and not yet served
     typedef Ar<STRICT> A;
     if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
-    for (int i = threadIdx.x; i < NW * NUTS_UC_J * NUTS_UC_A; i += NW * 32) (&ucache[0][0][0])[i] = 0;
+    // summary tables: the first NW * NUTS_TAB_SMEM * 16 bytes of dynamic shared memory (unused when the table is global)
+    NutsSummary* const memo_sh = reinterpret_cast<NutsSummary*>(smem);
+    for (int i = threadIdx.x; i < NW * NUTS_TAB_SMEM; i += NW * 32) { memo_sh[i].alpha = 0.0; memo_sh[i].w0 = 0u; memo_sh[i].w1 = 0u; }
+    double* const vsm = smem + (size_t)NW * NUTS_TAB_SMEM * 2;   // the vectors / panels follow the tables
     if (COOP && threadIdx.x == 0) {
         const long long left = a.n_chains - (long long)blockIdx.x * NW;
         n_active = left < NW ? (int)left : NW;
@@ -85,15 +110,15 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     const long long chain = (long long)blockIdx.x * NW + warp;
     const int d = a.d;
     const int dp = (d + 1) & ~1;
-    double* tscr = smem + (size_t)warp * 2 * dp;
+    double* tscr = vsm + (size_t)warp * 2 * dp;
     double* mscr = tscr + dp;
     typename std::conditional<COOP, CoopWarpCtx<NW>, WarpCtx>::type w;
     w.lane = lane; w.d = d; w.scr = tscr;
     if constexpr (COOP) {
         // dynamic shared memory: NW x (x, y) vectors, then (when the TMA path applies) two panel buffers and two mbarriers
-        w.warp = warp; w.coop_base = smem; w.coop_stride = 2 * dp; w.phase = 0u; w.n_active = &n_active; w.want = &coop_want;
+        w.warp = warp; w.coop_base = vsm; w.coop_stride = 2 * dp; w.phase = 0u; w.n_active = &n_active; w.want = &coop_want;
         const bool tma = (d % 2 == 0) && d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);
-        w.panels = tma ? smem + (size_t)NW * 2 * dp : nullptr;
+        w.panels = tma ? vsm + (size_t)NW * 2 * dp : nullptr;
         w.mbar = tma ? reinterpret_cast<unsigned long long*>(w.panels + (size_t)2 * COOP_PANEL_COLS * d) : nullptr;
         if (tma) {
             if (threadIdx.x == 0) { mbar_init(w.mbar, 1); mbar_init(w.mbar + 1, 1); mbar_init_fence(); }
@@ -114,6 +139,18 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     double* Wst = W + 6 * dp;  // state k (1-based): x at Wst + (k-1)*2dp, r at + dp
     double* Us = Wst + (size_t)2 * dp * m_max;
     double* Ks = Us + m_max;
+    double* Wstate = Ks + m_max + 2;   // saved scalars of a segmented run
+    const int memo_n = nuts_memo_entries(a.max_depth);
+    NutsSummary* const memo = (memo_n > NUTS_TAB_SMEM) ? reinterpret_cast<NutsSummary*>(Wstate + NUTS_STATE_DOUBLES) : memo_sh + (size_t)warp * NUTS_TAB_SMEM;
+    if (memo_n > NUTS_TAB_SMEM)
+        for (int i = lane; i < memo_n; i += 32) { memo[i].alpha = 0.0; memo[i].w0 = 0u; memo[i].w1 = 0u; }
+    if (lane == 0) {
+        const int Jm = a.max_depth - 1;
+        int run = 0;
+        for (int j = Jm; j >= 1; --j) { st.lvl_off[j] = run; run += (Jm * (Jm + 1) - j * (j + 1)) / 2 + 1; }
+        st.lvl_off[0] = 0;
+    }
+    __syncwarp();
 
     // K = p.(M^-1 p)/2  (src/nuts.cpp:204, nuts.ipp:140)
     auto kinetic = [&](const double (&p)[EPL]) -> double {
@@ -171,20 +208,23 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     };
 
     double x[EPL], xt[EPL], rt[EPL], gt[EPL];
+    ChainRng<RNGM> rng;
+    rng.init(a.rng, chain, a.chain_offset + chain);
+    long long n_lf = 0;
+    unsigned epoch = 0;
+    double eps, mu, h, eps_bar, prev_U;
+    int n_acc = 0;
+
+    if (a.t_begin == 0) {
     load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
     if (BOX) {
 #pragma unroll
         for (int k = 0; k < EPL; ++k) x[k] = bx.transform(BOX ? k : 0, x[k]);   // src/nuts.cpp:158-162
     }
-    ChainRng<RNGM> rng;
-    rng.init(a.rng, chain, a.chain_offset + chain);
-    long long n_lf = 0;
-    int uc_epoch = 0;
-
     // ---- pre-loop momentum draw (src/nuts.cpp:166-168) and nuts_find_initial_step_size (nuts.ipp:30-93) ----
     rng.template normals<EPL, false>(a.rng, -1, d, lane, rng_tab, rt);
     momentum(rt);
-    double eps = 1.0;
+    eps = 1.0;
     {
         const double pU = neg_logp_finite(box_eval<T, EPL, STRICT, BOX, true, true, true>(a.tdata, w, bx, x, gt, Jt));
         const double pK = kinetic(rt);
@@ -206,25 +246,44 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
             cond = dH > -0.69314718055994530942;
         }
     }
-    const double mu = log(10.0 * eps);  // src/nuts.cpp:174
-    double h = 0.0;
-    double eps_bar = a.eps_bar0;
-    double prev_U = -box_eval<T, EPL, STRICT, BOX, true, false, true>(a.tdata, w, bx, x, gt, Jt);  // :181 (no finite clamp here)
+    mu = log(10.0 * eps);  // src/nuts.cpp:174
+    h = 0.0;
+    eps_bar = a.eps_bar0;
+    prev_U = -box_eval<T, EPL, STRICT, BOX, true, false, true>(a.tdata, w, bx, x, gt, Jt);  // :181 (no finite clamp here)
     store_vec<EPL>(Wprev, d, lane, x);
+    } else {
+        // a later segment of a run that is driven draw by draw from the host (reference-stream mode): the chain's state
+        // was parked in its work area by the previous launch
+        load_vec<EPL>(Wprev, d, lane, x);
+        eps = Wstate[0]; eps_bar = Wstate[1]; h = Wstate[2]; mu = Wstate[3]; prev_U = Wstate[4];
+        n_acc = (int)Wstate[5];
+        n_lf = (long long)Wstate[6];
+    }
 
-    int n_acc = 0;
-    const int n_total = (int)(a.n_burnin + a.n_keep);
     const int n_burnin = (int)a.n_burnin;
-    double* out_row = a.draws + chain * a.n_keep * d;
-    double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
+    const int t_end = (int)a.t_end;
+    const int kept_before = (int)a.t_begin > n_burnin ? (int)a.t_begin - n_burnin : 0;
+    double* out_row = a.draws + (chain * a.n_keep + kept_before) * d;
+    double* out_lp = a.logp ? a.logp + chain * a.n_keep + kept_before : nullptr;
 
-    for (int t = 0; t < n_total; ++t) {
+    // leaf T(0, ao): state k = ao + 1 of the trajectory (nuts.ipp:132-157)
+    struct Leaf { int n, s; };
+    auto leaf_ns = [&](int k_state, double log_u) -> Leaf {
+        const double Uk = reinterpret_cast<volatile double*>(Us)[k_state - 1], Kk = reinterpret_cast<volatile double*>(Ks)[k_state - 1];
+        Leaf l;
+        l.n = (log_u <= A::sub(-Uk, Kk)) ? 1 : 0;                    // :146
+        l.s = (log_u < A::sub(A::sub(1000.0, Uk), Kk)) ? 1 : 0;      // :147
+        return l;
+    };
+
+    for (int t = (int)a.t_begin; t < t_end; ++t) {
         int ucount = 0;
         rng.template normals<EPL, false>(a.rng, t, d, lane, rng_tab, rt);   // :200
+        const long long ubase_cur = rng.cursor;                             // tape mode: where this draw's uniforms start
         momentum(rt);                                                       // :202
         const double prev_K = kinetic(rt);                                  // :204
         store_vec<EPL>(Wm, d, lane, rt);
-        const double log_u = A::sub(A::sub(log(rng.uniform(a.rng, t, ucount++)), prev_U), prev_K);   // :206
+        const double log_u = A::sub(A::sub(log(rng.uniform_at(a.rng, t, ucount++, ubase_cur)), prev_U), prev_K);   // :206
         store_vec<EPL>(Wxp, d, lane, x);   // :212-215
         store_vec<EPL>(Wxn, d, lane, x);
         store_vec<EPL>(Wrp, d, lane, rt);
@@ -236,28 +295,33 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
         double alpha = 0.0;
 
         while (s_val == 1 && depth < a.max_depth) {   // :227
-            const double zz = rng.uniform(a.rng, t, ucount++);   // :233
+            const double zz = rng.uniform_at(a.rng, t, ucount++, ubase_cur);   // :233
             const int dir = (zz <= 0.5) ? -1 : 1;
             const double e_signed = (dir == 1) ? eps : -eps;
             const double H0 = A::add(prev_U, prev_K);
 
             // tip of the lazily extended trajectory LF^k (prev_draw, draw momentum): always restarts here (Q12)
             int computed = 0;
-            ++uc_epoch;   // new restart point / direction: the cached U-turn results of the previous doubling are void
+            // new restart point / direction: the summaries of the previous doubling are void
+            if (++epoch > NUTS_EPOCH_MAX) {
+                for (int i = lane; i < memo_n; i += 32) memo[i].w1 = 0u;
+                __syncwarp();
+                epoch = 1;
+            }
 #pragma unroll
             for (int k = 0; k < EPL; ++k) xt[k] = x[k];
             load_vec<EPL>(Wm, d, lane, rt);
             box_eval<T, EPL, STRICT, BOX, false, true, true>(a.tdata, w, bx, xt, gt, Jt);
 
-            // ---- T(depth, 0) with an explicit stack ----
-            int R_sel = 0, R_s = 0, R_nalpha = 0, R_far = 0;
-            long long R_n = 0;
+            // ---- summary of T(depth, 0): explicit-stack walk over the DAG of distinct subtrees ----
+            int R_n = 0, R_s = 0, R_nalpha = 0, R_far = 0;
             double R_alpha = 0.0;
             int level = 0;
-            st.j[0] = depth; st.a[0] = 0; st.phase[0] = 0;
+            if (lane == 0) { st.j[0] = depth; st.a[0] = 0; st.phase[0] = 0; }
+            __syncwarp();
             while (level >= 0) {
                 if constexpr (COOP) {
-                    // the replay needs no gradients: attend the other chains' product rounds instead of making them wait
+                    // the walk needs no gradients: attend the other chains' product rounds instead of making them wait
                     // — but only once enough requests are pending to share the matrix pass (a.coop_batch, or every chain
                     // that is still running): a round costs the same whether it serves one chain or eight
                     int wv = *reinterpret_cast<volatile int*>(&coop_want);
@@ -266,90 +330,92 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
                     na = __shfl_sync(FULL, na, 0);
                     if (wv > 0 && wv >= (a.coop_batch < na - 1 ? a.coop_batch : na - 1)) coop_round<STRICT>(a.tdata, w, true);
                 }
-                const int j = st.j[level], ao = st.a[level], ph = st.phase[level];
+                const int j = reinterpret_cast<volatile int*>(st.j)[level], ao = reinterpret_cast<volatile int*>(st.a)[level],
+                          ph = reinterpret_cast<volatile int*>(st.phase)[level];
+                if (j == 0) {
+                    const int k_need = ao + 1;
+                    while (computed < k_need) {   // extend the trajectory by one leapfrog (nuts.ipp:132)
+                        const double lp = leapfrog(e_signed, xt, rt, gt);
+                        ++computed; ++n_lf;
+                        const double Uk = neg_logp_finite(lp);   // :134-138
+                        const double Kk = kinetic(rt);           // :140
+                        store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp, d, lane, xt);
+                        store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp + dp, d, lane, rt);
+                        if (lane == 0) { Us[computed - 1] = Uk; Ks[computed - 1] = Kk; }
+                        __syncwarp();
+                    }
+                    const double Uk = reinterpret_cast<volatile double*>(Us)[k_need - 1], Kk = reinterpret_cast<volatile double*>(Ks)[k_need - 1];
+                    const Leaf l = leaf_ns(k_need, log_u);
+                    R_n = l.n;
+                    R_s = l.s;
+                    R_alpha = exp(fmin(0.0, A::add(-A::add(Uk, Kk), H0)));        // :157
+                    R_nalpha = 1;
+                    R_far = k_need;
+                    --level;
+                    continue;
+                }
+                NutsSummary* const ent = memo + st.lvl_off[j] + ao;
                 if (ph == 0) {
-                    if (j == 0) {
-                        const int k_need = ao + 1;
-                        while (computed < k_need) {   // extend the trajectory by one leapfrog (nuts.ipp:132)
-                            const double lp = leapfrog(e_signed, xt, rt, gt);
-                            ++computed; ++n_lf;
-                            const double Uk = neg_logp_finite(lp);   // :134-138
-                            const double Kk = kinetic(rt);           // :140
-                            store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp, d, lane, xt);
-                            store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp + dp, d, lane, rt);
-                            if (lane == 0) { Us[computed - 1] = Uk; Ks[computed - 1] = Kk; }
-                            __syncwarp();
-                        }
-                        const double Uk = reinterpret_cast<volatile double*>(Us)[k_need - 1], Kk = reinterpret_cast<volatile double*>(Ks)[k_need - 1];
-                        R_n = (log_u <= A::sub(-Uk, Kk)) ? 1 : 0;                    // :146
-                        R_s = (log_u < A::sub(A::sub(1000.0, Uk), Kk)) ? 1 : 0;      // :147
-                        R_alpha = exp(fmin(0.0, A::add(-A::add(Uk, Kk), H0)));        // :157
-                        R_nalpha = 1;
-                        R_sel = k_need;
-                        R_far = k_need;
+                    const unsigned w1 = reinterpret_cast<volatile unsigned*>(&ent->w1)[0];
+                    if ((w1 >> 21) == epoch) {   // built earlier in this doubling
+                        const unsigned w0 = reinterpret_cast<volatile unsigned*>(&ent->w0)[0];
+                        R_alpha = reinterpret_cast<volatile double*>(&ent->alpha)[0];
+                        R_n = (int)(w0 & 0x1fffffu); R_far = (int)((w0 >> 21) & 0xffu); R_s = (int)((w0 >> 29) & 1u);
+                        R_nalpha = (int)(w1 & 0x1fffffu);
                         --level;
                     } else {
                         if (lane == 0) { st.phase[level] = 1; st.j[level + 1] = j - 1; st.a[level + 1] = ao; st.phase[level + 1] = 0; }
                         __syncwarp();
                         ++level;
                     }
-                } else if (ph == 1) {   // first half returned in R_*
-                    if (R_s == 1) {
-                        if (lane == 0) {
-                            st.sel[level] = R_sel; st.n[level] = R_n; st.alpha[level] = R_alpha; st.nalpha[level] = R_nalpha;
-                            st.phase[level] = 2;
-                            st.j[level + 1] = j - 1; st.a[level + 1] = ao + j; st.phase[level + 1] = 0;   // second half from far(A)
-                        }
-                        __syncwarp();
-                        ++level;
-                    } else {
-                        --level;   // result = first half's (nuts.ipp:234-239)
+                    continue;
+                }
+                if (ph == 1 && R_s == 1) {   // first half returned in R_* and did not stop: build the second half from far(A)
+                    if (lane == 0) {
+                        st.n[level] = R_n; st.alpha[level] = R_alpha; st.nalpha[level] = R_nalpha;
+                        st.phase[level] = 2;
+                        st.j[level + 1] = j - 1; st.a[level + 1] = ao + j; st.phase[level + 1] = 0;
                     }
-                } else {   // second half returned in R_*
-                    const long long nA = st.n[level];
-                    const double prob = (double)R_n / (double)(nA + R_n);        // :213
-                    const double z2 = rng.uniform(a.rng, t, ucount++);           // :214
-                    const int sel = (z2 < prob) ? R_sel : st.sel[level];
-                    // U-turn test on the updated slots: near = ao+1, far = ao+j+1 (Appendix C).  Its outcome only matters while
-                    // the subtree has not stopped (R_s = R_s * ... , nuts.ipp:229) and is a function of (j, ao) within a doubling.
+                    __syncwarp();
+                    ++level;
+                    continue;
+                }
+                if (ph == 2) {   // second half returned in R_*
+                    // U-turn test on the merged subtree's ends: near = ao+1, far = ao+j+1 (Appendix C).  Its outcome only
+                    // matters while the subtree has not stopped (s = s'' * ..., nuts.ipp:229).
                     const int near = ao + 1, far = ao + j + 1;
                     if (R_s == 1) {
-                        const bool cacheable = (j < NUTS_UC_J) && (ao < NUTS_UC_A);
-                        int ut = -1;
-                        if (cacheable) {
-                            const int e = reinterpret_cast<volatile int*>(&ucache[warp][j][ao])[0];
-                            if ((e >> 1) == uc_epoch) ut = e & 1;
-                        }
-                        if (ut < 0) {
-                            double xn_[EPL], xf_[EPL], rn_[EPL], rf_[EPL];
-                            load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp, d, lane, xn_);
-                            load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp + dp, d, lane, rn_);
-                            load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp, d, lane, xf_);
-                            load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp + dp, d, lane, rf_);
-                            double diff[EPL];
+                        double xn_[EPL], xf_[EPL], rn_[EPL], rf_[EPL];
+                        load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp, d, lane, xn_);
+                        load_vec<EPL>(Wst + (size_t)(near - 1) * 2 * dp + dp, d, lane, rn_);
+                        load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp, d, lane, xf_);
+                        load_vec<EPL>(Wst + (size_t)(far - 1) * 2 * dp + dp, d, lane, rf_);
+                        double diff[EPL];
 #pragma unroll
-                            for (int k = 0; k < EPL; ++k) diff[k] = (dir == 1) ? A::sub(xf_[k], xn_[k]) : A::sub(xn_[k], xf_[k]);   // pos - neg
-                            // dir=+1: pos=far, neg=near; dir=-1: pos=near, neg=far
-                            const double d_neg = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rn_) : warp_dot<EPL, STRICT>(diff, rf_);   // :226
-                            const double d_pos = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rf_) : warp_dot<EPL, STRICT>(diff, rn_);   // :227
-                            ut = ((d_neg >= 0.0) ? 1 : 0) * ((d_pos >= 0.0) ? 1 : 0);                                                  // :229
-                            if (cacheable) {
-                                if (lane == 0) ucache[warp][j][ao] = (uc_epoch << 1) | ut;
-                                __syncwarp();
-                            }
-                        }
-                        R_s = ut;
+                        for (int k = 0; k < EPL; ++k) diff[k] = (dir == 1) ? A::sub(xf_[k], xn_[k]) : A::sub(xn_[k], xf_[k]);   // pos - neg
+                        // dir=+1: pos=far, neg=near; dir=-1: pos=near, neg=far
+                        const double d_neg = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rn_) : warp_dot<EPL, STRICT>(diff, rf_);   // :226
+                        const double d_pos = (dir == 1) ? warp_dot<EPL, STRICT>(diff, rf_) : warp_dot<EPL, STRICT>(diff, rn_);   // :227
+                        R_s = ((d_neg >= 0.0) ? 1 : 0) * ((d_pos >= 0.0) ? 1 : 0);                                                 // :229
                     }
-                    R_sel = sel;
-                    R_n = nA + R_n;
-                    R_alpha = st.alpha[level] + R_alpha;
-                    R_nalpha = st.nalpha[level] + R_nalpha;
+                    R_n = reinterpret_cast<volatile int*>(st.n)[level] + R_n;
+                    R_alpha = reinterpret_cast<volatile double*>(st.alpha)[level] + R_alpha;
+                    R_nalpha = reinterpret_cast<volatile int*>(st.nalpha)[level] + R_nalpha;
                     R_far = far;
-                    --level;
                 }
+                // (ph == 1 with R_s == 0: the result is the first half's, nuts.ipp:234-239)
+                if (lane == 0) {
+                    ent->alpha = R_alpha;
+                    ent->w0 = (unsigned)R_n | ((unsigned)R_far << 21) | ((unsigned)R_s << 29);
+                    ent->w1 = (unsigned)R_nalpha | (epoch << 21);
+                }
+                __syncwarp();
+                --level;
             }
             alpha = R_alpha;   // overwritten by every doubling (Q12)
             n_alpha = R_nalpha;
+            const int ubase = ucount;   // the merges of this doubling drew uniforms ubase .. ubase + n_alpha - 2 (post-order)
+            ucount += R_nalpha - 1;
 
             // the far slot of T lands in theta^v / r^v (src/nuts.cpp:241-256)
             {
@@ -361,8 +427,37 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
                 __syncwarp();
             }
             if (R_s == 1) {
-                const double z3 = rng.uniform(a.rng, t, ucount++);   // :261
+                const double z3 = rng.uniform_at(a.rng, t, ucount++, ubase_cur);   // :261
                 if (z3 < (double)R_n / (double)n_val) {              // :263
+                    // theta' of T(depth, 0), resolved now: at every merge on the way down the second half's theta' replaces
+                    // the first half's with probability n''/(n' + n'') (nuts.ipp:213-221), the merge's uniform being the one
+                    // drawn after both halves were built
+                    int jj = depth, aa = 0, ob = ubase;
+                    while (jj > 0) {
+                        int nA, sA, cA, nB, cB;
+                        if (jj == 1) {
+                            const Leaf lA = leaf_ns(aa + 1, log_u);
+                            nA = lA.n; sA = lA.s; cA = 0;
+                        } else {
+                            const NutsSummary* eA = memo + st.lvl_off[jj - 1] + aa;
+                            const unsigned w0 = reinterpret_cast<const volatile unsigned*>(&eA->w0)[0], w1 = reinterpret_cast<const volatile unsigned*>(&eA->w1)[0];
+                            nA = (int)(w0 & 0x1fffffu); sA = (int)((w0 >> 29) & 1u); cA = (int)(w1 & 0x1fffffu) - 1;
+                        }
+                        if (sA == 1) {
+                            if (jj == 1) {
+                                nB = leaf_ns(aa + jj + 1, log_u).n; cB = 0;
+                            } else {
+                                const NutsSummary* eB = memo + st.lvl_off[jj - 1] + aa + jj;
+                                nB = (int)(reinterpret_cast<const volatile unsigned*>(&eB->w0)[0] & 0x1fffffu);
+                                cB = (int)(reinterpret_cast<const volatile unsigned*>(&eB->w1)[0] & 0x1fffffu) - 1;
+                            }
+                            const double prob = (double)nB / (double)(nA + nB);                       // :213
+                            const double z2 = rng.uniform_at(a.rng, t, ob + cA + cB, ubase_cur);     // :214
+                            if (z2 < prob) { ob += cA; aa += jj; }
+                        }
+                        --jj;
+                    }
+                    const int R_sel = aa + 1;
                     load_vec<EPL>(Wst + (size_t)(R_sel - 1) * 2 * dp, d, lane, x);   // prev_draw = theta'
                     prev_U = reinterpret_cast<volatile double*>(Us)[R_sel - 1];                                         // = -log pi(theta'), non-finite -> +inf
                     store_vec<EPL>(Wprev, d, lane, x);
@@ -384,6 +479,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
                 s_val = R_s * c1 * c2;                                     // :289
             }
         }
+        if (RNGM == RNG_TAPE) rng.cursor = ubase_cur + ucount;
 
         // ---- dual averaging (src/nuts.cpp:294-302) ----
         if (t < a.n_adapt) {
@@ -410,6 +506,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
             n_acc += good_round;   // :308
         }
     }
+    if (lane == 0 && a.save_state) {
+        Wstate[0] = eps; Wstate[1] = eps_bar; Wstate[2] = h; Wstate[3] = mu; Wstate[4] = prev_U;
+        Wstate[5] = (double)n_acc; Wstate[6] = (double)n_lf;
+    }
+    if (lane == 0 && a.tape_used) a.tape_used[chain] = rng.cursor;
     if (lane == 0) {
         if (a.n_accept) a.n_accept[chain] = n_acc;
         if (a.step_out) a.step_out[chain] = eps;
@@ -435,7 +536,8 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
         constexpr int NW = (T::dense_matrix && !BOX && !DENSE_M) ? 8 : WARPS_PER_BLOCK;
         const long long blocks = (a.n_chains + NW - 1) / NW;
         const bool tma = (a.d % 2 == 0) && a.d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);   // same test as the kernel
-        const size_t smem = (size_t)NW * 2 * dp * sizeof(double) + (tma ? (size_t)2 * COOP_PANEL_COLS * a.d * sizeof(double) + 16 : 0);
+        const size_t smem = (size_t)NW * NUTS_TAB_SMEM * sizeof(NutsSummary) + (size_t)NW * 2 * dp * sizeof(double) +
+                            (tma ? (size_t)2 * COOP_PANEL_COLS * a.d * sizeof(double) + 16 : 0);
         auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX, NW>;
         if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)blocks, NW * 32, smem, a.stream>>>(a);
@@ -443,7 +545,8 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
         return MCMCB200_OK;
     }
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
-    const size_t smem = (T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dp * sizeof(double) : 0;
+    const size_t smem = (size_t)WARPS_PER_BLOCK * NUTS_TAB_SMEM * sizeof(NutsSummary) +
+                        ((T::needs_scratch || DENSE_M) ? (size_t)WARPS_PER_BLOCK * 2 * dp * sizeof(double) : 0);
     auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX>;
     if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
@@ -453,14 +556,10 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
 
 template <class T, int EPL, bool DENSE_M> static int launch_mass(const NutsLaunch& a)
 {
-    if (a.lb != nullptr) {   // box constraints: M = I only
-        if (DENSE_M) {
-            set_error("nuts: vals_bound together with precond_mat is not supported on the device path");
-            return MCMCB200_ERR_UNSUPPORTED;
-        }
+    if (a.lb != nullptr) {   // box constraints, with or without a dense mass matrix (src/nuts.cpp:111-126,139-154)
         if (a.rng.mode == RNG_PHILOX)
-            return a.strict ? launch_one<T, EPL, false, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, false, false, RNG_PHILOX, true>(a);
-        return a.strict ? launch_one<T, EPL, false, true, RNG_TAPE, true>(a) : launch_one<T, EPL, false, false, RNG_TAPE, true>(a);
+            return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, true>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, true>(a);
+        return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_TAPE, true>(a) : launch_one<T, EPL, DENSE_M, false, RNG_TAPE, true>(a);
     }
     if (a.rng.mode == RNG_PHILOX)
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX>(a);
@@ -471,9 +570,9 @@ template <class T> static int launch_target(const NutsLaunch& a)
 {
     const bool dense = a.S_cm != nullptr;
     switch (epl_for_dim(a.d)) {
-    case 2: return dense ? launch_mass<T, 2, true>(a) : launch_mass<T, 2, false>(a);
-    case 4: return dense ? launch_mass<T, 4, true>(a) : launch_mass<T, 4, false>(a);
-    case 8: return dense ? launch_mass<T, 8, true>(a) : launch_mass<T, 8, false>(a);
+    MCMCB200_EPL_CASE(2, (dense ? launch_mass<T, 2, true>(a) : launch_mass<T, 2, false>(a)))
+    MCMCB200_EPL_CASE(4, (dense ? launch_mass<T, 4, true>(a) : launch_mass<T, 4, false>(a)))
+    MCMCB200_EPL_CASE(8, (dense ? launch_mass<T, 8, true>(a) : launch_mass<T, 8, false>(a)))
     default:
         set_error("nuts: n_dim=%d exceeds the register-resident kernels (max %d)", a.d, 256);
         return MCMCB200_ERR_UNSUPPORTED;

@@ -1,0 +1,454 @@
+// RM-HMC, FAST arithmetic, one CTA (128 threads) per chain, all metric algebra in SHARED memory, no derivative cube.
+//
+// Same algorithm as rmhmc_general.cu (/root/reference/src/rmhmc.cpp:30-294; Q16/Q17 semantics: the fixed-point momentum
+// iterations use the START-of-trajectory metric, the position iterations G_prev^-1 + G(w)^-1) — what changes is where the
+// data lives and what is never materialised:
+//   * The reference's metric callback returns the d x d x d derivative cube and the momentum update multiplies d matrices
+//     (src/rmhmc.cpp:136-140, O(d^4)).  Only its contractions enter the force:
+//         F_i = -grad_i + 1/2 (tr(A D_i) - ((A D_i)' q).(A q)) = -grad_i + 1/2 (<D_i, A>_F - u'^T D_i u),  u = A q, u' = A^T q,
+//     so a registered metric provides `contract()`: all d values <D_i, A>_F - u'^T D_i u from its own structure.  For the
+//     funnel's SoftAbs metric (arrow Hessian => G = [[g11, w x~'], [w x~, fa I + P x~ x~']]) every D_i is a rank-structured
+//     matrix and the d contractions cost two GEMVs with A — O(d^2) instead of streaming a 2 MB cube per update (the cube
+//     kernel moved 114 MB of DRAM traffic per chain-draw at d = 64; this one keeps the chain's whole state on chip).
+//   * Matrices: two d x (d|1) buffers in shared memory (leading dimension odd => rows AND columns are conflict-free):
+//     `Ainv0` = G_prev^-1 for the whole draw, `W` = scratch in which a metric is built and inverted IN PLACE (Gauss-Jordan
+//     with partial pivoting, 2 d^3 flop, log|det| from the pivots) — also used for the draw's Cholesky factor.  G at the
+//     current / proposed point is parked in the chain's small global area (2 d^2 doubles) only for the next draw's Cholesky.
+//   * 128 threads share each matrix operation (thread = row x column-parity), warp 0 evaluates the warp-cooperative target
+//     functor and the random variates.
+// FAST arithmetic only (operation orders differ from the reference's LU / Cholesky at rounding level, within the 1e-10
+// contract); STRICT arithmetic and metrics without contract() run on rmhmc_general.cu.
+#include "engine.h"
+#include "rng.cuh"
+#include "targets.cuh"
+#include "rmhmc_metrics.cuh"
+#include "rmhmc_cta.h"
+#include <math_constants.h>
+
+namespace mcmcb200
+{
+
+constexpr int RC_THREADS = 128;
+constexpr int RC_MAXD = 64;
+
+__device__ __forceinline__ void rc_sync() { __syncthreads(); }
+
+// sum over the CTA of one value per thread (result in every thread); red: RC_THREADS/32 doubles of shared memory
+__device__ __forceinline__ double rc_block_sum(double v, double* red)
+{
+    v = warp_sum<false>(v);
+    rc_sync();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    rc_sync();
+    return (red[0] + red[1]) + (red[2] + red[3]);
+}
+
+// ---- metrics: G into a shared matrix (leading dimension ld), and the contractions of their derivative ------------
+// build(): every thread calls it; thread t writes rows i = t % 64.. of columns j = t / 64 (mod 2).
+// contract(): c[k] = <D_k, A>_F - u'^T D_k u for k = 0..d-1 into c (shared); vs: scratch of >= 4 d doubles; red: 4 doubles.
+struct FunnelSoftabsCta {
+    FunnelSoftabsScalars<false> sc;
+    __device__ __forceinline__ void prepare(const double* xs, int d) { sc.compute(xs, d); }
+    __device__ __forceinline__ void build(const double* xs, int d, double* G, int ld) const
+    {
+        const int i = threadIdx.x & 63;
+        if (i < d)
+            for (int j = threadIdx.x >> 6; j < d; j += 2) {
+                double g;
+                if (i == 0 && j == 0) g = sc.g11.v;
+                else if (i == 0 || j == 0) g = sc.w.v * xs[i + j];
+                else g = ((i == j) ? sc.fa.v : 0.0) + (sc.P.v * xs[i]) * xs[j];
+                G[(size_t)j * ld + i] = g;
+            }
+    }
+    __device__ __forceinline__ void contract(const double* xs, int d, const double* Am, int ld, const double* u, const double* up, double* vs, double* red,
+                                             double* c) const
+    {
+        // yr = A x~, yc = A^T x~ (x~ = x with element 0 zeroed): threads 0..63 rows of A, threads 64..127 rows of A^T
+        double* yr = vs;
+        double* yc = vs + d;
+        const int t = threadIdx.x, i = t & 63;
+        if (i < d) {
+            double acc = 0.0;
+            if (t < 64) { for (int j = 1; j < d; ++j) acc = fma(Am[(size_t)j * ld + i], xs[j], acc); yr[i] = acc; }
+            else { for (int j = 1; j < d; ++j) acc = fma(Am[(size_t)i * ld + j], xs[j], acc); yc[i] = acc; }
+        }
+        rc_sync();
+        // scalars: a_rc = sum_{i>=1} x_i (A(0,i) + A(i,0)), trA1 = sum_{i>=1} A(i,i), xAx = x~' A x~, ux = u.x~, upx = u'.x~, uu1 = sum_{i>=1} u'_i u_i
+        double p_arc = 0.0, p_tr = 0.0, p_xax = 0.0, p_ux = 0.0, p_upx = 0.0, p_uu = 0.0;
+        if (t >= 1 && t < d) {
+            p_arc = xs[t] * (Am[(size_t)t * ld] + Am[t]);
+            p_tr = Am[(size_t)t * ld + t];
+            p_xax = xs[t] * yr[t];
+            p_ux = u[t] * xs[t];
+            p_upx = up[t] * xs[t];
+            p_uu = up[t] * u[t];
+        }
+        const double a_rc = rc_block_sum(p_arc, red), trA1 = rc_block_sum(p_tr, red), xAx = rc_block_sum(p_xax, red);
+        const double ux = rc_block_sum(p_ux, red), upx = rc_block_sum(p_upx, red), uu1 = rc_block_sum(p_uu, red);
+        const double A00 = Am[0], u0 = u[0], up0 = up[0];
+        const double cross = up0 * ux + upx * u0;
+        if (t == 0) {
+            const double fa_ = sc.g11.dv * A00 + sc.w.dv * a_rc + sc.fa.dv * trA1 + sc.P.dv * xAx;
+            const double fu_ = sc.g11.dv * (up0 * u0) + sc.w.dv * cross + sc.fa.dv * uu1 + sc.P.dv * (upx * ux);
+            c[0] = fa_ - fu_;
+        } else if (t < d) {
+            const double s2 = 2.0 * xs[t];
+            const double fa_ = s2 * (sc.g11.ds * A00 + sc.w.ds * a_rc + sc.P.ds * xAx) + sc.w.v * (Am[(size_t)t * ld] + Am[t]) + sc.P.v * (yc[t] + yr[t]);
+            const double fu_ = s2 * (sc.g11.ds * (up0 * u0) + sc.w.ds * cross + sc.P.ds * (upx * ux)) + sc.w.v * (up0 * u[t] + up[t] * u0) +
+                               sc.P.v * (up[t] * ux + upx * u[t]);
+            c[t] = fa_ - fu_;
+        }
+        rc_sync();
+    }
+};
+
+struct FunnelFisherCta {   // G = diag(1/9 + (d-1)/2, e^-v, ..., e^-v); dG/dv = diag(0, -e^-v, ...), everything else zero
+    double ev;
+    __device__ __forceinline__ void prepare(const double* xs, int) { ev = exp(-xs[0]); }
+    __device__ __forceinline__ void build(const double*, int d, double* G, int ld) const
+    {
+        const int i = threadIdx.x & 63;
+        if (i < d)
+            for (int j = threadIdx.x >> 6; j < d; j += 2) G[(size_t)j * ld + i] = (i != j) ? 0.0 : ((i == 0) ? 1.0 / 9.0 + (double)(d - 1) / 2.0 : ev);
+    }
+    __device__ __forceinline__ void contract(const double*, int d, const double* Am, int ld, const double* u, const double* up, double*, double* red,
+                                             double* c) const
+    {
+        const int t = threadIdx.x;
+        double p = 0.0;
+        if (t >= 1 && t < d) p = Am[(size_t)t * ld + t] - up[t] * u[t];
+        const double s = rc_block_sum(p, red);
+        if (t < d) c[t] = (t == 0) ? -ev * s : 0.0;
+        rc_sync();
+    }
+};
+
+// ---- CTA-wide dense algebra on a shared d x d matrix with leading dimension ld ------------------------------------
+// In-place inverse by Gauss-Jordan elimination with partial pivoting; returns log|det| (sum of log|pivot|; the sign is
+// ignored: the metrics are positive definite).  piv: d ints of shared memory.  A zero / NaN pivot propagates NaN like the
+// reference's LU does.
+__device__ double rc_inverse_inplace(double* W, int d, int ld, int* piv, double* red)
+{
+    const int t = threadIdx.x, i = t & 63, jpar = t >> 6;
+    double logdet = 0.0;
+    for (int k = 0; k < d; ++k) {
+        // pivot: first maximum of |W(r, k)|, r >= k (warp 0; a NaN never wins, a NaN at (k,k) keeps r = k)
+        if (t < 32) {
+            double bv = -2.0;
+            int bi = 0x7fffffff;
+            const double vk = fabs(W[(size_t)k * ld + k]);
+            if (vk == vk) {
+                for (int r = t; r < d; r += 32)
+                    if (r >= k) {
+                        double v = fabs(W[(size_t)k * ld + r]);
+                        if (!(v == v)) v = -1.0;
+                        if (v > bv) { bv = v; bi = r; }
+                    }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const double ov = __shfl_xor_sync(FULL, bv, off);
+                    const int oi = __shfl_xor_sync(FULL, bi, off);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+            } else {
+                bi = k;
+            }
+            if (t == 0) piv[k] = bi;
+        }
+        rc_sync();
+        const int p = piv[k];
+        if (p != k) {   // swap rows k and p (threads over columns)
+            for (int j = t; j < d; j += RC_THREADS) {
+                const double a = W[(size_t)j * ld + k], b = W[(size_t)j * ld + p];
+                W[(size_t)j * ld + k] = b;
+                W[(size_t)j * ld + p] = a;
+            }
+            rc_sync();
+        }
+        const double pv = W[(size_t)k * ld + k];
+        logdet += log(fabs(pv));
+        const double rinv = 1.0 / pv;
+        const double f = (i < d) ? W[(size_t)k * ld + i] : 0.0;   // column k of this thread's row, before it is overwritten
+        rc_sync();
+        // row k: W(k, j) = W(k, j) / pv (j != k), W(k, k) = 1 / pv
+        for (int j = t; j < d; j += RC_THREADS) W[(size_t)j * ld + k] = (j == k) ? rinv : W[(size_t)j * ld + k] * rinv;
+        rc_sync();
+        // rows i != k: W(i, j) -= f * W(k, j) (j != k), W(i, k) = -f / pv
+        if (i < d && i != k) {
+            for (int j = jpar; j < d; j += 2) {
+                const double rk = W[(size_t)j * ld + k];
+                W[(size_t)j * ld + i] = (j == k) ? -f * rinv : fma(-f, rk, W[(size_t)j * ld + i]);
+            }
+        }
+        rc_sync();
+    }
+    // row swaps of A are column swaps of A^-1, undone in reverse order
+    for (int k = d - 1; k >= 0; --k) {
+        const int p = piv[k];
+        if (p != k) {
+            for (int r = t; r < d; r += RC_THREADS) {
+                const double a = W[(size_t)k * ld + r], b = W[(size_t)p * ld + r];
+                W[(size_t)k * ld + r] = b;
+                W[(size_t)p * ld + r] = a;
+            }
+            rc_sync();
+        }
+    }
+    (void)red;
+    return logdet;
+}
+
+// in-place lower Cholesky of the shared matrix (right-looking); the strict upper triangle keeps the input's entries — the
+// Eigen matrixLLT storage the reference multiplies with in full; returns nothing, L in the lower triangle
+__device__ void rc_cholesky_inplace(double* W, int d, int ld)
+{
+    const int t = threadIdx.x, i = t & 63, jpar = t >> 6;
+    for (int j = 0; j < d; ++j) {
+        const double dj = sqrt(W[(size_t)j * ld + j]);
+        rc_sync();
+        if (t < d && t >= j) W[(size_t)j * ld + t] = (t == j) ? dj : W[(size_t)j * ld + t] / dj;
+        rc_sync();
+        // trailing update of the lower triangle: W(i, k) -= L(i, j) L(k, j), k > j, i >= k
+        if (i < d && i > j) {
+            const double lij = W[(size_t)j * ld + i];
+            for (int k = j + 1 + ((jpar + j + 1) & 1); k <= i; k += 2) W[(size_t)k * ld + i] = fma(-lij, W[(size_t)j * ld + k], W[(size_t)k * ld + i]);
+        }
+        rc_sync();
+    }
+}
+
+template <class T, class MC, int RNGM>
+__global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
+{
+    extern __shared__ double smem[];
+    __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
+    __shared__ int piv[RC_MAXD];
+    __shared__ double red[4];
+    __shared__ double sc_u, sc_lp;   // broadcast scalars (uniform, log-density)
+    if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const long long chain = blockIdx.x;
+    const int d = a.d;
+    const int ld = d | 1;
+    const int dp = (d + 1) & ~1;
+    double* Ainv0 = smem;                    // G_prev^-1, fixed during a draw
+    double* W = Ainv0 + (size_t)d * ld;      // scratch matrix
+    double* vec = W + (size_t)d * ld;        // vectors, dp doubles each
+    double* xprev = vec;            double* xcur = vec + dp;        double* pv = vec + 2 * dp;   double* qv = vec + 3 * dp;
+    double* wv = vec + 4 * dp;      double* gv = vec + 5 * dp;      double* uv = vec + 6 * dp;   double* upv = vec + 7 * dp;
+    double* cv = vec + 8 * dp;      double* zv = vec + 9 * dp;      double* tv = vec + 10 * dp;  double* scr = vec + 11 * dp;   // scr: 4 dp
+    double* tscr = scr + 4 * dp;    // target functor scratch (dp)
+    const WarpCtx wctx{lane, d, tscr};
+    // the chain's global area: G at the accepted point and at the proposal (column-major, leading dimension d)
+    double* Gacc = a.work + (size_t)chain * (size_t)a.work_stride;
+    double* Gnew = Gacc + (size_t)d * d;
+    const double eps = a.eps, heps = 0.5 * eps;
+    rc_sync();
+
+    ChainRng<RNGM> rng;
+    rng.init(a.rng, chain, a.chain_offset + chain);
+    // warp 0: d normals of `draw` into dst (shared)
+    auto normals_to = [&](long long draw, double* dst) {
+        if (warp == 0) {
+            double z[2];
+            rng.template normals<2, false>(a.rng, draw, d, lane, rng_tab, z);
+            if (2 * lane < d) dst[2 * lane] = z[0];
+            if (2 * lane + 1 < d) dst[2 * lane + 1] = z[1];
+        }
+    };
+    // warp 0: log pi and/or gradient at the shared vector xin -> sc_lp / gv
+    auto target_at = [&](const double* xin, bool want_value, bool want_grad) {
+        if (warp == 0) {
+            double x[2], g[2];
+            x[0] = (2 * lane < d) ? xin[2 * lane] : 0.0;
+            x[1] = (2 * lane + 1 < d) ? xin[2 * lane + 1] : 0.0;
+            double v = 0.0;
+            if (want_value && want_grad) v = T::template eval<2, false, true, true, true>(a.tdata, wctx, x, g);
+            else if (want_value) v = T::template eval<2, false, true, false, true>(a.tdata, wctx, x, g);
+            else T::template eval<2, false, false, true, true>(a.tdata, wctx, x, g);
+            if (want_grad) {
+                if (2 * lane < d) gv[2 * lane] = g[0];
+                if (2 * lane + 1 < d) gv[2 * lane + 1] = g[1];
+            }
+            if (want_value && lane == 0) sc_lp = v;
+        }
+        rc_sync();
+    };
+    // y = Am v (threads 0..63) and optionally y2 = Am^T v (threads 64..127)
+    auto gemv2 = [&](const double* Am, const double* v, double* y, double* y2) {
+        const int i = t & 63;
+        if (i < d) {
+            double acc = 0.0;
+            if (t < 64) { for (int j = 0; j < d; ++j) acc = fma(Am[(size_t)j * ld + i], v[j], acc); y[i] = acc; }
+            else if (y2) { for (int j = 0; j < d; ++j) acc = fma(Am[(size_t)i * ld + j], v[j], acc); y2[i] = acc; }
+        }
+        rc_sync();
+    };
+    MC metric;
+    // out = (eps F)/2 at position y with momentum q, metric inverse Am evaluated at the point the metric object was prepared for
+    auto mntm_update = [&](const double* y, const double* q, const double* Am, const MC& m, const double* xm, double* out) {
+        target_at(y, false, true);
+        gemv2(Am, q, uv, upv);
+        m.contract(xm, d, Am, ld, uv, upv, scr, red, cv);
+        if (t < d) out[t] = (eps * fma(0.5, cv[t], -gv[t])) * 0.5;
+        rc_sync();
+    };
+    auto store_global = [&](double* G) {   // W (ld) -> global (d), before it is inverted in place
+        const int i = t & 63;
+        if (i < d)
+            for (int j = t >> 6; j < d; j += 2) G[(size_t)j * d + i] = W[(size_t)j * ld + i];
+    };
+
+    // ---- set-up: pre-loop normals (value unused), metric / inverse / energy at the initial point ----
+    normals_to(-1, zv);
+    if (t < d) xprev[t] = a.x0[(a.broadcast_x0 ? 0 : chain * d) + t];
+    rc_sync();
+    metric.prepare(xprev, d);
+    metric.build(xprev, d, W, ld);
+    rc_sync();
+    store_global(Gacc);
+    double logdet_prev = rc_inverse_inplace(W, d, ld, piv, red);
+    for (int k = t; k < d * ld; k += RC_THREADS) Ainv0[k] = W[k];
+    MC metric_prev = metric;   // the start-of-trajectory metric (Q17) of every draw until an accept replaces it
+    target_at(xprev, true, false);
+    double prev_U = (a.cons_term - sc_lp) + 0.5 * logdet_prev;
+    rc_sync();
+
+    int n_acc = 0;
+    const int n_total = (int)(a.n_burnin + a.n_keep), n_burnin = (int)a.n_burnin;
+    double* out_row = a.draws + chain * a.n_keep * d;
+    double* out_lp = a.logp ? a.logp + chain * a.n_keep : nullptr;
+
+    for (int it = 0; it < n_total; ++it) {
+        normals_to(it, zv);
+        if (warp == 0) {
+            const double u = rng.uniform(a.rng, it, 0);
+            if (lane == 0) sc_u = u;
+        }
+        // p = chol(G_prev) z with the Eigen matrixLLT storage quirk when asked for (Q8); K0 = p.(G_prev^-1 p)/2
+        {
+            const int i = t & 63;
+            if (i < d)
+                for (int j = t >> 6; j < d; j += 2) W[(size_t)j * ld + i] = Gacc[(size_t)j * d + i];
+        }
+        rc_sync();
+        rc_cholesky_inplace(W, d, ld);
+        if (t < d) {
+            double acc = 0.0;
+            const int jmax = (a.chol_mode == MCMCB200_CHOL_EIGEN_LLT) ? d : t + 1;
+            for (int j = 0; j < jmax; ++j) acc = fma(W[(size_t)j * ld + t], zv[j], acc);
+            pv[t] = acc;
+            xcur[t] = xprev[t];
+        }
+        rc_sync();
+        gemv2(Ainv0, pv, tv, nullptr);
+        const double prev_K = 0.5 * rc_block_sum(t < d ? pv[t] * tv[t] : 0.0, red);
+        double logdet_new = logdet_prev;
+        MC metric_new = metric_prev;
+        bool have_new = false;
+
+        for (int s = 0; s < a.n_leap; ++s) {
+            if (t < d) qv[t] = pv[t];
+            rc_sync();
+            for (int kk = 0; kk < a.n_fp; ++kk) {   // momentum half step, fixed point, start-of-trajectory metric (Q16/Q17)
+                mntm_update(xcur, qv, Ainv0, metric_prev, xprev, wv);
+                if (t < d) qv[t] = pv[t] + wv[t];
+                rc_sync();
+            }
+            if (t < d) { pv[t] = qv[t]; wv[t] = xcur[t]; }
+            rc_sync();
+            for (int kk = 0; kk < a.n_fp; ++kk) {   // position step, fixed point: w = x + (eps/2)(G_prev^-1 + G(w)^-1) p
+                MC mw;
+                mw.prepare(wv, d);
+                mw.build(wv, d, W, ld);
+                rc_sync();
+                rc_inverse_inplace(W, d, ld, piv, red);
+                if (t < d) {
+                    double acc = 0.0;
+                    for (int j = 0; j < d; ++j) acc = fma(Ainv0[(size_t)j * ld + t] + W[(size_t)j * ld + t], heps * pv[j], acc);
+                    tv[t] = xcur[t] + acc;
+                }
+                rc_sync();
+                if (t < d) wv[t] = tv[t];
+                rc_sync();
+            }
+            if (t < d) xcur[t] = wv[t];
+            rc_sync();
+            metric_new.prepare(xcur, d);
+            metric_new.build(xcur, d, W, ld);
+            rc_sync();
+            if (s + 1 == a.n_leap) store_global(Gnew);   // only the end point's metric can become the next draw's G_prev
+            logdet_new = rc_inverse_inplace(W, d, ld, piv, red);
+            have_new = true;
+            mntm_update(xcur, pv, W, metric_new, xcur, wv);
+            if (t < d) pv[t] = pv[t] + wv[t];
+            rc_sync();
+        }
+        if (!have_new) {   // n_leap == 0: the "new" metric is the current one
+            for (int k = t; k < d * ld; k += RC_THREADS) W[k] = Ainv0[k];
+            const int i = t & 63;
+            if (i < d)
+                for (int j = t >> 6; j < d; j += 2) Gnew[(size_t)j * d + i] = Gacc[(size_t)j * d + i];
+            rc_sync();
+        }
+        target_at(xcur, true, false);
+        double prop_U = (a.cons_term - sc_lp) + 0.5 * logdet_new;
+        if (!isfinite(prop_U)) prop_U = CUDART_INF;
+        gemv2(W, pv, tv, nullptr);
+        const double prop_K = 0.5 * rc_block_sum(t < d ? pv[t] * tv[t] : 0.0, red);
+        const double comp = fmin(0.01, -(prop_U + prop_K) + (prev_U + prev_K));   // src/rmhmc.cpp:250 (min(0.01, NaN) = 0.01: a NaN energy accepts)
+        const bool acc = sc_u < exp(comp);
+        if (acc) {   // src/rmhmc.cpp:254-261
+            if (t < d) xprev[t] = xcur[t];
+            for (int k = t; k < d * ld; k += RC_THREADS) Ainv0[k] = W[k];
+            prev_U = prop_U;
+            logdet_prev = logdet_new;
+            metric_prev = metric_new;
+            double* tp = Gacc; Gacc = Gnew; Gnew = tp;
+        }
+        rc_sync();
+        if (it >= n_burnin) {
+            if (t < d) out_row[t] = xprev[t];
+            out_row += d;
+            if (out_lp) {
+                if (t == 0) *out_lp = -(prev_U - a.cons_term);
+                ++out_lp;
+            }
+            n_acc += acc ? 1 : 0;
+        }
+    }
+    if (t == 0 && a.n_accept) a.n_accept[chain] = n_acc;
+}
+
+long long rmhmc_cta_work_doubles(int d) { return 2ll * d * d; }
+
+bool rmhmc_cta_applicable(int target_id, int metric_id, int d, bool strict, bool has_bounds)
+{
+    if (strict || has_bounds || d < 2 || d > RC_MAXD) return false;
+    return target_id == MCMCB200_TARGET_FUNNEL && metric_id >= 0 && metric_id <= 2;
+}
+
+template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
+{
+    const int d = a.d, ld = d | 1, dp = (d + 1) & ~1;
+    const size_t smem = ((size_t)2 * d * ld + (size_t)16 * dp) * sizeof(double);
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)a.n_chains, RC_THREADS, smem, a.stream>>>(a);
+        MCMCB200_CUDA_TRY(cudaGetLastError());
+        return MCMCB200_OK;
+    };
+    if (a.rng.mode == RNG_PHILOX) return launch(rmhmc_cta_kernel<T, MC, RNG_PHILOX>);
+    return launch(rmhmc_cta_kernel<T, MC, RNG_TAPE>);
+}
+
+int launch_rmhmc_cta(const RmhmcLaunch& a)
+{
+    if (a.broadcast_x0 && a.n_chains > 0 && false) return MCMCB200_ERR_UNSUPPORTED;
+    if (a.target_id == MCMCB200_TARGET_FUNNEL) return a.metric_id == 2 ? launch_cta<Funnel, FunnelSoftabsCta>(a) : launch_cta<Funnel, FunnelFisherCta>(a);
+    set_error("rmhmc (CTA kernel): target %d has no contraction-form metric", a.target_id);
+    return MCMCB200_ERR_UNSUPPORTED;
+}
+
+}  // namespace mcmcb200

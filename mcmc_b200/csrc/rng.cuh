@@ -328,6 +328,7 @@ template <int MODE> struct ChainRng {
     unsigned spare;       // Philox: 24 spare bits of this lane's block m = 0 of the current draw
     const double* tape;   // tape mode: this chain's stream
     long long cursor;
+    long long limit;      // tape mode: doubles available to this chain (reads past it return a constant and raise a.err_flag)
 
     __device__ __forceinline__ void init(const RngArgs& a, long long local_chain, long long global_chain)
     {
@@ -335,6 +336,7 @@ template <int MODE> struct ChainRng {
         spare = 0;
         tape = (MODE == RNG_TAPE) ? a.tape + local_chain * a.tape_stride : nullptr;
         cursor = 0;
+        limit = a.tape_stride;
     }
 
     // d standard normals into the lane-striped vector z (FT: d == 32*EPL, no padding slots).
@@ -387,13 +389,20 @@ template <int MODE> struct ChainRng {
                 }
             }
         } else {
-            const double* t = tape + cursor + seg_off;
+            const long long adv = (d_total < 0) ? d : d_total;
+            if (cursor + adv > limit) {   // tape exhausted (only reachable with data-dependent consumption: host checks static counts)
+                if (a.err_flag) *a.err_flag = 1;
 #pragma unroll
-            for (int k = 0; k < EPL; ++k) {
-                const int j = elem_index(lane, k);
-                z[k] = (j < d) ? t[j] : 0.0;
+                for (int k = 0; k < EPL; ++k) z[k] = 0.0;
+            } else {
+                const double* t = tape + cursor + seg_off;
+#pragma unroll
+                for (int k = 0; k < EPL; ++k) {
+                    const int j = elem_index(lane, k);
+                    z[k] = (j < d) ? t[j] : 0.0;
+                }
             }
-            cursor += (d_total < 0) ? d : d_total;
+            cursor += adv;
         }
     }
 
@@ -413,7 +422,26 @@ template <int MODE> struct ChainRng {
             const double kd = __hiloint2double(0x43300000 | hi, lo) - 4503599627370496.0;
             return fma(kd, 2.220446049250313e-16, 1.1102230246251565e-16);  // (k + 1/2) 2^-52
         }
+        if (cursor >= limit) {
+            if (a.err_flag) *a.err_flag = 1;
+            ++cursor;
+            return 0.5;
+        }
         return tape[cursor++];
+    }
+
+    // Random access to the k-th uniform of the draw without moving the cursor (NUTS resolves its theta' selection lazily,
+    // out of order).  Philox is counter-based anyway; in tape mode the uniforms of a draw sit at ubase + k, ubase = the
+    // cursor right after the draw's normals.  The caller sets cursor = ubase + (uniforms consumed) at the end of the draw.
+    __device__ __forceinline__ double uniform_at(const RngArgs& a, long long draw, int k, long long ubase)
+    {
+        if (MODE == RNG_PHILOX) return uniform(a, draw, k);
+        const long long pos = ubase + k;
+        if (pos >= limit) {
+            if (a.err_flag) *a.err_flag = 1;
+            return 0.5;
+        }
+        return tape[pos];
     }
 };
 

@@ -12,6 +12,7 @@ struct RngArgs {
     unsigned rk[20];        // the 10 round keys (k0 + r*W0, k1 + r*W1): read straight from the constant bank by LOP3
     const double* tape;     // [n_chains][tape_stride]
     long long tape_stride;
+    int* err_flag;          // device int, set to 1 by a chain whose tape cursor would pass tape_stride (checked after the run)
 };
 
 inline void rng_set_key(RngArgs& a, unsigned long long seed)

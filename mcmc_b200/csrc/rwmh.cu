@@ -141,10 +141,10 @@ template <class T, int EPL> static int launch_epl(const RwmhLaunch& a)
 template <class T> static int launch_target(const RwmhLaunch& a)
 {
     switch (epl_for_dim(a.d)) {
-    case 2: return launch_epl<T, 2>(a);
-    case 4: return launch_epl<T, 4>(a);
-    case 8: return launch_epl<T, 8>(a);
-    case 16: return launch_epl<T, 16>(a);
+    MCMCB200_EPL_CASE(2, (launch_epl<T, 2>(a)))
+    MCMCB200_EPL_CASE(4, (launch_epl<T, 4>(a)))
+    MCMCB200_EPL_CASE(8, (launch_epl<T, 8>(a)))
+    MCMCB200_EPL_CASE(16, (launch_epl<T, 16>(a)))
     default:
         set_error("rwmh: n_dim=%d exceeds the register-resident kernels (max %d)", a.d, 32 * MAX_EPL);
         return MCMCB200_ERR_UNSUPPORTED;

@@ -10,8 +10,9 @@
 // WANT_GRAD.  With REDUCE = false the return value is this lane's partial sum (the warp
 // total is log pi), so a caller can fold it into one butterfly with its other terms.
 // One fused evaluation may serve several reference calls.
-// To add a target: write a struct with the same eval<> signature, give it an id in
-// include/mcmc_b200.h and add it to MCMCB200_FOREACH_TARGET below.
+// To add a target WITHOUT rebuilding the library: include/mcmc_b200_device.cuh (a user's .cu defines the struct and
+// registers it at load time; examples/user_target/).  To add a built-in: write a struct with the same eval<> signature,
+// give it an id in include/mcmc_b200.h and add it to MCMCB200_FOREACH_TARGET below.
 #pragma once
 
 #include "warp.cuh"
@@ -200,8 +201,16 @@ struct Funnel {
 // MCMCB200_TARGET_SLICE = k (build.py compiles hmc.cu / mala.cu / nuts.cu once per target, in parallel): the
 // translation unit instantiates the kernels of target k only and exports launch_<sampler>_slice<k>; the
 // by-target dispatch lives in dispatch.cu.
+// MCMCB200_USER_TARGET_TYPE (include/mcmc_b200_device.cuh): the translation unit belongs to a USER's shared library; the
+// kernels are instantiated for the user's functor only, under the id MCMCB200_TARGET_USER, and exported as
+// launch_<sampler>_user_<tag> for the registration call.
 #define MCMCB200_N_TARGETS 6
-#if defined(MCMCB200_TARGET_SLICE)
+#define MCMCB200_CAT2(a, b) a##b
+#define MCMCB200_CAT(a, b) MCMCB200_CAT2(a, b)
+#if defined(MCMCB200_USER_TARGET_TYPE)
+#define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_USER, MCMCB200_USER_TARGET_TYPE)
+#define MCMCB200_SLICED(name) MCMCB200_CAT(MCMCB200_CAT(name, _user_), MCMCB200_USER_TARGET_TAG)
+#elif defined(MCMCB200_TARGET_SLICE)
 #if MCMCB200_TARGET_SLICE == 0
 #define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)
 #elif MCMCB200_TARGET_SLICE == 1
@@ -217,8 +226,6 @@ struct Funnel {
 #else
 #error "MCMCB200_TARGET_SLICE out of range"
 #endif
-#define MCMCB200_CAT2(a, b) a##b
-#define MCMCB200_CAT(a, b) MCMCB200_CAT2(a, b)
 #define MCMCB200_SLICED(name) MCMCB200_CAT(MCMCB200_CAT(name, _slice), MCMCB200_TARGET_SLICE)
 #elif defined(MCMCB200_FAST_BUILD)
 #define MCMCB200_FOREACH_TARGET(X) X(MCMCB200_TARGET_ISO_GAUSS, IsoGauss)

@@ -42,23 +42,75 @@ template <class T, int EPL> static int eval_one(const EvalLaunch& a)
 template <class T> static int eval_target(const EvalLaunch& a)
 {
     switch (epl_for_dim(a.d)) {
-    case 2: return eval_one<T, 2>(a);
-    case 4: return eval_one<T, 4>(a);
-    case 8: return eval_one<T, 8>(a);
-    case 16: return eval_one<T, 16>(a);
+    MCMCB200_EPL_CASE(2, (eval_one<T, 2>(a)))
+    MCMCB200_EPL_CASE(4, (eval_one<T, 4>(a)))
+    MCMCB200_EPL_CASE(8, (eval_one<T, 8>(a)))
+    MCMCB200_EPL_CASE(16, (eval_one<T, 16>(a)))
     default: set_error("target_eval: n_dim=%d unsupported", a.d); return MCMCB200_ERR_UNSUPPORTED;
     }
 }
 
-int launch_target_eval(const EvalLaunch& a)
+int MCMCB200_SLICED(launch_target_eval)(const EvalLaunch& a)
 {
     switch (a.target_id) {
 #define X(ID, TYPE) \
     case ID: return eval_target<TYPE>(a);
         MCMCB200_FOREACH_TARGET(X)
 #undef X
-    default: set_error("target_eval: unknown target id %d", a.target_id); return MCMCB200_ERR_UNKNOWN_TARGET;
+    default:
+#ifndef MCMCB200_USER_TARGET_TYPE
+        if (user_target_has(USER_LAUNCH_EVAL, a.target_id)) {
+            EvalLaunch b = a;
+            b.target_id = MCMCB200_TARGET_USER;
+            return user_target_launch(USER_LAUNCH_EVAL, a.target_id, &b);
+        }
+#endif
+        set_error("target_eval: unknown target id %d", a.target_id);
+        return MCMCB200_ERR_UNKNOWN_TARGET;
     }
+}
+
+#ifndef MCMCB200_USER_TARGET_TYPE   // the raw-stream dump and the peak probe belong to the library only
+// fp64 peak probe: 8 independent DFMA chains per thread, 8 warps per SM sub-partition — the denominator of the
+// compute-bound rooflines (C3 / C4 / C5), measured in the same process as the kernels it is compared with.
+__global__ void __launch_bounds__(1024) fp64_peak_kernel(double* out, int iters, double a, double b)
+{
+    double v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = threadIdx.x * 1e-9 + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = fma(v[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+    if (s == 123.456) out[0] = s;   // never true: keeps the loop alive
+}
+
+int launch_fp64_peak(double* scratch_dev, cudaStream_t stream, double* tflops_out)
+{
+    int dev = 0, sms = 0;
+    MCMCB200_CUDA_TRY(cudaGetDevice(&dev));
+    MCMCB200_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    cudaEvent_t e0, e1;
+    MCMCB200_CUDA_TRY(cudaEventCreate(&e0));
+    MCMCB200_CUDA_TRY(cudaEventCreate(&e1));
+    const int iters = 20000;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        MCMCB200_CUDA_TRY(cudaEventRecord(e0, stream));
+        fp64_peak_kernel<<<sms * 2, 1024, 0, stream>>>(scratch_dev, iters, 0.999999, 1e-7);
+        MCMCB200_CUDA_TRY(cudaEventRecord(e1, stream));
+        MCMCB200_CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        MCMCB200_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops_out = 2.0 * 8.0 * iters * 1024.0 * sms * 2 / (best * 1e-3) / 1e12;
+    return MCMCB200_OK;
 }
 
 template <int EPL> __global__ void philox_stream_kernel(const RngArgs r, long long chain, long long draw, int d, int n_unif, double* out)
@@ -86,6 +138,7 @@ int launch_philox_stream(unsigned long long seed, long long chain, long long dra
     rng_set_key(r, seed);
     r.tape = nullptr;
     r.tape_stride = 0;
+    r.err_flag = nullptr;
     switch (epl_for_dim(d)) {
     case 2: philox_stream_kernel<2><<<1, 32, 0, stream>>>(r, chain, draw, d, n_unif, out_dev); break;
     case 4: philox_stream_kernel<4><<<1, 32, 0, stream>>>(r, chain, draw, d, n_unif, out_dev); break;
@@ -96,5 +149,6 @@ int launch_philox_stream(unsigned long long seed, long long chain, long long dra
     MCMCB200_CUDA_TRY(cudaGetLastError());
     return MCMCB200_OK;
 }
+#endif
 
 }  // namespace mcmcb200

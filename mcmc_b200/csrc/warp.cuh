@@ -111,6 +111,18 @@ template <int EPL> __device__ __forceinline__ void load_vec(const double* __rest
     }
 }
 
+// same striping for memory the kernel also WRITES (population matrices, work areas): no __restrict__ / read-only promise,
+// L2-coherent loads (ld.global.cg), so a row stored by the warp and re-read after __syncwarp() is never served stale
+template <int EPL> __device__ __forceinline__ void load_vec_rw(const double* src, int d, int lane, double (&x)[EPL])
+{
+#pragma unroll
+    for (int m = 0; m < EPL / 2; ++m) {
+        const int j = m * 64 + 2 * lane;
+        x[2 * m] = (j < d) ? __ldcg(src + j) : 0.0;
+        x[2 * m + 1] = (j + 1 < d) ? __ldcg(src + j + 1) : 0.0;
+    }
+}
+
 // full-tile variants: d == 32*EPL and 16-byte aligned rows (checked on the host), no predicates
 template <int EPL> __device__ __forceinline__ void load_vec_full(const double* __restrict__ src, int lane, double (&x)[EPL])
 {
@@ -187,6 +199,30 @@ __device__ __forceinline__ void gemv_cm(const double* __restrict__ A, int d, int
         }
     }
     // padding slots stay exactly 0 even if v carried inf/nan
+#pragma unroll
+    for (int k = 0; k < EPL; ++k)
+        if (elem_index(lane, k) >= d) y[k] = 0.0;
+}
+
+// y_i = sum_j ((rs_i * A[j*d + i]) * post) * v_j, j increasing: what the reference's  (scalar * diag) * Matrix * vector
+// chains evaluate to with box constraints (bounded MALA with a dense precond_mat: drift ((eps^2 J) M) grad, noise
+// ((eps chol J) sqrtM) z — the diagonal factor scales the ROWS of the dense matrix before the product; oracle.cpp mala_mean).
+template <int EPL, bool STRICT>
+__device__ __forceinline__ void gemv_cm_rowscaled(const double* __restrict__ A, int d, int lane, const double* __restrict__ v_smem,
+                                                  const double (&rs)[EPL], double post, double (&y)[EPL])
+{
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) y[k] = 0.0;
+    for (int j = 0; j < d; ++j) {
+        const double t = v_smem[j];
+        const double* __restrict__ col = A + (size_t)j * (size_t)d;
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int i = elem_index(lane, k);
+            const double a = (i < d) ? __ldg(col + i) : 0.0;
+            y[k] = Ar<STRICT>::mad(Ar<STRICT>::mul(Ar<STRICT>::mul(rs[k], a), post), t, y[k]);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < EPL; ++k)
         if (elem_index(lane, k) >= d) y[k] = 0.0;

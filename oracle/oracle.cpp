@@ -449,7 +449,20 @@ void setup_precond(Ctx& c, const double* precond, int chol_mode)
 
 }  // namespace
 
+// Optional diagnostic for the parity tests: the margin u - exp(comp) of every accept test of the chain being run (negative
+// = accepted).  A GPU chain that leaves the oracle's path must do so at a draw whose margin is at rounding level — anything
+// else is a defect, not a flipped coin (tests/parity_util.py).
+static thread_local double* g_margin_buf = nullptr;
+static thread_local long g_margin_cap = 0;
+static inline void note_margin(long it, double u, double comp)
+{
+    if (g_margin_buf && it >= 0 && it < g_margin_cap) g_margin_buf[it] = u - std::exp(comp);
+}
+
 extern "C" {
+
+void oracle_set_margin_buffer(double* buf, long cap) { g_margin_buf = buf; g_margin_cap = cap; }
+
 
 struct oracle_cfg_t {
     int sampler, target_id;
@@ -519,6 +532,7 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
         const double prop_K = kinetic(c, p.data());     // :184
         const double comp = std::min(0.01, -(prop_U + prop_K) + (prev_U + prev_K));  // :188 (Q6)
         const double u = rng.uniform(t, 0);             // :189
+        note_margin(t, u, comp);
         const bool acc = u < std::exp(comp);            // :191
         if (acc) { prev = cur; prev_U = prop_U; }
         if (t >= cfg->n_burnin) {
@@ -543,8 +557,16 @@ static void mala_mean(const Ctx& c, double eps, const double* v, double* out, do
     box_grad(c, v, g.data(), J.data());
     const double e2 = eps * eps;
     if (c.bounded) {
-        // ((e2*J) * I) -> matrix product then "*= e2": entries J_ii * e2; times grad, /2, added to v
-        for (int i = 0; i < d; ++i) out[i] = v[i] + ((J[i] * e2) * g[i]) / 2.0;
+        // ((e2*J) * M) -> matrix product then "*= e2" (ScaledMat * Matrix in the stand-in): entries (J_ii * M_ij) * e2; times
+        // grad (j increasing), /2, added to v.  M = I: (J_ii * 1) * e2 on the diagonal, exact zeros elsewhere.
+        if (c.identity) {
+            for (int i = 0; i < d; ++i) out[i] = v[i] + ((J[i] * e2) * g[i]) / 2.0;
+        } else {
+            for (int i = 0; i < d; ++i) t[i] = 0.0;
+            for (int j = 0; j < d; ++j)
+                for (int i = 0; i < d; ++i) t[i] += ((J[i] * c.M[size_t(j) * d + i]) * e2) * g[j];
+            for (int i = 0; i < d; ++i) out[i] = v[i] + t[i] / 2.0;
+        }
         if (J_out) for (int i = 0; i < d; ++i) J_out[i] = J[i];
         return;
     }
@@ -571,7 +593,6 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
     setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
-    if (c.bounded && !c.identity) return -2;   // bounded MALA is restated for M = I only
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -592,8 +613,14 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     for (long it = 0; it < n_total; ++it) {
         rng.normals(it, d, z.data());                 // :150
         mala_mean(c, eps, prev.data(), mean_prev.data(), Jprev.data());
-        if (c.bounded)   // :155-157: mean + ((eps*chol(J)) * sqrtM) * z, chol of the diagonal J = sqrt(J_ii), sqrtM = I
+        if (c.bounded && c.identity)   // :155-157: mean + ((eps*chol(J)) * sqrtM) * z, chol of the diagonal J = sqrt(J_ii), sqrtM = I
             for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + (std::sqrt(Jprev[i]) * eps) * z[i];
+        else if (c.bounded) {          // dense sqrtM: entries (sqrt(J_ii) * S_ij) * eps, times z (j increasing)
+            for (int i = 0; i < d; ++i) t[i] = 0.0;
+            for (int j = 0; j < d; ++j)
+                for (int i = 0; i < d; ++i) t[i] += ((std::sqrt(Jprev[i]) * c.S[size_t(j) * d + i]) * eps) * z[j];
+            for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + t[i];
+        }
         else if (c.identity) for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + eps * z[i];   // :159
         else { gemv_scaled(c.S, d, eps, z.data(), t.data()); for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + t[i]; }
         double prop_LP = box_logp(c, cur.data());  // :162
@@ -604,8 +631,21 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
             // both densities use Sigma = eps^2 * J(prop) * M (mala.ipp:55-56); M = I -> diagonal entries J_ii * e2
             if (cfg->mala_exact_dmvnorm) {
                 vec Sg(size_t(d) * d, 0.0);
-                for (int i = 0; i < d; ++i) Sg[size_t(i) * d + i] = Jprop[i] * e2;
+                if (c.identity) for (int i = 0; i < d; ++i) Sg[size_t(i) * d + i] = Jprop[i] * e2;
+                else   // (J(prop) * M) * e2: NOT symmetric; LLT reads its lower triangle, the QR solve the whole matrix — as the reference does
+                    for (int j = 0; j < d; ++j)
+                        for (int i = 0; i < d; ++i) Sg[size_t(j) * d + i] = (Jprop[i] * c.M[size_t(j) * d + i]) * e2;
                 adj = dmvnorm_log(prev.data(), mean_prop.data(), Sg, d, c.sum_mode) - dmvnorm_log(cur.data(), mean_prev.data(), Sg, d, c.sum_mode);
+            } else if (!c.identity) {
+                // cancelled form with a dense M: Sigma^-1 r = M^-1 (r / (J(prop) e2)); the two log-dets are the same number
+                vec wv(d);
+                for (int i = 0; i < d; ++i) { r[i] = prev[i] - mean_prop[i]; wv[i] = r[i] / (Jprop[i] * e2); }
+                gemv_plain(c.Minv, d, wv.data(), t.data());
+                const double q1 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
+                for (int i = 0; i < d; ++i) { r[i] = cur[i] - mean_prev[i]; wv[i] = r[i] / (Jprop[i] * e2); }
+                gemv_plain(c.Minv, d, wv.data(), t.data());
+                const double q2 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
+                adj = -0.5 * (q1 - q2);
             } else {
                 for (int i = 0; i < d; ++i) { r[i] = prev[i] - mean_prop[i]; t[i] = r[i] / (Jprop[i] * e2); }
                 const double q1 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
@@ -629,6 +669,7 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
         }
         const double comp = std::min(0.01, prop_LP - prev_LP + adj);   // src/mala.cpp:170
         const double u = rng.uniform(it, 0);                            // :171
+        note_margin(it, u, comp);
         const bool acc = u < std::exp(comp);                            // :173
         if (acc) { prev = cur; prev_LP = prop_LP; }
         if (it >= cfg->n_burnin) {
@@ -681,6 +722,7 @@ static int run_rwmh(const oracle_cfg_t* cfg, const double* x0, double* draws, do
         if (!std::isfinite(prop_LP)) prop_LP = -std::numeric_limits<double>::infinity();   // :129-131
         const double comp = std::min(0.0, prop_LP - prev_LP);   // :135
         const double u = rng.uniform(it, 0);              // :136
+        note_margin(it, u, comp);
         const bool acc = u < std::exp(comp);              // :138
         if (acc) { prev = cur; prev_LP = prop_LP; }
         if (it >= cfg->n_burnin) {
@@ -956,6 +998,7 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
         const double prop_K = otgt::dot(p.data(), t.data(), d, c.sum_mode) / 2.0;               // :246
         const double comp = std::min(0.01, -(prop_U + prop_K) + (prev_U + prev_K));             // :250
         const double u = rng.uniform(it, 0);
+        note_margin(it, u, comp);
         const bool acc = u < std::exp(comp);
         if (acc) { prev = cur; prev_U = prop_U; prevG = newG; invPrev = invNew; prevdG = newdG; }   // :254-261
         if (it >= cfg->n_burnin) {

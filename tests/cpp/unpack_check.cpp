@@ -1,5 +1,6 @@
-// CPU-only check of the draws_out adapter of include/mcmc_b200.hpp: chain-major [C][n_keep][d] -> one column-major
-// n_keep x d Mat_t per chain, tiled and multi-threaded, against the obvious double loop.
+// CPU-only check of the draws_out adapter of include/mcmc_b200.hpp: the library returns [C][d][n_keep] (every chain's block
+// is the reference's column-major n_keep x d Mat_t, SURVEY Q23, transposed on the device); unpack() copies the blocks into
+// the Cube_t's matrices, chains spread over host threads.
 #include <cstdio>
 #include <random>
 #include <vector>
@@ -16,21 +17,14 @@ int main()
         std::vector<double> buf(C * T * d);
         for (double& v : buf) v = u(gen);
         mcmc::Cube_t cube;
-        mcmc::b200_detail::unpack(buf, C, T, d, nullptr, &cube);
+        mcmc::b200_detail::unpack(buf.data(), C, T, d, cube);
         if (cube.n_mat() != C) { std::printf("FAIL n_mat\n"); return 1; }
         for (size_t c = 0; c < C; ++c) {
             const mcmc::Mat_t& m = cube.mat(c);
             if (size_t(m.rows()) != T || size_t(m.cols()) != d) { std::printf("FAIL shape\n"); return 1; }
             for (size_t t = 0; t < T; ++t)
                 for (size_t j = 0; j < d; ++j)
-                    if (m(t, j) != buf[(c * T + t) * d + j]) { std::printf("FAIL value C=%zu T=%zu d=%zu\n", C, T, d); return 1; }
-        }
-        if (C == 1) {
-            mcmc::Mat_t single;
-            mcmc::b200_detail::unpack(buf, 1, T, d, &single, nullptr);
-            for (size_t t = 0; t < T; ++t)
-                for (size_t j = 0; j < d; ++j)
-                    if (single(t, j) != buf[t * d + j]) { std::printf("FAIL single\n"); return 1; }
+                    if (m(t, j) != buf[(c * d + j) * T + t]) { std::printf("FAIL value C=%zu T=%zu d=%zu\n", C, T, d); return 1; }
         }
     }
     std::printf("unpack ok\n");

@@ -213,7 +213,7 @@ class Oracle:
         self.lib.oracle_target.restype = ctypes.c_double
 
     def run_chain(self, sampler, target_id, tdata, x0, st, seed=0, rng_mode=RNG_MT, tape=None, chain_id=0,
-                  sum_mode=SUM_SEQ, chol_mode=1, mala_exact=0, record_tape=0, want_logp=False):
+                  sum_mode=SUM_SEQ, chol_mode=1, mala_exact=0, record_tape=0, want_logp=False, want_margins=False):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         d = x0.size
         tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
@@ -231,12 +231,21 @@ class Oracle:
         draws = np.zeros((st["n_keep"], d))
         logp = np.zeros(st["n_keep"]) if want_logp else None
         res = _OracleRes()
-        rc = self.lib.oracle_run_chain(ctypes.byref(cfg), _ptr(x0), _ptr(draws), _ptr(logp), ctypes.byref(res))
+        margins = np.full(st["n_burnin"] + st["n_keep"], np.nan) if want_margins else None
+        if want_margins:   # u - exp(comp) of every accept test (HMC / MALA / RWMH / RM-HMC), see oracle.cpp note_margin
+            self.lib.oracle_set_margin_buffer(_ptr(margins), ctypes.c_long(margins.size))
+        try:
+            rc = self.lib.oracle_run_chain(ctypes.byref(cfg), _ptr(x0), _ptr(draws), _ptr(logp), ctypes.byref(res))
+        finally:
+            if want_margins:
+                self.lib.oracle_set_margin_buffer(None, ctypes.c_long(0))
         assert rc == 0, rc
         out = dict(draws=draws, n_accept=res.n_accept, tape_used=res.tape_used, final_step=res.final_step,
                    n_leapfrog=res.n_leapfrog)
         if want_logp:
             out["logp"] = logp
+        if want_margins:
+            out["margins"] = margins
         if record_tape:
             out["tape"] = rec[:min(record_tape, res.tape_used)]
         return out

@@ -91,3 +91,31 @@ def test_product_does_not_reference_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle_lib" not in txt and "liboracle" not in txt and "oracle/" not in txt.replace("oracle/oracle.cpp", "").replace(
                     "oracle/host_targets.hpp", ""), os.path.join(dirpath, f)
+
+
+def test_de_reference_stream_matches_the_oracle_tape(oracle):
+    """Host side of MCMCB200_RNG_MT19937_TAPE for mcmc::de (host_tape.cpp host_de_tape, no GPU needed): exactly the variates
+    the restated sampler — bit-identical to the unmodified src/de.cpp — consumes, in order."""
+    import numpy as np
+    import oracle_lib as ol
+    from mcmc_b200 import api
+    from test_oracle_vs_reference import _de_cases
+
+    for name, tid, tdata, x0, st, seed in _de_cases():
+        o = oracle.run_de(tid, tdata, x0, st, seed=seed, record_tape=2_000_000)
+        t = api.de_tape(seed, st["n_pop"], len(x0), st["n_burnin"] + st["n_keep"], st["par_b"])
+        assert t.size == o["tape_used"] and np.array_equal(t, o["tape"]), name
+
+
+def test_user_target_library_registers_without_a_gpu():
+    """examples/user_target/normal_raw.cu (a USER-defined functor + metric, built by mcmc_b200.build into its own shared
+    library) registers itself with libmcmc_b200.so at load time; the sampler kernels themselves need a GPU."""
+    import os
+    from mcmc_b200 import api, build
+
+    assert os.path.exists(build.USER_EXAMPLE_LIB), "run __graft_entry__.build()"
+    api.load_user_library(build.USER_EXAMPLE_LIB)
+    tid = api.target_id("normal_raw")
+    assert tid >= 64
+    assert api.load().mcmcb200_target_data_len(tid, 2) == 1 and api.load().mcmcb200_target_data_len(tid, 3) == -1
+    assert api.metric_lookup("funnel_softabs") == (api.TARGET_FUNNEL, 2)

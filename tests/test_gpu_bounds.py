@@ -177,12 +177,43 @@ def test_bounds_error_paths(engine):
     with pytest.raises(api.McmcB200Error) as e:   # lower >= upper
         engine.hmc(x0, "iso_gauss", n_keep=2, n_burnin=0, lower_bounds=np.ones(4), upper_bounds=np.ones(4))
     assert e.value.code == api.ERR_INVALID_ARG
-    with pytest.raises(api.McmcB200Error) as e:   # bounds + dense mass matrix
-        engine.hmc(x0, "iso_gauss", n_keep=2, n_burnin=0, lower_bounds=np.zeros(4), precond_mat=np.eye(4) * 2)
-    assert e.value.code == api.ERR_UNSUPPORTED
-    with pytest.raises(api.McmcB200Error) as e:
-        engine.mala(x0, "iso_gauss", n_keep=2, n_burnin=0, lower_bounds=np.zeros(4), precond_mat=np.eye(4) * 2)
-    assert e.value.code == api.ERR_UNSUPPORTED
     with pytest.raises(api.McmcB200Error) as e:   # wide kernels carry no bounds
         engine.hmc(np.full((2, 1024), 0.5), "iso_gauss", n_keep=2, n_burnin=0, lower_bounds=np.zeros(1024))
     assert e.value.code == api.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("d", [3, 6, 40, 130])
+def test_bounds_together_with_a_dense_precond_mat(engine, oracle, reference, d):
+    """vals_bound AND precond_mat (reachable in the reference: src/hmc.cpp:107-122, src/mala.cpp:97-125, mala.ipp:55-56, src/nuts.cpp:111-154):
+    the kick uses J o grad and the drift (eps M^-1) p in HMC / NUTS; MALA's drift is ((eps^2 J) M) grad / 2, its noise
+    ((eps chol J) sqrtM) z and both proposal densities use eps^2 J(proposal) M.  STRICT on the reference's stream and FAST on
+    Philox against the oracle (warp order); the oracle itself is bit-identical to the unmodified reference on these cases."""
+    rng = np.random.default_rng(100 + d)
+    C = 5
+    lo, hi = _mixed_bounds(d, rng)
+    x0 = _start(C, d, lo, hi, rng)
+    a = rng.normal(size=(d, d))
+    M = a @ a.T / d + 0.6 * np.eye(d)
+    w = np.exp(rng.uniform(-0.7, 0.7, size=d))
+    nk = 25 if d <= 40 else 10
+    for sampler, st in ((ol.HMC, ol.Settings(n_burnin=3, n_keep=nk, n_leap_steps=4, step_size=0.15, precond=M, lower_bounds=lo, upper_bounds=hi)),
+                        (ol.MALA, ol.Settings(n_burnin=3, n_keep=nk, step_size=0.2, precond=M, lower_bounds=lo, upper_bounds=hi))):
+        if d <= 6:   # the oracle's restatement == the unmodified reference, bit for bit (bounded + dense M)
+            ref, acc, _ = reference.run_chains(sampler, ol.TGT_DIAG_GAUSS, w, x0, st, 50)
+            for c in range(C):
+                o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=50 + c, rng_mode=ol.RNG_MT)
+                assert np.array_equal(o["draws"], ref[c]) and o["n_accept"] == acc[c]
+        r = _engine_run(engine, sampler, ol.TGT_DIAG_GAUSS, w, x0, st, engine.api.ARITH_STRICT, rng_mode=engine.api.RNG_MT19937_TAPE, seed=50,
+                        precond_mat=M)
+        for c in range(C):
+            o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=50 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP)
+            assert np.abs(r["draws"][c] - o["draws"]).max() <= TOL, (sampler, d, c, np.abs(r["draws"][c] - o["draws"]).max())
+            assert r["n_accept"][c] == o["n_accept"], (sampler, d, c)
+        rf = _engine_run(engine, sampler, ol.TGT_DIAG_GAUSS, w, x0, st, engine.api.ARITH_FAST, rng_mode=engine.api.RNG_PHILOX, seed=51, chain_offset=3,
+                         precond_mat=M)
+        for c in range(C):
+            o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=51, rng_mode=ol.RNG_PHILOX, chain_id=3 + c, sum_mode=ol.SUM_WARP)
+            assert np.abs(rf["draws"][c] - o["draws"]).max() <= TOL and rf["n_accept"][c] == o["n_accept"], (sampler, d, c)
+    if d <= 40:   # NUTS, no adaptation (contract tolerance), oracle tape protocol
+        st = ol.Settings(n_burnin=2, n_keep=12, step_size=0.12, n_adapt_draws=0, max_tree_depth=6, precond=M, lower_bounds=lo, upper_bounds=hi)
+        _run_pair(engine, oracle, ol.TGT_DIAG_GAUSS, "diag_gauss", w, x0, st, 60, engine.api.ARITH_STRICT, precond=M)

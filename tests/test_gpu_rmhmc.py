@@ -5,6 +5,7 @@ import pytest
 
 import oracle_lib as ol
 from test_gpu_hmc import TOL
+from parity_util import assert_tracks_or_flips_at_threshold
 
 pytestmark = pytest.mark.gpu
 
@@ -38,10 +39,16 @@ def test_many_seeds_vs_reference(engine, reference, oracle, L, eps):
     r = engine.rmhmc(x0, "normal_model", target_data=td, n_leap_steps=L, step_size=eps, n_burnin=10, n_keep=150,
                      rng_mode=engine.api.RNG_MT19937_TAPE, seed=500, arith=engine.api.ARITH_STRICT, want_logp=True)
     # the Normal model is nonlinear: a rounding-level difference (device log vs glibc log) can in principle flip an
-    # accept decision and decorrelate one chain; require all but at most one chain to track to the contract tolerance
-    linf = np.abs(r["draws"] - ref).max(axis=(1, 2))
-    assert (linf <= TOL).sum() >= C - 1, np.sort(linf)[-3:]
-    assert (r["n_accept"] == acc).sum() >= C - 1
+    # accept decision.  Every chain must track the oracle (== the reference, bit for bit) to the contract tolerance, or leave
+    # its path at a draw whose accept margin |u - exp(comp)| is at rounding level (parity_util) — nothing else passes.
+    tracked = 0
+    for c in range(C):
+        o = oracle.run_chain(ol.RMHMC, ol.TGT_NORMAL_MODEL, td, x0[c], st, seed=500 + c, rng_mode=ol.RNG_MT, want_margins=True)
+        assert np.array_equal(o["draws"], ref[c]) and o["n_accept"] == acc[c]   # oracle == unmodified reference
+        if assert_tracks_or_flips_at_threshold(r["draws"][c], o, 10, TOL, "chain %d" % c):
+            assert r["n_accept"][c] == acc[c]
+            tracked += 1
+    assert tracked >= C - 1, tracked
     assert 0 < acc.min() and acc.max() < 150
 
 
@@ -52,12 +59,10 @@ def test_philox_mode_vs_oracle(engine, oracle):
     st = ol.Settings(n_burnin=5, n_keep=80, n_leap_steps=2, step_size=0.15)
     r = engine.rmhmc(x0, "normal_model", target_data=td, n_leap_steps=2, step_size=0.15, n_burnin=5, n_keep=80,
                      rng_mode=engine.api.RNG_PHILOX, seed=31337, chain_offset=7)
-    bad = 0
     for c in range(C):
-        o = oracle.run_chain(ol.RMHMC, ol.TGT_NORMAL_MODEL, td, x0[c], st, seed=31337, rng_mode=ol.RNG_PHILOX, chain_id=7 + c)
-        if np.abs(r["draws"][c] - o["draws"]).max() > TOL or r["n_accept"][c] != o["n_accept"]:
-            bad += 1
-    assert bad <= 1
+        o = oracle.run_chain(ol.RMHMC, ol.TGT_NORMAL_MODEL, td, x0[c], st, seed=31337, rng_mode=ol.RNG_PHILOX, chain_id=7 + c, want_margins=True)
+        if assert_tracks_or_flips_at_threshold(r["draws"][c], o, 5, TOL, "chain %d" % c):
+            assert r["n_accept"][c] == o["n_accept"]
     assert np.abs(r["draws"][0] - r["draws"][1]).max() > 1e-6  # distinct substreams
 
 
@@ -138,22 +143,27 @@ def test_funnel_rmhmc_vs_oracle_and_reference(engine, oracle, reference, d, L, e
     st = ol.Settings(n_burnin=2, n_keep=nk, n_leap_steps=L, step_size=eps, n_fp_steps=4, metric_id=metric_id)
     kw = dict(n_leap_steps=L, step_size=eps, n_fp_steps=4, n_burnin=2, n_keep=nk, want_logp=True, metric_id=metric_id)
     r = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_MT19937_TAPE, seed=900, arith=engine.api.ARITH_STRICT, **kw)
-    bad = 0
+    tracked = []
     for c in range(C):
-        o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=900 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP, want_logp=True)
-        ok = _close(r["draws"][c], o["draws"]) and r["n_accept"][c] == o["n_accept"] and _close(r["logp"][c], o["logp"], 1e-9)
-        bad += 0 if ok else 1
-    assert bad <= 1
+        o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=900 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP, want_logp=True,
+                             want_margins=True)
+        ok = assert_tracks_or_flips_at_threshold(r["draws"][c], o, 2, TOL, "strict d=%d chain %d" % (d, c))
+        if ok:
+            assert r["n_accept"][c] == o["n_accept"] and _close(r["logp"][c], o["logp"], 1e-9)
+        tracked.append(ok)
+    assert sum(tracked) >= C - 1
     assert 0 < r["n_accept"].sum()
     if d <= 8:
         ref, acc, _ = reference.run_chains(ol.RMHMC, ol.TGT_FUNNEL, None, x0, st, 900)
-        assert sum(_close(r["draws"][c], ref[c]) for c in range(C)) >= C - 1 and (r["n_accept"] == acc).sum() >= C - 1
+        for c in range(C):
+            if tracked[c]:
+                assert _close(r["draws"][c], ref[c]) and r["n_accept"][c] == acc[c]
     rf = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_PHILOX, seed=901, chain_offset=11, arith=engine.api.ARITH_FAST, **kw)
-    bad = 0
     for c in range(C):
-        o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=901, rng_mode=ol.RNG_PHILOX, chain_id=11 + c, sum_mode=ol.SUM_WARP)
-        bad += 0 if (_close(rf["draws"][c], o["draws"]) and rf["n_accept"][c] == o["n_accept"]) else 1
-    assert bad <= 1
+        o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=901, rng_mode=ol.RNG_PHILOX, chain_id=11 + c, sum_mode=ol.SUM_WARP,
+                             want_margins=True)
+        if assert_tracks_or_flips_at_threshold(rf["draws"][c], o, 2, TOL, "fast d=%d chain %d" % (d, c)):
+            assert rf["n_accept"][c] == o["n_accept"]
 
 
 def test_funnel_other_samplers_and_unsupported_combinations(engine, oracle):
@@ -204,3 +214,43 @@ def test_funnel_goldens(engine):
         assert r["n_accept"][0] == c["n_accept"], c["name"]
         seen += 1
     assert seen == 3
+
+
+@pytest.mark.parametrize("metric_id", [1, 2])
+def test_cta_kernel_matches_the_cube_kernel(engine, monkeypatch, metric_id):
+    """FAST arithmetic runs one CTA per chain with the metric algebra in shared memory and the derivative cube replaced by the
+    metric's closed-form contractions (rmhmc_cta.cu); MCMCB200_RMHMC_CTA=0 forces the warp-per-chain cube kernel
+    (rmhmc_general.cu).  Same algorithm, different operation order: <= 1e-10 and identical accept counts, Philox and tape,
+    ragged and full n_dim, both chol modes."""
+    rng = np.random.default_rng(50 + metric_id)
+    for d, L, eps in ((2, 2, 0.1), (7, 3, 0.08), (33, 2, 0.05), (64, 3, 0.02)):
+        x0 = _funnel_start(12, d, rng)
+        for mode, chol in ((engine.api.RNG_PHILOX, 1), (engine.api.RNG_MT19937_TAPE, 0)):
+            kw = dict(n_leap_steps=L, step_size=eps, n_fp_steps=4, n_burnin=2, n_keep=10, want_logp=True, metric_id=metric_id, rng_mode=mode, seed=77,
+                      chol_mode=chol)
+            a = engine.rmhmc(x0, "funnel", **kw)
+            monkeypatch.setenv("MCMCB200_RMHMC_CTA", "0")
+            b = engine.rmhmc(x0, "funnel", **kw)
+            monkeypatch.delenv("MCMCB200_RMHMC_CTA")
+            assert _close(a["draws"], b["draws"]), (d, mode, np.nanmax(np.abs(a["draws"] - b["draws"])))
+            assert np.array_equal(a["n_accept"], b["n_accept"]) and _close(a["logp"], b["logp"], 1e-8)
+            assert a["n_accept"].sum() > 0
+
+
+def test_c5_full_size(engine, monkeypatch):
+    """BASELINE config 5 at full size: RM-HMC, Neal's funnel d = 64, SoftAbs metric, 2048 chains, L = 5, n_fp = 5 (a few draws).
+    Every chain stays finite, the acceptance rate is in the range the reference's sampler shows at this step size, and a
+    subset of the chains agrees with the cube kernel draw for draw."""
+    rng = np.random.default_rng(5)
+    d, C = 64, 2048
+    x0 = _funnel_start(C, d, rng)
+    kw = dict(n_leap_steps=5, step_size=0.01, n_fp_steps=5, n_burnin=1, n_keep=5, rng_mode=engine.api.RNG_PHILOX, seed=5, metric_id=2)
+    r = engine.rmhmc(x0, "funnel", **kw)
+    assert np.isfinite(r["draws"]).all()
+    acc = r["n_accept"].mean() / 5
+    assert 0.2 < acc < 0.95, acc
+    monkeypatch.setenv("MCMCB200_RMHMC_CTA", "0")
+    sub = engine.rmhmc(x0[1000:1024], "funnel", chain_offset=1000, **kw)
+    monkeypatch.delenv("MCMCB200_RMHMC_CTA")
+    assert np.abs(sub["draws"] - r["draws"][1000:1024]).max() <= TOL and np.array_equal(sub["n_accept"], r["n_accept"][1000:1024])
+    print("C5 full size: kernel %.1f ms for 6 draws (%.2f ms/draw), acceptance %.2f" % (r["kernel_ms"], r["kernel_ms"] / 6, acc))

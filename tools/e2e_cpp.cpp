@@ -1,0 +1,49 @@
+// End-to-end timing of the REFERENCE-SHAPED C++ call (bench.py's e2e_cpp leg): the C2 job through
+//   mcmc::hmc(const Mat_t& initial_vals /* one column per chain */, kernel, Cube_t& draws_out, data, settings)
+// of include/mcmc_b200.hpp — what a user of the reference who switches headers actually calls.  Inside the timed region:
+// H2D of initial_vals, the kernel, the device transpose to the reference's column-major Mat_t layout, the D2H of draws_out
+// into page-locked staging and the copy into the Cube_t's matrices.  Wall clock (the call is blocking), best-of and mean.
+// usage: e2e_cpp <n_chains> <n_burnin> <n_keep> <device> <steps>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "mcmc_b200.hpp"
+
+int main(int argc, char** argv)
+{
+    const size_t C = argc > 1 ? std::strtoul(argv[1], nullptr, 10) : 4096, nb = argc > 2 ? std::strtoul(argv[2], nullptr, 10) : 100,
+                 nk = argc > 3 ? std::strtoul(argv[3], nullptr, 10) : 1000;
+    const int device = argc > 4 ? std::atoi(argv[4]) : 0, steps = argc > 5 ? std::atoi(argv[5]) : 3;
+    const size_t d = 128;
+    mcmc::Mat_t x0(d, C);
+    for (size_t c = 0; c < C; ++c)
+        for (size_t j = 0; j < d; ++j) x0(j, c) = std::sin(0.37 * double(c) + 0.11 * double(j));
+    mcmc::algo_settings_t s;
+    s.rng_seed_value = 12345;
+    s.hmc_settings.n_burnin_draws = nb;
+    s.hmc_settings.n_keep_draws = nk;
+    s.hmc_settings.n_leap_steps = 10;
+    s.hmc_settings.step_size = 0.1;
+    s.b200.rng_mode = MCMCB200_RNG_PHILOX;
+    s.b200.device = device;
+    double best = 1e30, sum = 0.0, check = 0.0;
+    for (int it = 0; it < steps + 1; ++it) {   // the first call is the warm-up (module load, allocations)
+        mcmc::Cube_t draws;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (!mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) {
+            std::fprintf(stderr, "mcmc::hmc failed: %s\n", mcmc::last_error());
+            return 1;
+        }
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (it > 0) { best = ms < best ? ms : best; sum += ms; }
+        check = draws.mat(C - 1)(nk - 1, d - 1);
+    }
+    const double mean = sum / steps, n_draws = double(C) * double(nb + nk);
+    std::printf("{\"value\": %.6e, \"unit\": \"draws/s\", \"ms_per_step\": %.3f, \"best_ms\": %.3f, \"steps\": %d, \"accept_rate\": %.4f, "
+                "\"h2d_bytes_per_step\": %zu, \"d2h_bytes_per_step\": %zu, \"last_value\": %.17g, "
+                "\"api\": \"mcmc::hmc(Mat_t, registered_kernel, Cube_t&, void*, algo_settings_t&) of include/mcmc_b200.hpp; wall clock of the blocking call\"}\n",
+                n_draws / (mean * 1e-3), mean, best, steps, double(s.hmc_settings.n_accept_draws) / double(nk), C * d * 8, C * nk * d * 8 + C * 8, check);
+    return 0;
+}
