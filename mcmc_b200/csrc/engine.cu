@@ -592,6 +592,15 @@ static int mala_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng
                       mcmcb200_output_t* out)
 {
     if (!st) { set_error("null settings"); return MCMCB200_ERR_INVALID_ARG; }
+    if (pr && pr->vals_bound && st->precond_mat) {
+        // The reference then evaluates both proposal densities with the covariance eps^2 J(proposal) M (mala.ipp:55-56), which is
+        // not symmetric: dmvnorm's LLT log-det reads its lower triangle and turns NaN whenever that is not positive definite, and
+        // min(0.01, NaN) = 0.01 accepts the proposal.  Reproducing that needs an O(d^3) factorisation per draw and chain only to
+        // detect the NaN; the device path refuses the combination instead of sampling something else.  (HMC and NUTS take
+        // bounds together with a precond_mat: there the mass matrix and the Jacobian do not mix.)
+        set_error("mala: vals_bound together with precond_mat is not supported on the device path");
+        return MCMCB200_ERR_UNSUPPORTED;
+    }
     Staged s;
     // dense quadratic targets with M = I run chain-batched (one fp64 tensor-core GEMM per draw for all chains) when the
     // dimension is beyond the register-resident kernels or there are enough chains to fill GEMM tiles
@@ -813,6 +822,8 @@ static int nuts_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng
     if (const char* e = std::getenv("MCMCB200_NUTS_COOP")) a.coop = (e[0] == '1');
     a.coop_batch = 6;   // measured on B200 (C4 shape, 1184 chains x 40 draws): 2 -> 456 ms, 4 -> 332, 6 -> 314, 8 -> 332
     if (const char* e = std::getenv("MCMCB200_NUTS_BATCH")) a.coop_batch = std::atoi(e) > 0 ? std::atoi(e) : 1;
+    a.coop_dmma = true;
+    if (const char* e = std::getenv("MCMCB200_NUTS_DMMA")) a.coop_dmma = (e[0] != '0');
     a.t_begin = 0;
     a.t_end = n_total;
     a.save_state = false;

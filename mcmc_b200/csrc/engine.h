@@ -20,8 +20,9 @@ constexpr int MCMCB200_TARGET_USER = 1000;   // id under which a user's translat
 #endif
 #define MCMCB200_EPL_CASE(n, expr)                                          \
     case n:                                                                 \
-        if constexpr (n <= MCMCB200_USER_MAX_EPL) { return expr; }          \
-        else { set_error("n_dim needs %d elements per lane; this build stops at %d", n, MCMCB200_USER_MAX_EPL); return MCMCB200_ERR_UNSUPPORTED; }
+        if constexpr (n <= MCMCB200_USER_MAX_EPL && n <= target_max_epl<T>::value) { return expr; }          \
+        else { set_error("n_dim needs %d elements per lane; this target / build stops at %d", n,          \
+                         MCMCB200_USER_MAX_EPL < target_max_epl<T>::value ? MCMCB200_USER_MAX_EPL : target_max_epl<T>::value); return MCMCB200_ERR_UNSUPPORTED; }
 constexpr int MAX_EPL = 16;          // n_dim <= 64*MAX_EPL/2 = 512 in the register-resident kernels
 
 // everything below is DEVICE memory unless noted
@@ -77,6 +78,7 @@ struct NutsLaunch : CommonLaunch {
     long long work_stride;     // doubles per chain
     bool coop;                 // dense targets: 8 chains per CTA with cooperative gradients (nuts.cu)
     int coop_batch;            // requests that must be pending before busy warps attend a cooperative round
+    bool coop_dmma;            // FAST arithmetic: cooperative products on the fp64 tensor cores (DMMA); MCMCB200_NUTS_DMMA=0 keeps the scalar body
     // segmented runs (reference-stream mode drives the kernel draw by draw from the host): this launch performs draws
     // [t_begin, t_end); with t_begin > 0 the chain state is reloaded from the work area, with save_state it is parked there
     long long t_begin, t_end;

@@ -218,7 +218,9 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
 //     in shared memory and reloaded by a PREDICATED ld.shared into the same registers on a rejection, so neither
 //     path needs register moves; exp() is evaluated only in the thin band 1 + dH <= u;
 //   * burn-in and kept draws are separate loops (no per-draw store predicate, no carried row pointer).
-// LS = compile-time number of leapfrog steps (0 = runtime a.n_leap), UNR = draw-loop unroll (1 or 2).
+// LS = compile-time number of leapfrog steps that carry the slices of the next draw's variates (0 = none: runtime a.n_leap,
+// variates generated up front), UNR = draw-loop unroll (1 or 2), MORE = the trajectory continues after the LS unrolled steps
+// with a.n_leap - LS plain steps (so every trajectory length >= LS keeps the interleaved variate generation, not only LS).
 template <int EPL> __device__ __forceinline__ void restore_if(const double* home, int lane, double (&x)[EPL], bool pred)
 {
     const unsigned addr = static_cast<unsigned>(__cvta_generic_to_shared(home + 2 * lane));
@@ -240,7 +242,7 @@ template <int EPL> __device__ __forceinline__ void park(double* home, int lane, 
         asm volatile("st.shared.v2.f64 [%0], {%1, %2};" : : "r"(addr + m * 512), "d"(x[2 * m]), "d"(x[2 * m + 1]) : "memory");
 }
 
-template <class T, int EPL, int LS, int UNR>
+template <class T, int EPL, int LS, int UNR, bool MORE = false>
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc_pipe_kernel(const __grid_constant__ HmcLaunch a)
 {
     extern __shared__ double smem[];
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
             auto step = [&](int s) {
 #pragma unroll
                 for (int k = 0; k < EPL; ++k) x[k] = fma(eps, p[k], x[k]);
-                if (LS > 0 ? (s + 1 < LS) : (s + 1 < L)) {
+                if ((LS > 0 && !MORE) ? (s + 1 < LS) : (s + 1 < L)) {
                     T::template eval<EPL, false, false, true, false>(a.tdata, w, x, g);
                     kick_full<EPL, false, false>(p, g, g, eps);
                 }
@@ -306,6 +308,8 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, hmc_min_blocks(EPL)) hmc
                     bp.template slice<s, NS>(a.rng, rng_tab, zn, kn);
                     step(s);
                 });
+                if (MORE)
+                    for (int s = LS; s < L; ++s) step(s);
             } else {
                 for (int s = 0; s < L; ++s) step(s);
             }
@@ -368,11 +372,11 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool FT, bool B
     return MCMCB200_OK;
 }
 
-template <class T, int EPL, int LS> static int launch_pipe(const HmcLaunch& a)
+template <class T, int EPL, int LS, bool MORE = false> static int launch_pipe(const HmcLaunch& a)
 {
     const long long blocks = (a.n_chains + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;
     const size_t smem = (size_t)WARPS_PER_BLOCK * (T::needs_scratch ? 2 : 1) * a.d * sizeof(double);
-    auto kern = hmc_pipe_kernel<T, EPL, LS, 1>;   // UNR = 2 is slower on B200 (instruction cache): 2.33 vs 2.23 ms
+    auto kern = hmc_pipe_kernel<T, EPL, LS, 1, MORE>;   // UNR = 2 is slower on B200 (instruction cache): 2.33 vs 2.23 ms
     if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<(unsigned)blocks, WARPS_PER_BLOCK * 32, smem, a.stream>>>(a);
     MCMCB200_CUDA_TRY(cudaGetLastError());
@@ -392,7 +396,11 @@ template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch
         if (!DENSE_M && ft) {
             if (a.strict) return launch_one<T, EPL, false, true, RNG_PHILOX, true>(a);
             // production configuration: the software-pipelined kernel; the most common trajectory length is unrolled
-            if (a.n_leap == 10 && T::separable && EPL <= 8) return launch_pipe<T, EPL, 10>(a);   // EPL = 16: the unrolled loop outgrows the instruction cache (2.67 vs 2.55 ms)
+            if constexpr (T::separable && EPL <= 8) {   // EPL = 16: the unrolled loop outgrows the instruction cache (2.67 vs 2.55 ms)
+                if (a.n_leap == 10) return launch_pipe<T, EPL, 10>(a);
+                // any other trajectory length >= 5: the variates are interleaved with the first five steps, the rest run plain
+                if (a.n_leap >= 5) return launch_pipe<T, EPL, 5, true>(a);
+            }
             return launch_pipe<T, EPL, 0>(a);
         }
         return a.strict ? launch_one<T, EPL, DENSE_M, true, RNG_PHILOX, false>(a) : launch_one<T, EPL, DENSE_M, false, RNG_PHILOX, false>(a);

@@ -110,16 +110,23 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     const long long chain = (long long)blockIdx.x * NW + warp;
     const int d = a.d;
     const int dp = (d + 1) & ~1;
-    double* tscr = vsm + (size_t)warp * 2 * dp;
+    // FAST arithmetic, dense target, n_dim a multiple of 4 that fits one row per lane: the cooperative product runs as fp64
+    // tensor-core MMAs (coop_gemv_body_dmma); its operand layout needs 4 doubles of padding per chain and per matrix column
+    const bool coop_tma = COOP && (d % 2 == 0) && d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);
+    const bool coop_dmma = coop_tma && !STRICT && (d % 4 == 0) && a.coop_dmma;
+    const int cstride = 2 * dp + (coop_dmma ? 4 : 0);   // doubles between the staged vectors of consecutive chains
+    double* tscr = vsm + (size_t)warp * cstride;
     double* mscr = tscr + dp;
     typename std::conditional<COOP, CoopWarpCtx<NW>, WarpCtx>::type w;
     w.lane = lane; w.d = d; w.scr = tscr;
     if constexpr (COOP) {
         // dynamic shared memory: NW x (x, y) vectors, then (when the TMA path applies) two panel buffers and two mbarriers
-        w.warp = warp; w.coop_base = vsm; w.coop_stride = 2 * dp; w.phase = 0u; w.n_active = &n_active; w.want = &coop_want;
-        const bool tma = (d % 2 == 0) && d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);
-        w.panels = tma ? vsm + (size_t)NW * 2 * dp : nullptr;
-        w.mbar = tma ? reinterpret_cast<unsigned long long*>(w.panels + (size_t)2 * COOP_PANEL_COLS * d) : nullptr;
+        w.warp = warp; w.coop_base = vsm; w.coop_stride = cstride; w.phase = 0u; w.n_active = &n_active; w.want = &coop_want;
+        const bool tma = coop_tma;
+        w.dmma = coop_dmma ? 1 : 0;
+        w.panel_stride = coop_dmma ? d + 4 : d;
+        w.panels = tma ? vsm + (size_t)NW * cstride : nullptr;
+        w.mbar = tma ? reinterpret_cast<unsigned long long*>(w.panels + (size_t)2 * COOP_PANEL_COLS * w.panel_stride) : nullptr;
         if (tma) {
             if (threadIdx.x == 0) { mbar_init(w.mbar, 1); mbar_init(w.mbar + 1, 1); mbar_init_fence(); }
             __syncthreads();
@@ -535,9 +542,10 @@ template <class T, int EPL, bool DENSE_M, bool STRICT, int RNGM, bool BOX = fals
     if (T::dense_matrix && !BOX && !DENSE_M && a.coop) {   // dense target, M = I, many chains: cooperative gradients, 8 chains per CTA
         constexpr int NW = (T::dense_matrix && !BOX && !DENSE_M) ? 8 : WARPS_PER_BLOCK;
         const long long blocks = (a.n_chains + NW - 1) / NW;
-        const bool tma = (a.d % 2 == 0) && a.d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);   // same test as the kernel
-        const size_t smem = (size_t)NW * NUTS_TAB_SMEM * sizeof(NutsSummary) + (size_t)NW * 2 * dp * sizeof(double) +
-                            (tma ? (size_t)2 * COOP_PANEL_COLS * a.d * sizeof(double) + 16 : 0);
+        const bool tma = (a.d % 2 == 0) && a.d <= 32 * NW && ((reinterpret_cast<uintptr_t>(a.tdata) & 15) == 0);   // same tests as the kernel
+        const bool dmma = tma && !STRICT && (a.d % 4 == 0) && a.coop_dmma;
+        const size_t smem = (size_t)NW * NUTS_TAB_SMEM * sizeof(NutsSummary) + (size_t)NW * (2 * dp + (dmma ? 4 : 0)) * sizeof(double) +
+                            (tma ? (size_t)2 * COOP_PANEL_COLS * (a.d + (dmma ? 4 : 0)) * sizeof(double) + 16 : 0);
         auto kern = nuts_kernel<T, EPL, DENSE_M, STRICT, RNGM, BOX, NW>;
         if (smem > 16 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)blocks, NW * 32, smem, a.stream>>>(a);

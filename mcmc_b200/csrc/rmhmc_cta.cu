@@ -10,7 +10,7 @@
 //     funnel's SoftAbs metric (arrow Hessian => G = [[g11, w x~'], [w x~, fa I + P x~ x~']]) every D_i is a rank-structured
 //     matrix and the d contractions cost two GEMVs with A — O(d^2) instead of streaming a 2 MB cube per update (the cube
 //     kernel moved 114 MB of DRAM traffic per chain-draw at d = 64; this one keeps the chain's whole state on chip).
-//   * Matrices: two d x (d|1) buffers in shared memory (leading dimension odd => rows AND columns are conflict-free):
+//   * Matrices: two d-column buffers in shared memory with an even leading dimension d + 2 (row pairs move as 128-bit words):
 //     `Ainv0` = G_prev^-1 for the whole draw, `W` = scratch in which a metric is built and inverted IN PLACE (Gauss-Jordan
 //     with partial pivoting, 2 d^3 flop, log|det| from the pivots) — also used for the draw's Cholesky factor.  G at the
 //     current / proposed point is parked in the chain's small global area (2 d^2 doubles) only for the next draw's Cholesky.
@@ -124,14 +124,24 @@ struct FunnelFisherCta {   // G = diag(1/9 + (d-1)/2, e^-v, ..., e^-v); dG/dv = 
     }
 };
 
-// ---- CTA-wide dense algebra on a shared d x d matrix with leading dimension ld ------------------------------------
-// In-place inverse by Gauss-Jordan elimination with partial pivoting; returns log|det| (sum of log|pivot|; the sign is
-// ignored: the metrics are positive definite).  piv: d ints of shared memory.  A zero / NaN pivot propagates NaN like the
-// reference's LU does.
-__device__ double rc_inverse_inplace(double* W, int d, int ld, int* piv, double* red)
+// ---- CTA-wide dense algebra on a shared d x d matrix with leading dimension ld (even, >= d + 1) ---------------------
+// In-place inverse by Gauss-Jordan elimination with partial pivoting (2 d^3 flop).  Thread (rp, cg) = (t % 32, t / 32) owns
+// the row PAIR (2 rp, 2 rp + 1) in a contiguous block of columns: one 128-bit shared load brings both rows of a column, one
+// brings two entries of the pivot row, so the rank-1 update costs ~2.3 instructions per multiply-add (the first version,
+// one row per thread with 64-bit accesses and per-element special cases, needed 11 and was issue-bound).  There are no
+// special rows inside the update: the pivot row is exchanged physically first, and its own scaling is folded into the
+// update by giving it the multiplier pivot - 1 (W(k,j) - (pivot - 1) W(k,j) / pivot = W(k,j) / pivot).
+// piv: d ints; rc: 2 (RC_MAXD + 2) doubles (the scaled pivot row and the multiplier column), 16-byte aligned.
+// A zero / NaN pivot propagates NaN like the reference's LU does.
+__device__ void rc_inverse_inplace(double* W, int d, int ld, int* piv, double* rc)
 {
-    const int t = threadIdx.x, i = t & 63, jpar = t >> 6;
-    double logdet = 0.0;
+    double* rowbuf = rc;
+    double* colbuf = rc + RC_MAXD + 2;
+    const int t = threadIdx.x, rp = t & 31, cg = t >> 5;
+    const int i0 = 2 * rp;
+    const bool rows_ok = i0 < d;
+    const int cb = ((d + 7) / 8) * 2;                 // columns per thread group (even)
+    const int jb = cg * cb, je = (jb + cb < d) ? jb + cb : d;
     for (int k = 0; k < d; ++k) {
         // pivot: first maximum of |W(r, k)|, r >= k (warp 0; a NaN never wins, a NaN at (k,k) keeps r = k)
         if (t < 32) {
@@ -158,27 +168,45 @@ __device__ double rc_inverse_inplace(double* W, int d, int ld, int* piv, double*
         }
         rc_sync();
         const int p = piv[k];
-        if (p != k) {   // swap rows k and p (threads over columns)
-            for (int j = t; j < d; j += RC_THREADS) {
-                const double a = W[(size_t)j * ld + k], b = W[(size_t)j * ld + p];
-                W[(size_t)j * ld + k] = b;
-                W[(size_t)j * ld + p] = a;
+        if (p != k) {   // exchange rows k and p (threads over columns)
+            if (t < d) {
+                const double a = W[(size_t)t * ld + k], b = W[(size_t)t * ld + p];
+                W[(size_t)t * ld + k] = b;
+                W[(size_t)t * ld + p] = a;
             }
             rc_sync();
         }
         const double pv = W[(size_t)k * ld + k];
-        logdet += log(fabs(pv));
         const double rinv = 1.0 / pv;
-        const double f = (i < d) ? W[(size_t)k * ld + i] : 0.0;   // column k of this thread's row, before it is overwritten
+        if (t < d) rowbuf[t] = W[(size_t)t * ld + k] * rinv;                                  // scaled pivot row
+        else if (t >= 64 && t - 64 < d + 1) {
+            const int r = t - 64;
+            colbuf[r] = (r == k) ? pv - 1.0 : ((r < d) ? W[(size_t)k * ld + r] : 0.0);        // multipliers (see above); padding row: 0
+        }
         rc_sync();
-        // row k: W(k, j) = W(k, j) / pv (j != k), W(k, k) = 1 / pv
-        for (int j = t; j < d; j += RC_THREADS) W[(size_t)j * ld + k] = (j == k) ? rinv : W[(size_t)j * ld + k] * rinv;
-        rc_sync();
-        // rows i != k: W(i, j) -= f * W(k, j) (j != k), W(i, k) = -f / pv
-        if (i < d && i != k) {
-            for (int j = jpar; j < d; j += 2) {
-                const double rk = W[(size_t)j * ld + k];
-                W[(size_t)j * ld + i] = (j == k) ? -f * rinv : fma(-f, rk, W[(size_t)j * ld + i]);
+        if (rows_ok) {
+            const double f0 = colbuf[i0], f1 = colbuf[i0 + 1];
+            int j = jb;
+            for (; j + 1 < je; j += 2) {
+                const double2 r2 = *reinterpret_cast<const double2*>(rowbuf + j);
+                double2 wa = *reinterpret_cast<double2*>(W + (size_t)j * ld + i0);
+                double2 wb = *reinterpret_cast<double2*>(W + (size_t)(j + 1) * ld + i0);
+                wa.x = fma(-f0, r2.x, wa.x); wa.y = fma(-f1, r2.x, wa.y);
+                wb.x = fma(-f0, r2.y, wb.x); wb.y = fma(-f1, r2.y, wb.y);
+                *reinterpret_cast<double2*>(W + (size_t)j * ld + i0) = wa;
+                *reinterpret_cast<double2*>(W + (size_t)(j + 1) * ld + i0) = wb;
+            }
+            if (j < je) {
+                const double r1 = rowbuf[j];
+                double2 wa = *reinterpret_cast<double2*>(W + (size_t)j * ld + i0);
+                wa.x = fma(-f0, r1, wa.x); wa.y = fma(-f1, r1, wa.y);
+                *reinterpret_cast<double2*>(W + (size_t)j * ld + i0) = wa;
+            }
+            if (k >= jb && k < je) {   // column k: 1 / pivot in the pivot row, -multiplier / pivot elsewhere
+                double2 wk;
+                wk.x = (i0 == k) ? rinv : -f0 * rinv;
+                wk.y = (i0 + 1 == k) ? rinv : -f1 * rinv;
+                *reinterpret_cast<double2*>(W + (size_t)k * ld + i0) = wk;
             }
         }
         rc_sync();
@@ -187,16 +215,14 @@ __device__ double rc_inverse_inplace(double* W, int d, int ld, int* piv, double*
     for (int k = d - 1; k >= 0; --k) {
         const int p = piv[k];
         if (p != k) {
-            for (int r = t; r < d; r += RC_THREADS) {
-                const double a = W[(size_t)k * ld + r], b = W[(size_t)p * ld + r];
-                W[(size_t)k * ld + r] = b;
-                W[(size_t)p * ld + r] = a;
+            if (t < d) {
+                const double a = W[(size_t)k * ld + t], b = W[(size_t)p * ld + t];
+                W[(size_t)k * ld + t] = b;
+                W[(size_t)p * ld + t] = a;
             }
             rc_sync();
         }
     }
-    (void)red;
-    return logdet;
 }
 
 // in-place lower Cholesky of the shared matrix (right-looking); the strict upper triangle keeps the input's entries — the
@@ -221,16 +247,17 @@ __device__ void rc_cholesky_inplace(double* W, int d, int ld)
 template <class T, class MC, int RNGM>
 __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
 {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
     __shared__ int piv[RC_MAXD];
     __shared__ double red[4];
+    __shared__ __align__(16) double rcbuf[2 * (RC_MAXD + 2)];
     __shared__ double sc_u, sc_lp;   // broadcast scalars (uniform, log-density)
     if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const long long chain = blockIdx.x;
     const int d = a.d;
-    const int ld = d | 1;
+    const int ld = (d + 2) & ~1;   // even (128-bit row-pair accesses), > d (one padding row), transposed reads at most 4-way conflicted
     const int dp = (d + 1) & ~1;
     double* Ainv0 = smem;                    // G_prev^-1, fixed during a draw
     double* W = Ainv0 + (size_t)d * ld;      // scratch matrix
@@ -280,12 +307,32 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
         const int i = t & 63;
         if (i < d) {
             double acc = 0.0;
-            if (t < 64) { for (int j = 0; j < d; ++j) acc = fma(Am[(size_t)j * ld + i], v[j], acc); y[i] = acc; }
-            else if (y2) { for (int j = 0; j < d; ++j) acc = fma(Am[(size_t)i * ld + j], v[j], acc); y2[i] = acc; }
+            double acc2 = 0.0;
+            int j = 0;
+            if (t < 64) {
+                for (; j + 1 < d; j += 2) { acc = fma(Am[(size_t)j * ld + i], v[j], acc); acc2 = fma(Am[(size_t)(j + 1) * ld + i], v[j + 1], acc2); }
+                if (j < d) acc = fma(Am[(size_t)j * ld + i], v[j], acc);
+                y[i] = acc + acc2;
+            } else if (y2) {
+                for (; j + 1 < d; j += 2) { acc = fma(Am[(size_t)i * ld + j], v[j], acc); acc2 = fma(Am[(size_t)i * ld + j + 1], v[j + 1], acc2); }
+                if (j < d) acc = fma(Am[(size_t)i * ld + j], v[j], acc);
+                y2[i] = acc + acc2;
+            }
         }
         rc_sync();
     };
     MC metric;
+    // log det G the way the reference takes it — 2 sum log diag(chol G) (core/log_det.hpp:35), NaN when G is not numerically
+    // positive definite, which the accept rule then treats like the reference does — for the metric `m` prepared at xm; W is
+    // used as scratch and holds G again on return
+    auto logdet_chol = [&](const MC& m, const double* xm) -> double {
+        rc_cholesky_inplace(W, d, ld);
+        const double s = rc_block_sum(t < d ? 2.0 * log(W[(size_t)t * ld + t]) : 0.0, red);
+        rc_sync();
+        m.build(xm, d, W, ld);
+        rc_sync();
+        return s;
+    };
     // out = (eps F)/2 at position y with momentum q, metric inverse Am evaluated at the point the metric object was prepared for
     auto mntm_update = [&](const double* y, const double* q, const double* Am, const MC& m, const double* xm, double* out) {
         target_at(y, false, true);
@@ -308,7 +355,8 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
     metric.build(xprev, d, W, ld);
     rc_sync();
     store_global(Gacc);
-    double logdet_prev = rc_inverse_inplace(W, d, ld, piv, red);
+    double logdet_prev = logdet_chol(metric, xprev);
+    rc_inverse_inplace(W, d, ld, piv, rcbuf);
     for (int k = t; k < d * ld; k += RC_THREADS) Ainv0[k] = W[k];
     MC metric_prev = metric;   // the start-of-trajectory metric (Q17) of every draw until an accept replaces it
     target_at(xprev, true, false);
@@ -363,7 +411,7 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
                 mw.prepare(wv, d);
                 mw.build(wv, d, W, ld);
                 rc_sync();
-                rc_inverse_inplace(W, d, ld, piv, red);
+                rc_inverse_inplace(W, d, ld, piv, rcbuf);
                 if (t < d) {
                     double acc = 0.0;
                     for (int j = 0; j < d; ++j) acc = fma(Ainv0[(size_t)j * ld + t] + W[(size_t)j * ld + t], heps * pv[j], acc);
@@ -378,8 +426,11 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
             metric_new.prepare(xcur, d);
             metric_new.build(xcur, d, W, ld);
             rc_sync();
-            if (s + 1 == a.n_leap) store_global(Gnew);   // only the end point's metric can become the next draw's G_prev
-            logdet_new = rc_inverse_inplace(W, d, ld, piv, red);
+            if (s + 1 == a.n_leap) {   // only the end point's metric can become the next draw's G_prev and enters the energy
+                store_global(Gnew);
+                logdet_new = logdet_chol(metric_new, xcur);
+            }
+            rc_inverse_inplace(W, d, ld, piv, rcbuf);
             have_new = true;
             mntm_update(xcur, pv, W, metric_new, xcur, wv);
             if (t < d) pv[t] = pv[t] + wv[t];
@@ -431,7 +482,7 @@ bool rmhmc_cta_applicable(int target_id, int metric_id, int d, bool strict, bool
 
 template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
 {
-    const int d = a.d, ld = d | 1, dp = (d + 1) & ~1;
+    const int d = a.d, ld = (d + 2) & ~1, dp = (d + 1) & ~1;
     const size_t smem = ((size_t)2 * d * ld + (size_t)16 * dp) * sizeof(double);
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

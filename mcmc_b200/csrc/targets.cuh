@@ -17,8 +17,15 @@
 
 #include "warp.cuh"
 
+#include <type_traits>
+
 namespace mcmcb200
 {
+
+// A functor whose n_dim is bounded may say so (static constexpr int max_epl = 2, 4, 8 or 16: n_dim <= 32 * max_epl); larger
+// tiles are then not instantiated for it (the 2-parameter Normal model would otherwise compile every tile width for nothing).
+template <class T, class = void> struct target_max_epl { static constexpr int value = 16; };
+template <class T> struct target_max_epl<T, std::void_t<decltype(T::max_epl)>> { static constexpr int value = T::max_epl; };
 
 // log pi = -1/2 |x|^2                       (SURVEY §8d C1/C2 target)
 struct IsoGauss {
@@ -130,6 +137,7 @@ struct LinReg {
 // 2-parameter Normal(mu, sigma) likelihood (examples/eigen/hmc_normal.cpp:44-76) on the sufficient
 // statistics data = {n, xbar, M2 = sum (x_k - xbar)^2}:  sum (x_k - mu)^2 = M2 + n (xbar - mu)^2.
 struct NormalModel {
+    static constexpr int max_epl = 2;   // n_dim = 2
     static constexpr bool needs_scratch = false;
     static constexpr bool dense_matrix = false;   // data starts with a d x d matrix applied through dense_matvec
     static constexpr bool separable = false;

@@ -629,23 +629,16 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
         double adj;
         if (c.bounded) {
             // both densities use Sigma = eps^2 * J(prop) * M (mala.ipp:55-56); M = I -> diagonal entries J_ii * e2
-            if (cfg->mala_exact_dmvnorm) {
+            if (cfg->mala_exact_dmvnorm || !c.identity) {
+                // (with a dense M there is no cancelled form that keeps the reference's behaviour: Sigma is not symmetric, the
+                //  LLT log-det of its lower triangle can be NaN — in BOTH densities — and then min(0.01, NaN) accepts; only the
+                //  literal evaluation reproduces that.  The device path refuses this combination.)
                 vec Sg(size_t(d) * d, 0.0);
                 if (c.identity) for (int i = 0; i < d; ++i) Sg[size_t(i) * d + i] = Jprop[i] * e2;
                 else   // (J(prop) * M) * e2: NOT symmetric; LLT reads its lower triangle, the QR solve the whole matrix — as the reference does
                     for (int j = 0; j < d; ++j)
                         for (int i = 0; i < d; ++i) Sg[size_t(j) * d + i] = (Jprop[i] * c.M[size_t(j) * d + i]) * e2;
                 adj = dmvnorm_log(prev.data(), mean_prop.data(), Sg, d, c.sum_mode) - dmvnorm_log(cur.data(), mean_prev.data(), Sg, d, c.sum_mode);
-            } else if (!c.identity) {
-                // cancelled form with a dense M: Sigma^-1 r = M^-1 (r / (J(prop) e2)); the two log-dets are the same number
-                vec wv(d);
-                for (int i = 0; i < d; ++i) { r[i] = prev[i] - mean_prop[i]; wv[i] = r[i] / (Jprop[i] * e2); }
-                gemv_plain(c.Minv, d, wv.data(), t.data());
-                const double q1 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
-                for (int i = 0; i < d; ++i) { r[i] = cur[i] - mean_prev[i]; wv[i] = r[i] / (Jprop[i] * e2); }
-                gemv_plain(c.Minv, d, wv.data(), t.data());
-                const double q2 = otgt::dot(r.data(), t.data(), d, c.sum_mode);
-                adj = -0.5 * (q1 - q2);
             } else {
                 for (int i = 0; i < d; ++i) { r[i] = prev[i] - mean_prop[i]; t[i] = r[i] / (Jprop[i] * e2); }
                 const double q1 = otgt::dot(r.data(), t.data(), d, c.sum_mode);

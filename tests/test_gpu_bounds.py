@@ -184,10 +184,10 @@ def test_bounds_error_paths(engine):
 
 @pytest.mark.parametrize("d", [3, 6, 40, 130])
 def test_bounds_together_with_a_dense_precond_mat(engine, oracle, reference, d):
-    """vals_bound AND precond_mat (reachable in the reference: src/hmc.cpp:107-122, src/mala.cpp:97-125, mala.ipp:55-56, src/nuts.cpp:111-154):
-    the kick uses J o grad and the drift (eps M^-1) p in HMC / NUTS; MALA's drift is ((eps^2 J) M) grad / 2, its noise
-    ((eps chol J) sqrtM) z and both proposal densities use eps^2 J(proposal) M.  STRICT on the reference's stream and FAST on
-    Philox against the oracle (warp order); the oracle itself is bit-identical to the unmodified reference on these cases."""
+    """vals_bound AND precond_mat (reachable in the reference: src/hmc.cpp:107-122, src/nuts.cpp:111-154): the kick uses J o grad
+    and the drift (eps M^-1) p.  STRICT on the reference's stream and FAST on Philox against the oracle (warp order); the
+    oracle itself is bit-identical to the unmodified reference on these cases.  MALA with bounds and a precond_mat is refused
+    on the device (engine.cu explains why); its restatement in the oracle is still pinned to the reference here."""
     rng = np.random.default_rng(100 + d)
     C = 5
     lo, hi = _mixed_bounds(d, rng)
@@ -196,24 +196,26 @@ def test_bounds_together_with_a_dense_precond_mat(engine, oracle, reference, d):
     M = a @ a.T / d + 0.6 * np.eye(d)
     w = np.exp(rng.uniform(-0.7, 0.7, size=d))
     nk = 25 if d <= 40 else 10
-    for sampler, st in ((ol.HMC, ol.Settings(n_burnin=3, n_keep=nk, n_leap_steps=4, step_size=0.15, precond=M, lower_bounds=lo, upper_bounds=hi)),
-                        (ol.MALA, ol.Settings(n_burnin=3, n_keep=nk, step_size=0.2, precond=M, lower_bounds=lo, upper_bounds=hi))):
-        if d <= 6:   # the oracle's restatement == the unmodified reference, bit for bit (bounded + dense M)
-            ref, acc, _ = reference.run_chains(sampler, ol.TGT_DIAG_GAUSS, w, x0, st, 50)
+    st = ol.Settings(n_burnin=3, n_keep=nk, n_leap_steps=4, step_size=0.15, precond=M, lower_bounds=lo, upper_bounds=hi)
+    stm = ol.Settings(n_burnin=3, n_keep=nk, step_size=0.2, precond=M, lower_bounds=lo, upper_bounds=hi)
+    if d <= 6:   # the oracle's restatement == the unmodified reference, bit for bit (bounded + dense M), HMC and MALA
+        for sampler, s_ in ((ol.HMC, st), (ol.MALA, stm)):
+            ref, acc, _ = reference.run_chains(sampler, ol.TGT_DIAG_GAUSS, w, x0, s_, 50)
             for c in range(C):
-                o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=50 + c, rng_mode=ol.RNG_MT)
-                assert np.array_equal(o["draws"], ref[c]) and o["n_accept"] == acc[c]
-        r = _engine_run(engine, sampler, ol.TGT_DIAG_GAUSS, w, x0, st, engine.api.ARITH_STRICT, rng_mode=engine.api.RNG_MT19937_TAPE, seed=50,
-                        precond_mat=M)
-        for c in range(C):
-            o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=50 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP)
-            assert np.abs(r["draws"][c] - o["draws"]).max() <= TOL, (sampler, d, c, np.abs(r["draws"][c] - o["draws"]).max())
-            assert r["n_accept"][c] == o["n_accept"], (sampler, d, c)
-        rf = _engine_run(engine, sampler, ol.TGT_DIAG_GAUSS, w, x0, st, engine.api.ARITH_FAST, rng_mode=engine.api.RNG_PHILOX, seed=51, chain_offset=3,
-                         precond_mat=M)
-        for c in range(C):
-            o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=51, rng_mode=ol.RNG_PHILOX, chain_id=3 + c, sum_mode=ol.SUM_WARP)
-            assert np.abs(rf["draws"][c] - o["draws"]).max() <= TOL and rf["n_accept"][c] == o["n_accept"], (sampler, d, c)
+                o = oracle.run_chain(sampler, ol.TGT_DIAG_GAUSS, w, x0[c], s_, seed=50 + c, rng_mode=ol.RNG_MT)
+                assert np.array_equal(o["draws"], ref[c]) and o["n_accept"] == acc[c], (sampler, c)
+    r = _engine_run(engine, ol.HMC, ol.TGT_DIAG_GAUSS, w, x0, st, engine.api.ARITH_STRICT, rng_mode=engine.api.RNG_MT19937_TAPE, seed=50, precond_mat=M)
+    for c in range(C):
+        o = oracle.run_chain(ol.HMC, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=50 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP)
+        assert np.abs(r["draws"][c] - o["draws"]).max() <= TOL, (d, c, np.abs(r["draws"][c] - o["draws"]).max())
+        assert r["n_accept"][c] == o["n_accept"], (d, c)
+    rf = _engine_run(engine, ol.HMC, ol.TGT_DIAG_GAUSS, w, x0, st, engine.api.ARITH_FAST, rng_mode=engine.api.RNG_PHILOX, seed=51, chain_offset=3, precond_mat=M)
+    for c in range(C):
+        o = oracle.run_chain(ol.HMC, ol.TGT_DIAG_GAUSS, w, x0[c], st, seed=51, rng_mode=ol.RNG_PHILOX, chain_id=3 + c, sum_mode=ol.SUM_WARP)
+        assert np.abs(rf["draws"][c] - o["draws"]).max() <= TOL and rf["n_accept"][c] == o["n_accept"], (d, c)
     if d <= 40:   # NUTS, no adaptation (contract tolerance), oracle tape protocol
-        st = ol.Settings(n_burnin=2, n_keep=12, step_size=0.12, n_adapt_draws=0, max_tree_depth=6, precond=M, lower_bounds=lo, upper_bounds=hi)
-        _run_pair(engine, oracle, ol.TGT_DIAG_GAUSS, "diag_gauss", w, x0, st, 60, engine.api.ARITH_STRICT, precond=M)
+        stn = ol.Settings(n_burnin=2, n_keep=12, step_size=0.12, n_adapt_draws=0, max_tree_depth=6, precond=M, lower_bounds=lo, upper_bounds=hi)
+        _run_pair(engine, oracle, ol.TGT_DIAG_GAUSS, "diag_gauss", w, x0, stn, 60, engine.api.ARITH_STRICT, precond=M)
+    with pytest.raises(engine.McmcB200Error) as e:
+        _engine_run(engine, ol.MALA, ol.TGT_DIAG_GAUSS, w, x0, stm, engine.api.ARITH_FAST, rng_mode=engine.api.RNG_PHILOX, seed=1, precond_mat=M)
+    assert e.value.code == engine.api.ERR_UNSUPPORTED

@@ -239,5 +239,11 @@ def test_wide_hmc_four_warps_per_chain(engine, oracle, d):
                        rng_mode=engine.api.RNG_PHILOX, seed=56, chain_offset=9)
         assert np.abs(r["draws"] - od).max() <= TOL and np.array_equal(r["n_accept"], oa)
     assert 0 < oa.max()
-    with pytest.raises(engine.McmcB200Error):  # dense targets are not separable across warps
-        engine.hmc(np.zeros((2, d)), "dense_gauss", target_data=np.eye(d), n_burnin=1, n_keep=1)
+    # dense targets are not separable across warps: beyond 512 elements they run chain-batched (hmc_batched.cu, FAST arithmetic,
+    # even n_dim); STRICT has no such path and is refused
+    with pytest.raises(engine.McmcB200Error):
+        engine.hmc(np.zeros((2, d)), "dense_gauss", target_data=np.eye(d), n_burnin=1, n_keep=1, arith=engine.api.ARITH_STRICT)
+    r = engine.hmc(x0, "dense_gauss", target_data=np.eye(d), n_leap_steps=6, step_size=eps, n_burnin=3, n_keep=15, rng_mode=engine.api.RNG_PHILOX,
+                   seed=56, chain_offset=9)
+    od, oa, _ = _oracle_chains(oracle, ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, 56, ol.RNG_PHILOX, ol.SUM_WARP, chain_offset=9)
+    assert np.abs(r["draws"] - od).max() <= TOL and np.array_equal(r["n_accept"], oa)   # precision matrix I == the iso-Gaussian

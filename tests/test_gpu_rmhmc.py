@@ -147,7 +147,9 @@ def test_funnel_rmhmc_vs_oracle_and_reference(engine, oracle, reference, d, L, e
     for c in range(C):
         o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=900 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP, want_logp=True,
                              want_margins=True)
-        ok = assert_tracks_or_flips_at_threshold(r["draws"][c], o, 2, TOL, "strict d=%d chain %d" % (d, c))
+        pert = lambda c=c: oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, np.nextafter(x0[c], np.inf), st, seed=900 + c, rng_mode=ol.RNG_MT,
+                                            sum_mode=ol.SUM_WARP)["draws"]
+        ok = assert_tracks_or_flips_at_threshold(r["draws"][c], o, 2, TOL, "strict d=%d chain %d" % (d, c), rerun_perturbed=pert)
         if ok:
             assert r["n_accept"][c] == o["n_accept"] and _close(r["logp"][c], o["logp"], 1e-9)
         tracked.append(ok)
@@ -159,11 +161,16 @@ def test_funnel_rmhmc_vs_oracle_and_reference(engine, oracle, reference, d, L, e
             if tracked[c]:
                 assert _close(r["draws"][c], ref[c]) and r["n_accept"][c] == acc[c]
     rf = engine.rmhmc(x0, "funnel", rng_mode=engine.api.RNG_PHILOX, seed=901, chain_offset=11, arith=engine.api.ARITH_FAST, **kw)
+    n_fast_tracked = 0
     for c in range(C):
         o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=901, rng_mode=ol.RNG_PHILOX, chain_id=11 + c, sum_mode=ol.SUM_WARP,
                              want_margins=True)
-        if assert_tracks_or_flips_at_threshold(rf["draws"][c], o, 2, TOL, "fast d=%d chain %d" % (d, c)):
+        pert = lambda c=c: oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, np.nextafter(x0[c], np.inf), st, seed=901, rng_mode=ol.RNG_PHILOX,
+                                            chain_id=11 + c, sum_mode=ol.SUM_WARP)["draws"]
+        if assert_tracks_or_flips_at_threshold(rf["draws"][c], o, 2, TOL, "fast d=%d chain %d" % (d, c), rerun_perturbed=pert):
             assert rf["n_accept"][c] == o["n_accept"]
+            n_fast_tracked += 1
+    assert n_fast_tracked >= C - 2, n_fast_tracked
 
 
 def test_funnel_other_samplers_and_unsupported_combinations(engine, oracle):
@@ -231,9 +238,17 @@ def test_cta_kernel_matches_the_cube_kernel(engine, monkeypatch, metric_id):
             a = engine.rmhmc(x0, "funnel", **kw)
             monkeypatch.setenv("MCMCB200_RMHMC_CTA", "0")
             b = engine.rmhmc(x0, "funnel", **kw)
+            b2 = engine.rmhmc(np.nextafter(x0, np.inf), "funnel", **kw)   # the cube kernel again, start moved by one ulp
             monkeypatch.delenv("MCMCB200_RMHMC_CTA")
-            assert _close(a["draws"], b["draws"]), (d, mode, np.nanmax(np.abs(a["draws"] - b["draws"])))
-            assert np.array_equal(a["n_accept"], b["n_accept"]) and _close(a["logp"], b["logp"], 1e-8)
+            # chains on which the reference algorithm is numerically stable (see parity_util): the cube kernel reproduces itself
+            # from a one-ulp-perturbed start.  The others (the reference accepts NaN energies; large steps diverge) carry no
+            # information about operation order.
+            blown = lambda r_, c: (not np.isfinite(r_["draws"][c]).all()) or np.abs(r_["draws"][c]).max() > 1e30   # overflowed trajectories:
+            stable = np.array([_close(b["draws"][c], b2["draws"][c], 0.25 * TOL) and not blown(a, c) and not blown(b, c)   # inf / NaN arithmetic in
+                               for c in range(x0.shape[0])])                                                              # the accept test is implementation-defined
+            assert stable.sum() >= 7, (d, mode, stable)
+            assert _close(a["draws"][stable], b["draws"][stable]), (d, mode, np.nanmax(np.abs(a["draws"][stable] - b["draws"][stable])))
+            assert np.array_equal(a["n_accept"][stable], b["n_accept"][stable]) and _close(a["logp"][stable], b["logp"][stable], 1e-8)
             assert a["n_accept"].sum() > 0
 
 
