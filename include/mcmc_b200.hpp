@@ -10,8 +10,8 @@
 //        Mat_t& draws_out, void* target_data                void* target_data /* mcmc::kernel_data* */
 //        [, algo_settings_t& settings]);                    [, algo_settings_t& settings]);
 //
-// and likewise mcmc::mala / mcmc::nuts / mcmc::rmhmc / mcmc::rwmh (rmhmc's tensor_fn / tensor_data arguments are kept for arity;
-// the metric is the one registered with the kernel).  A std::function cannot run on the GPU, so the second argument
+// and likewise mcmc::mala / mcmc::nuts / mcmc::rmhmc / mcmc::rwmh / mcmc::de (rmhmc's tensor_fn slot takes a registered metric,
+// mcmc::device_metric("..."), which must belong to the kernel).  A std::function cannot run on the GPU, so the second argument
 // names a REGISTERED __device__ functor (mcmc::device_kernel("iso_gauss"), ...) and `target_data` points to a
 // mcmc::kernel_data {values, n} that the library copies to the device.
 //
@@ -27,10 +27,10 @@
 //     the default for drop-in parity; MCMCB200_RNG_PHILOX is the in-kernel production generator), arithmetic mode,
 //     device ordinal.
 //
-// Box constraints (vals_bound / lower_bounds / upper_bounds, +-inf = open side) run on the device path for M = I
-// (HMC, NUTS, MALA), for RM-HMC and for RWMH (with or without a cov_mat).  Unsupported combinations fail loudly: bounds together with a precond_mat, or on
-// the wide (n_vals > 512) kernels, make the call return false with mcmc::last_error() set; nothing is ever silently
-// ignored and nothing is computed on the host.
+// Box constraints (vals_bound / lower_bounds / upper_bounds, +-inf = open side) run on the device path for HMC and NUTS (with or
+// without a precond_mat), MALA (M = I), RM-HMC, RWMH (with or without a cov_mat) and DE.  Unsupported combinations fail loudly:
+// MALA with bounds AND a precond_mat, or bounds on the wide (n_vals > 512) kernels, make the call return false with
+// mcmc::last_error() set; nothing is ever silently ignored and nothing is computed on the host.
 //
 // Vector / matrix types: with MCMC_ENABLE_EIGEN_WRAPPERS or MCMC_ENABLE_ARMA_WRAPPERS defined (as for the reference)
 // the Eigen / Armadillo types are used; otherwise a minimal column-major ColVec_t / Mat_t pair is provided.
@@ -202,6 +202,19 @@ struct rwmh_settings_t {   // mcmc_structs.hpp:138-149
     Mat_t cov_mat;
     size_t n_accept_draws = 0;
 };
+struct de_settings_t {   // mcmc_structs.hpp:44-62
+    bool jumps = false;
+    size_t n_pop = 100;
+    size_t n_burnin_draws = 1E03;
+    size_t n_keep_draws = 1E03;
+    int omp_n_threads = -1;
+    fp_t par_b = 1E-04;
+    fp_t par_gamma = 1.0;        // never read by the reference either (src/de.cpp:58-59 uses 2.38 / sqrt(2 n_vals))
+    fp_t par_gamma_jump = 2.0;
+    ColVec_t initial_lb;         // defaults to initial_vals - 0.5
+    ColVec_t initial_ub;         // defaults to initial_vals + 0.5
+    size_t n_accept_draws = 0;
+};
 struct b200_settings_t {
     int rng_mode = MCMCB200_RNG_MT19937_TAPE;  // reference-compatible stream by default (all samplers, NUTS included)
     int arith = MCMCB200_ARITH_FAST;
@@ -223,6 +236,7 @@ struct algo_settings_t {
     rmhmc_settings_t rmhmc_settings;
     mala_settings_t mala_settings;
     rwmh_settings_t rwmh_settings;
+    de_settings_t de_settings;
     b200_settings_t b200;
 };
 
@@ -309,7 +323,7 @@ inline void unpack(const fp_t* buf, size_t n_chains, size_t n_keep, size_t d, Cu
     auto work = [&](size_t c_begin, size_t c_end) {
         for (size_t c = c_begin; c < c_end; ++c) {
             mresize(cube.mat(c), n_keep, d);   // allocation and first touch happen on the copying thread
-            if (n_keep * d) std::memcpy(mdata(cube.mat(c)), buf + c * n_keep * d, n_keep * d * sizeof(fp_t));
+            if (n_keep > 0 && d > 0) std::memcpy(mdata(cube.mat(c)), buf + c * n_keep * d, n_keep * d * sizeof(fp_t));
         }
     };
     size_t n_thr = 1;
@@ -530,6 +544,83 @@ inline bool rwmh(const Mat_t& initial_vals, registered_kernel target_log_kernel,
 {
     return internal::rwmh_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals),
                                target_log_kernel, target_data, &settings, nullptr, &draws_out);
+}
+
+// ================================================= DE ========================================================
+// bool mcmc::de(initial_vals, target_log_kernel (value only), Cube_t& draws_out, target_data[, settings])
+// include/mcmc/de.hpp:43-72, src/de.cpp:249-271: draws_out = n_keep matrices of n_pop x n_vals.  Many independent populations
+// per call: initial_vals as a d x P matrix (one column per population) and one Cube_t per population.
+namespace internal
+{
+inline bool de_impl(const fp_t* x0, size_t d, size_t n_pops, registered_kernel k, void* target_data, algo_settings_t* sp, Cube_t* cubes)
+{
+    algo_settings_t local;
+    algo_settings_t& s = sp ? *sp : local;
+    b200_detail::wrapper_error().clear();
+    const de_settings_t& ds = s.de_settings;
+    if (s.vals_bound && (b200_detail::vsize(s.lower_bounds) != d || b200_detail::vsize(s.upper_bounds) != d)) {
+        b200_detail::wrapper_error() = "mcmc_b200: vals_bound = true needs lower_bounds and upper_bounds of length n_vals";
+        return false;
+    }
+    mcmcb200_problem_t pr;
+    mcmcb200_rng_t rng;
+    b200_detail::fill_problem(pr, rng, x0, d, n_pops, k, target_data, s, s.b200.rng_mode);
+    if (s.vals_bound) {
+        pr.vals_bound = 1;
+        pr.lower_bounds = b200_detail::cdata(s.lower_bounds);
+        pr.upper_bounds = b200_detail::cdata(s.upper_bounds);
+    }
+    mcmcb200_de_settings_t st;
+    mcmcb200_de_settings_default(&st);
+    st.n_burnin_draws = static_cast<int64_t>(ds.n_burnin_draws);
+    st.n_keep_draws = static_cast<int64_t>(ds.n_keep_draws);
+    st.n_pop = static_cast<int64_t>(ds.n_pop);
+    st.jumps = ds.jumps ? 1 : 0;
+    st.arith = s.b200.arith;
+    st.par_b = ds.par_b;
+    st.par_gamma_jump = ds.par_gamma_jump;
+    st.initial_lb = (b200_detail::vsize(ds.initial_lb) == d) ? b200_detail::cdata(ds.initial_lb) : nullptr;   // src/de.cpp:70-71
+    st.initial_ub = (b200_detail::vsize(ds.initial_ub) == d) ? b200_detail::cdata(ds.initial_ub) : nullptr;
+    const size_t n_keep = ds.n_keep_draws, n_pop = ds.n_pop;
+    std::vector<fp_t> buf(n_pops * n_keep * n_pop * d);
+    std::vector<int64_t> acc(n_pops, 0);
+    mcmcb200_output_t out;
+    std::memset(&out, 0, sizeof(out));
+    out.draws_out = buf.data();
+    out.draws_mem = MCMCB200_MEM_HOST;
+    out.n_accept_draws = acc.data();
+    if (mcmcb200_de_run(&pr, &rng, &st, &out) != MCMCB200_OK) return false;
+    for (size_t p = 0; p < n_pops; ++p) {   // [generation][member][d] row-major -> n_keep column-major n_pop x d matrices
+        cubes[p].set_n_mat(n_keep);
+        for (size_t g = 0; g < n_keep; ++g) {
+            Mat_t& m = cubes[p].mat(g);
+            b200_detail::mresize(m, n_pop, d);
+            const fp_t* src = buf.data() + ((p * n_keep + g) * n_pop) * d;
+            fp_t* dst = b200_detail::mdata(m);
+            for (size_t j = 0; j < d; ++j)
+                for (size_t i = 0; i < n_pop; ++i) dst[j * n_pop + i] = src[i * d + j];
+        }
+    }
+    if (sp) s.de_settings.n_accept_draws = static_cast<size_t>(acc[0]);   // src/de.cpp:237-239 (population 0 in many-population calls)
+    return true;
+}
+}  // namespace internal
+
+inline bool de(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Cube_t& draws_out, void* target_data)
+{
+    return internal::de_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, nullptr, &draws_out);
+}
+inline bool de(const ColVec_t& initial_vals, registered_kernel target_log_kernel, Cube_t& draws_out, void* target_data, algo_settings_t& settings)
+{
+    return internal::de_impl(b200_detail::cdata(initial_vals), b200_detail::vsize(initial_vals), 1, target_log_kernel, target_data, &settings, &draws_out);
+}
+// many independent populations: one column of initial_vals and one Cube_t per population
+inline bool de(const Mat_t& initial_vals, registered_kernel target_log_kernel, std::vector<Cube_t>& draws_out, void* target_data,
+               algo_settings_t& settings)
+{
+    draws_out.resize(b200_detail::mcols(initial_vals));
+    return internal::de_impl(b200_detail::cdata(initial_vals), b200_detail::mrows(initial_vals), b200_detail::mcols(initial_vals), target_log_kernel,
+                             target_data, &settings, draws_out.data());
 }
 
 // ================================================= NUTS ======================================================

@@ -1068,19 +1068,71 @@ int mcmcb200_philox_stream(uint64_t seed, int64_t chain, int64_t draw, int32_t n
     return MCMCB200_OK;
 }
 
+// Page-locked host buffers.  Pinning 4 GB costs about a second, so freed buffers are kept (at most 4, reused best-fit when a
+// request is no less than half their size) until mcmcb200_release_workspace(): a caller that samples repeatedly — the C++
+// wrapper stages every many-chain draws_out through one — pays for the pinning once.
+struct PinnedBuf { void* p; size_t bytes; };
+static std::mutex g_pinned_mu;
+static std::vector<PinnedBuf>& pinned_cache()
+{
+    static std::vector<PinnedBuf>* v = new std::vector<PinnedBuf>;
+    return *v;
+}
+static std::vector<PinnedBuf>& pinned_live()
+{
+    static std::vector<PinnedBuf>* v = new std::vector<PinnedBuf>;
+    return *v;
+}
 void* mcmcb200_host_alloc(size_t bytes)
 {
+    if (bytes == 0) bytes = 8;
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        std::vector<PinnedBuf>& c = pinned_cache();
+        size_t best = c.size();
+        for (size_t i = 0; i < c.size(); ++i)
+            if (c[i].bytes >= bytes && c[i].bytes <= 2 * bytes && (best == c.size() || c[i].bytes < c[best].bytes)) best = i;
+        if (best != c.size()) {
+            PinnedBuf b = c[best];
+            c.erase(c.begin() + (long)best);
+            pinned_live().push_back(b);
+            return b.p;
+        }
+    }
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 8, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
         cudaGetLastError();
         set_error("cudaHostAlloc(%zu bytes) failed", bytes);
         return nullptr;
     }
+    std::lock_guard<std::mutex> g(g_pinned_mu);
+    pinned_live().push_back(PinnedBuf{p, bytes});
     return p;
 }
 void mcmcb200_host_free(void* p)
 {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    PinnedBuf b{p, 0};
+    void* evict = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        std::vector<PinnedBuf>& l = pinned_live();
+        for (size_t i = 0; i < l.size(); ++i)
+            if (l[i].p == p) { b = l[i]; l.erase(l.begin() + (long)i); break; }
+        if (b.bytes == 0) { evict = p; }   // not ours to cache (unknown size): just free it
+        else {
+            std::vector<PinnedBuf>& c = pinned_cache();
+            c.push_back(b);
+            if (c.size() > 4) {   // keep the four largest
+                size_t smallest = 0;
+                for (size_t i = 1; i < c.size(); ++i)
+                    if (c[i].bytes < c[smallest].bytes) smallest = i;
+                evict = c[smallest].p;
+                c.erase(c.begin() + (long)smallest);
+            }
+        }
+    }
+    if (evict) cudaFreeHost(evict);
 }
 
 int mcmcb200_fp64_peak(int32_t device, double* tflops_out)
@@ -1110,8 +1162,16 @@ void mcmcb200_release_workspace(void)
 {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= MAX_DEVICES) return;
-    std::lock_guard<std::mutex> g(g_pool_mu);
-    pool_trim_locked(dev, 0);
+    {
+        std::lock_guard<std::mutex> g(g_pool_mu);
+        pool_trim_locked(dev, 0);
+    }
+    std::vector<PinnedBuf> drop;
+    {
+        std::lock_guard<std::mutex> g(g_pinned_mu);
+        drop.swap(pinned_cache());
+    }
+    for (const PinnedBuf& b : drop) cudaFreeHost(b.p);
 }
 
 }  // extern "C"

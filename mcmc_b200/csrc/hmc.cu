@@ -398,8 +398,8 @@ template <class T, int EPL, bool DENSE_M> static int launch_mass(const HmcLaunch
             // production configuration: the software-pipelined kernel; the most common trajectory length is unrolled
             if constexpr (T::separable && EPL <= 8) {   // EPL = 16: the unrolled loop outgrows the instruction cache (2.67 vs 2.55 ms)
                 if (a.n_leap == 10) return launch_pipe<T, EPL, 10>(a);
-                // any other trajectory length >= 5: the variates are interleaved with the first five steps, the rest run plain
-                if (a.n_leap >= 5) return launch_pipe<T, EPL, 5, true>(a);
+                // (a variant that interleaves the variates with the first five steps of ANY trajectory length >= 5 — LS = 5,
+                //  MORE = true — measured no faster than the up-front generation on B200: L = 5 2.197 vs 2.204 ms; not instantiated)
             }
             return launch_pipe<T, EPL, 0>(a);
         }

@@ -29,6 +29,7 @@
 #include "engine.h"
 #include "rng.cuh"
 #include "targets.cuh"
+#include "coop_dmma.cuh"
 #include "box.cuh"
 #include <math_constants.h>
 #include <type_traits>

@@ -92,5 +92,32 @@ int main()
         const bool ok = mcmc::hmc(x0, mcmc::device_kernel("diag_gauss"), draws, &dta, bad);
         std::printf("bounds_refused %d\n", ok ? 0 : 1);
     }
+    {   // G5: NUTS, 1-D N(0,1), seed 3 — on the reference's own stream, which is the wrapper's default (one launch per draw)
+        mcmc::ColVec_t x0(1); x0(0) = 0.3;
+        mcmc::algo_settings_t s; s.rng_seed_value = 3; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.nuts_settings.n_burnin_draws = 0; s.nuts_settings.n_keep_draws = 3; s.nuts_settings.step_size = 0.05; s.nuts_settings.n_adapt_draws = 0;
+        if (!mcmc::nuts(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        dump("G5_nuts_1d", draws, s.nuts_settings.n_accept_draws);
+    }
+    {   // golden de_iso_d3: mcmc::de, one population of 12 members, seed 11 (Cube_t of n_keep matrices n_pop x n_vals)
+        mcmc::ColVec_t x0(3); x0(0) = 0.5; x0(1) = -0.5; x0(2) = 1.0;
+        mcmc::algo_settings_t s; s.rng_seed_value = 11; s.b200.arith = MCMCB200_ARITH_STRICT;
+        s.de_settings.n_pop = 12; s.de_settings.n_burnin_draws = 5; s.de_settings.n_keep_draws = 20;
+        mcmc::Cube_t cube;
+        if (!mcmc::de(x0, mcmc::device_kernel("iso_gauss"), cube, nullptr, s)) { std::fprintf(stderr, "%s\n", mcmc::last_error()); return 1; }
+        std::printf("de_iso_d3 %zu %zu %zu", cube.n_mat() * (size_t)cube.mat(0).rows(), (size_t)cube.mat(0).cols(), s.de_settings.n_accept_draws);
+        for (size_t g = 0; g < cube.n_mat(); ++g)
+            for (size_t i = 0; i < cube.mat(g).rows(); ++i)
+                for (size_t j = 0; j < cube.mat(g).cols(); ++j) std::printf(" %a", cube.mat(g)(i, j));
+        std::printf("\n");
+    }
+    {   // the tensor_fn slot: a registered metric that does not belong to the kernel is refused, not ignored
+        mcmc::ColVec_t x0(2); x0(0) = 3; x0(1) = 3;
+        const double stats[3] = {100.0, 2.0, 400.0};
+        mcmc::kernel_data dta = {stats, 3};
+        mcmc::algo_settings_t s; s.rmhmc_settings.n_burnin_draws = 0; s.rmhmc_settings.n_keep_draws = 1;
+        const bool ok = mcmc::rmhmc(x0, mcmc::device_kernel("normal_model"), mcmc::device_metric("funnel_softabs"), draws, &dta, nullptr, s);
+        std::printf("foreign_metric_refused %d\n", ok ? 0 : 1);
+    }
     return 0;
 }

