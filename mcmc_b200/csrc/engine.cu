@@ -822,6 +822,8 @@ static int nuts_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng
     if (const char* e = std::getenv("MCMCB200_NUTS_COOP")) a.coop = (e[0] == '1');
     a.coop_batch = 6;   // measured on B200 (C4 shape, 1184 chains x 40 draws): 2 -> 456 ms, 4 -> 332, 6 -> 314, 8 -> 332
     if (const char* e = std::getenv("MCMCB200_NUTS_BATCH")) a.coop_batch = std::atoi(e) > 0 ? std::atoi(e) : 1;
+    a.coop_prefetch = true;
+    if (const char* e = std::getenv("MCMCB200_NUTS_PREFETCH")) a.coop_prefetch = (e[0] != '0');
     a.coop_dmma = true;
     if (const char* e = std::getenv("MCMCB200_NUTS_DMMA")) a.coop_dmma = (e[0] != '0');
     a.t_begin = 0;

@@ -78,6 +78,7 @@ struct NutsLaunch : CommonLaunch {
     long long work_stride;     // doubles per chain
     bool coop;                 // dense targets: 8 chains per CTA with cooperative gradients (nuts.cu)
     int coop_batch;            // requests that must be pending before busy warps attend a cooperative round
+    bool coop_prefetch;        // cooperative kernel: request the next trajectory state's product before the tree logic of the current one
     bool coop_dmma;            // FAST arithmetic: cooperative products on the fp64 tensor cores (DMMA); MCMCB200_NUTS_DMMA=0 keeps the scalar body
     // segmented runs (reference-stream mode drives the kernel draw by draw from the host): this launch performs draws
     // [t_begin, t_end); with t_begin > 0 the chain state is reloaded from the work area, with save_state it is parked there

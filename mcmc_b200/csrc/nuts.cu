@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     __shared__ NutsStack stacks[NW];
     __shared__ int n_active;   // COOP: chains of this CTA still running
     __shared__ int coop_want;  // COOP: products requested and not yet served
+    __shared__ int coop_seq;   // COOP: rounds run so far
     typedef Ar<STRICT> A;
     if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
     // summary tables: the first NW * NUTS_TAB_SMEM * 16 bytes of dynamic shared memory (unused when the table is global)
@@ -105,6 +106,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
         const long long left = a.n_chains - (long long)blockIdx.x * NW;
         n_active = left < NW ? (int)left : NW;
         coop_want = 0;
+        coop_seq = 0;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -123,6 +125,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
     if constexpr (COOP) {
         // dynamic shared memory: NW x (x, y) vectors, then (when the TMA path applies) two panel buffers and two mbarriers
         w.warp = warp; w.coop_base = vsm; w.coop_stride = cstride; w.phase = 0u; w.n_active = &n_active; w.want = &coop_want;
+        w.round_seq = &coop_seq; w.prefetched = 0;
         const bool tma = coop_tma;
         w.dmma = coop_dmma ? 1 : 0;
         w.panel_stride = coop_dmma ? d + 4 : d;
@@ -210,12 +213,48 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
         kick(e, p, g);
         return lp;
     };
+    double x[EPL], xt[EPL], rt[EPL], gt[EPL];
+    // COOP: the leapfrog in two halves around the cooperative product (see the leaf code): begin = first half kick, drift, stage x,
+    // post the request; finish = wait until a round has served it, gradient / log pi from the product, second half kick.
+    bool pend = false;
+    int pend_seq = 0;
+    auto begin_next = [&](double e) {
+        if constexpr (COOP) {
+            kick(e, rt, gt);
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) xt[k] = A::mad(e, rt[k], xt[k]);
+            stage_vec<EPL>(w.scr, d, lane, xt);
+            pend_seq = *reinterpret_cast<volatile int*>(&coop_seq);
+            if (lane == 0) atomicAdd(&coop_want, 1);
+            pend = true;
+        }
+    };
+    auto finish_next = [&](double e) -> double {
+        double lp = 0.0;
+        if constexpr (COOP) {
+            while (__shfl_sync(FULL, *reinterpret_cast<volatile int*>(&coop_seq), 0) == pend_seq) coop_round<STRICT>(a.tdata, w, true);
+            w.prefetched = 1;
+            lp = box_eval<T, EPL, STRICT, BOX, true, true, true>(a.tdata, w, bx, xt, gt, Jt);
+            w.prefetched = 0;
+            kick(e, rt, gt);
+            pend = false;
+        }
+        return lp;
+    };
+    auto cancel_next = [&]() {
+        if constexpr (COOP) {
+            if (pend) {
+                // no round can be running (it needs this warp): either ours was served (nothing to undo) or it is still counted
+                if (__shfl_sync(FULL, *reinterpret_cast<volatile int*>(&coop_seq), 0) == pend_seq && lane == 0) atomicSub(&coop_want, 1);
+                pend = false;
+            }
+        }
+    };
     auto neg_logp_finite = [](double lp) -> double {
         const double U = -lp;
         return isfinite(U) ? U : CUDART_INF;  // "if (!std::isfinite(prop_U)) prop_U = posinf"
     };
 
-    double x[EPL], xt[EPL], rt[EPL], gt[EPL];
     ChainRng<RNGM> rng;
     rng.init(a.rng, chain, a.chain_offset + chain);
     long long n_lf = 0;
@@ -343,7 +382,13 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
                 if (j == 0) {
                     const int k_need = ao + 1;
                     while (computed < k_need) {   // extend the trajectory by one leapfrog (nuts.ipp:132)
-                        const double lp = leapfrog(e_signed, xt, rt, gt);
+                        double lp;
+                        if constexpr (COOP) {
+                            if (!pend) begin_next(e_signed);
+                            lp = finish_next(e_signed);
+                        } else {
+                            lp = leapfrog(e_signed, xt, rt, gt);
+                        }
                         ++computed; ++n_lf;
                         const double Uk = neg_logp_finite(lp);   // :134-138
                         const double Kk = kinetic(rt);           // :140
@@ -351,6 +396,12 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
                         store_vec<EPL>(Wst + (size_t)(computed - 1) * 2 * dp + dp, d, lane, rt);
                         if (lane == 0) { Us[computed - 1] = Uk; Ks[computed - 1] = Kk; }
                         __syncwarp();
+                        if constexpr (COOP) {
+                            // the trajectory continues unless this doubling stops or is complete: start the next state's product NOW,
+                            // before the merges and U-turn tests this leaf closes — those then overlap with the other chains' work
+                            // instead of delaying the CTA's next round (a state that turns out not to be needed is discarded below)
+                            if (a.coop_prefetch && computed < 1 + depth * (depth + 1) / 2) begin_next(e_signed);
+                        }
                     }
                     const double Uk = reinterpret_cast<volatile double*>(Us)[k_need - 1], Kk = reinterpret_cast<volatile double*>(Ks)[k_need - 1];
                     const Leaf l = leaf_ns(k_need, log_u);
@@ -420,6 +471,7 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 1 : nuts_min_blocks(EPL)) n
                 __syncwarp();
                 --level;
             }
+            if constexpr (COOP) cancel_next();   // a prefetched state this doubling did not use
             alpha = R_alpha;   // overwritten by every doubling (Q12)
             n_alpha = R_nalpha;
             const int ubase = ucount;   // the merges of this doubling drew uniforms ubase .. ubase + n_alpha - 2 (post-order)

@@ -10,10 +10,12 @@
 //     funnel's SoftAbs metric (arrow Hessian => G = [[g11, w x~'], [w x~, fa I + P x~ x~']]) every D_i is a rank-structured
 //     matrix and the d contractions cost two GEMVs with A — O(d^2) instead of streaming a 2 MB cube per update (the cube
 //     kernel moved 114 MB of DRAM traffic per chain-draw at d = 64; this one keeps the chain's whole state on chip).
-//   * Matrices: two d-column buffers in shared memory with an even leading dimension d + 2 (row pairs move as 128-bit words):
-//     `Ainv0` = G_prev^-1 for the whole draw, `W` = scratch in which a metric is built and inverted IN PLACE (Gauss-Jordan
-//     with partial pivoting, 2 d^3 flop, log|det| from the pivots) — also used for the draw's Cholesky factor.  G at the
-//     current / proposed point is parked in the chain's small global area (2 d^2 doubles) only for the next draw's Cholesky.
+//   * Matrices: ONE d-column scratch matrix `W` in shared memory (even leading dimension d + 2: row pairs move as 128-bit
+//     words) in which a metric is built and inverted IN PLACE (Gauss-Jordan with partial pivoting, 2 d^3 flop) and in which the
+//     draw's Cholesky factor / log det are taken.  `Ainv0` = G_prev^-1, constant during a draw and only ever read as the
+//     operand of matrix-vector products, lives in the chain's global area (L2-resident, streamed with coalesced loads) next
+//     to G at the accepted / proposed point (kept for the next draw's Cholesky): one shared matrix instead of two lets three
+//     CTAs share an SM, and the eliminations are latency chains that only more resident warps can hide.
 //   * 128 threads share each matrix operation (thread = row x column-parity), warp 0 evaluates the warp-cooperative target
 //     functor and the random variates.
 // FAST arithmetic only (operation orders differ from the reference's LU / Cholesky at rounding level, within the 1e-10
@@ -245,7 +247,7 @@ __device__ void rc_cholesky_inplace(double* W, int d, int ld)
 }
 
 template <class T, class MC, int RNGM>
-__global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
+__global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
 {
     extern __shared__ __align__(16) double smem[];
     __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
@@ -259,8 +261,7 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
     const int d = a.d;
     const int ld = (d + 2) & ~1;   // even (128-bit row-pair accesses), > d (one padding row), transposed reads at most 4-way conflicted
     const int dp = (d + 1) & ~1;
-    double* Ainv0 = smem;                    // G_prev^-1, fixed during a draw
-    double* W = Ainv0 + (size_t)d * ld;      // scratch matrix
+    double* W = smem;                        // scratch matrix
     double* vec = W + (size_t)d * ld;        // vectors, dp doubles each
     double* xprev = vec;            double* xcur = vec + dp;        double* pv = vec + 2 * dp;   double* qv = vec + 3 * dp;
     double* wv = vec + 4 * dp;      double* gv = vec + 5 * dp;      double* uv = vec + 6 * dp;   double* upv = vec + 7 * dp;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
     // the chain's global area: G at the accepted point and at the proposal (column-major, leading dimension d)
     double* Gacc = a.work + (size_t)chain * (size_t)a.work_stride;
     double* Gnew = Gacc + (size_t)d * d;
+    double* Ainv0 = Gnew + (size_t)d * d;    // G_prev^-1 (leading dimension ld), fixed during a draw; written on an accept only
     const double eps = a.eps, heps = 0.5 * eps;
     rc_sync();
 
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
                 for (; j + 1 < d; j += 2) { acc = fma(Am[(size_t)j * ld + i], v[j], acc); acc2 = fma(Am[(size_t)(j + 1) * ld + i], v[j + 1], acc2); }
                 if (j < d) acc = fma(Am[(size_t)j * ld + i], v[j], acc);
                 y[i] = acc + acc2;
-            } else if (y2) {
+            } else if (y2) {   // A^T v with the same coalesced column access: threads 64.. walk the other half of the columns
                 for (; j + 1 < d; j += 2) { acc = fma(Am[(size_t)i * ld + j], v[j], acc); acc2 = fma(Am[(size_t)i * ld + j + 1], v[j + 1], acc2); }
                 if (j < d) acc = fma(Am[(size_t)i * ld + j], v[j], acc);
                 y2[i] = acc + acc2;
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(RC_THREADS) rmhmc_cta_kernel(const __grid_cons
     if (t == 0 && a.n_accept) a.n_accept[chain] = n_acc;
 }
 
-long long rmhmc_cta_work_doubles(int d) { return 2ll * d * d; }
+long long rmhmc_cta_work_doubles(int d) { return 2ll * d * d + (long long)d * ((d + 2) & ~1); }
 
 bool rmhmc_cta_applicable(int target_id, int metric_id, int d, bool strict, bool has_bounds)
 {
@@ -483,9 +485,10 @@ bool rmhmc_cta_applicable(int target_id, int metric_id, int d, bool strict, bool
 template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
 {
     const int d = a.d, ld = (d + 2) & ~1, dp = (d + 1) & ~1;
-    const size_t smem = ((size_t)2 * d * ld + (size_t)16 * dp) * sizeof(double);
+    const size_t smem = ((size_t)d * ld + (size_t)16 * dp) * sizeof(double);
     auto launch = [&](auto kern) -> int {
-        if (smem > 48 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // static (tables, buffers: ~18 KB) + dynamic shared memory together exceed the 48 KB default long before the dynamic part alone does
+        if (smem > 24 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<(unsigned)a.n_chains, RC_THREADS, smem, a.stream>>>(a);
         MCMCB200_CUDA_TRY(cudaGetLastError());
         return MCMCB200_OK;

@@ -52,6 +52,8 @@ template <int NW> struct CoopWarpCtx : WarpCtx {
     int dmma;                 // FAST arithmetic: the NW-chain product runs on the fp64 tensor cores (coop_gemv_body_dmma)
     const int* n_active;      // chains of this CTA still running (shared memory)
     int* want;                // products requested and not yet served (shared memory): busy warps poll it, see coop_round
+    int* round_seq;           // number of rounds this CTA has run (shared memory): a request posted at sequence s is served once it is > s
+    mutable int prefetched;   // the product for the staged vector was requested earlier and has been served: dense_matvec only reads it
     mutable unsigned phase;   // bit b = parity of panel buffer b's next completed phase (identical in every thread)
 };
 
@@ -377,7 +379,10 @@ template <bool STRICT, class Ctx> __device__ __forceinline__ bool coop_round(con
     if (!draining && w.lane == 0) atomicAdd(w.want, 1);
     coop_barrier<NW>();   // every chain's x is staged
     if (draining && *reinterpret_cast<const volatile int*>(w.n_active) == 0) return false;
-    if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(w.want) = 0;   // visible to everyone after the last barrier
+    if (threadIdx.x == 0) {   // visible to everyone after the last barrier
+        *reinterpret_cast<volatile int*>(w.want) = 0;
+        *reinterpret_cast<volatile int*>(w.round_seq) = *reinterpret_cast<volatile int*>(w.round_seq) + 1;
+    }
     if (w.panels) {
         coop_panels_prologue(A, w.d, w.panels, w.panel_stride, w.mbar);
         if (!STRICT && w.dmma) coop_gemv_body_dmma<NW>(A, w.d, w.warp, w.lane, w.coop_base, w.coop_stride, w.panels, w.panel_stride, w.mbar, w.phase);
@@ -393,11 +398,14 @@ template <bool STRICT, class Ctx> __device__ __forceinline__ bool coop_round(con
 template <int EPL, bool STRICT, class Ctx>
 __device__ __forceinline__ void dense_matvec(const double* __restrict__ A, const Ctx& w, const double (&x)[EPL], double (&y)[EPL])
 {
-    stage_vec<EPL>(w.scr, w.d, w.lane, x);
     if constexpr (Ctx::coop > 0) {
-        coop_round<STRICT>(A, w, false);
+        if (!w.prefetched) {   // (else: x was staged and its product requested ahead of time, and a round has served it — nuts.cu)
+            stage_vec<EPL>(w.scr, w.d, w.lane, x);
+            coop_round<STRICT>(A, w, false);
+        }
         load_vec<EPL>(w.scr + (w.coop_stride >> 1), w.d, w.lane, y);
     } else {
+        stage_vec<EPL>(w.scr, w.d, w.lane, x);
         gemv_cm<EPL, STRICT>(A, w.d, w.lane, w.scr, 1.0, y);
     }
 }
