@@ -20,6 +20,7 @@
 #include "transpose.h"
 #include "rmhmc_cta.h"
 #include "hmc_batched.h"
+#include "nuts_batched.h"
 
 namespace mcmcb200
 {
@@ -812,7 +813,13 @@ static int nuts_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng
     if ((rc = pool_get(s.lease, s.scope.dev, SLOT_NLF, (size_t)pr->n_chains * sizeof(long long), &p))) return rc;
     a.n_leapfrog = static_cast<long long*>(p);
     a.work_stride = nuts_work_doubles_per_chain(pr->n_dim, a.max_depth);
-    if ((rc = pool_get(s.lease, s.scope.dev, SLOT_WORK, (size_t)pr->n_chains * (size_t)a.work_stride * sizeof(double), &p))) return rc;
+    // dense quadratic target, many chains, FAST arithmetic: chain-batched rounds — one fp64 tensor-core GEMM per round for the
+    // gradient products of ALL chains + a resumable per-chain state machine (nuts_batched.cu); everything else: nuts.cu
+    const bool batched = !s.deferred_mt_tape && pr->target_id < MCMCB200_USER_TARGET_BASE &&
+                         nuts_batched_supported(pr->target_id, pr->n_dim, a.S_cm != nullptr, a.strict, a.lb != nullptr, pr->n_chains, a.max_depth);
+    const size_t work_doubles = batched ? (size_t)nuts_batched_work_doubles(pr->n_chains, pr->n_dim, a.max_depth)
+                                        : (size_t)pr->n_chains * (size_t)a.work_stride;
+    if ((rc = pool_get(s.lease, s.scope.dev, SLOT_WORK, work_doubles * sizeof(double), &p))) return rc;
     a.work = static_cast<double*>(p);
     // dense targets with enough chains to fill the GPU run 8 chains per CTA with cooperative gradients (nuts.cu);
     // MCMCB200_NUTS_COOP=0/1 forces the choice (tests compare the two kernels bit for bit)
@@ -832,7 +839,9 @@ static int nuts_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng
     a.tape_used = nullptr;
     int launches = 1;
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
-    if (!s.deferred_mt_tape) {
+    if (batched) {
+        if ((rc = launch_nuts_batched(a, a.work, &launches, nullptr))) return rc;
+    } else if (!s.deferred_mt_tape) {
         if ((rc = launch_nuts(a))) return rc;
     } else {
         // Reference-stream mode (MCMCB200_RNG_MT19937_TAPE).  The reference draws, per iteration, n_dim normals and then a

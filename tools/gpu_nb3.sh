@@ -1,0 +1,9 @@
+#!/bin/bash
+tag=${1:-nb3}
+mkdir -p gpurun_out /tmp/ncu
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:nuts_ls_step -s 12000 -c 1 -f -o /tmp/ncu/ls python tools/prof_c4.py 4096 60 60 > gpurun_out/${tag}_ls.log 2>&1
+tail -2 gpurun_out/${tag}_ls.log
+python tools/ncu_summary.py /tmp/ncu/ls.ncu-rep 4096 > gpurun_out/${tag}_ls.ncu_summary.txt 2>&1
+python tools/ncu_hot.py /tmp/ncu/ls.ncu-rep 60 > gpurun_out/${tag}_ls.hot.txt 2>&1
+ncu -i /tmp/ncu/ls.ncu-rep --page source --csv --print-source cuda > gpurun_out/${tag}_ls.src.csv 2>/dev/null
+ls -la /tmp/ncu gpurun_out | tail -8
