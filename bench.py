@@ -318,7 +318,10 @@ def run_configs(which, rank, world, local_rank, allmax, fp64_peak, hbm_peak, wit
                      "kernel_ms": ms, "value": Ctot * (nb + nk) / (ms * 1e-3), "unit": "draws/s", "leapfrogs_per_draw": nlf / (Ctot * (nb + nk)),
                      "leapfrogs_per_s": nlf / (ms * 1e-3), "step_size_mean": float(r["step_size"].mean()),
                      "roofline": {"bound": "tensor", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None,
-                                  "note": "fp64: 2 d^2 flop (the Sigma^-1 x product) per distinct leapfrog state; per GPU"}}
+                                  "note": "fp64: 2 d^2 flop (the Sigma^-1 x product) per distinct leapfrog state; per GPU; chain-batched rounds "
+                                          "(csrc/nuts_batched.cu: one DMMA GEMM + one step-kernel launch per round and chain group) when the "
+                                          "shard has >= 512 chains, else the persistent cooperative kernel (csrc/nuts.cu)"},
+                     "kernel_launches": int(r["kernel_launches"])}
         del draws, x0d
         if ref is not None:
             st = ol.Settings(n_burnin=20, n_keep=10, n_adapt_draws=20)

@@ -26,6 +26,7 @@
 #include "rmhmc_metrics.cuh"
 #include "rmhmc_cta.h"
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace mcmcb200
 {
@@ -227,6 +228,182 @@ __device__ void rc_inverse_inplace(double* W, int d, int ld, int* piv, double* r
     }
 }
 
+// The same elimination with the matrix in REGISTERS (n_dim > 32).  Thread t owns the 8 x 4 tile of rows 8 (t % 8) .. + 7 and
+// columns 4 (t / 8) .. + 3 of the (padded) 64 x 64 matrix for all d pivot steps; a step exchanges only what the rank-1 update
+// needs through shared memory — column k (the multipliers and the pivot candidates) and the scaled pivot row — so it costs
+// 32 multiply-adds against ~12 shared accesses per thread instead of 40 for 32 (rc_inverse_inplace) and two CTA barriers
+// instead of four.  Rows are never exchanged: the permutation of partial pivoting is tracked (`lof` = logical position of a
+// physical row, `pof` = its inverse) and applied once when the tile is stored — A^-1(i, r) = W(pof[i], lof[r]) read the other
+// way round.  Pivot choice (first maximum by LOGICAL position, NaN rules), multipliers and update formulas are those of
+// rc_inverse_inplace: the two produce the same bits.
+// buf: 3 * RC_MAXD doubles (column k double-buffered, scaled pivot row), perm: 2 * RC_MAXD ints; both 16-byte aligned.
+// (The tile is 32 named scalars, not an array: with an array the compiler merges the per-column / per-row cases of a step into
+//  one dynamically addressed access and the whole tile moves to local memory — measured 30 ms per C5 draw instead of 16.)
+#define RC_R8(OP, c) OP(c, 0) OP(c, 1) OP(c, 2) OP(c, 3) OP(c, 4) OP(c, 5) OP(c, 6) OP(c, 7)
+#define RC_C4R8(OP) RC_R8(OP, 0) RC_R8(OP, 1) RC_R8(OP, 2) RC_R8(OP, 3)
+#define RC_A(c, r) a##c##r
+#define RC_F(r) f##r
+__device__ __noinline__ void rc_inverse_regtile(double* W, int d, int ld, double* buf, int* perm)
+{
+    constexpr int N = RC_MAXD;
+    double* const rowbuf = buf + 2 * N;
+    int* const lof = perm;       // logical position of physical row r
+    int* const pof = perm + N;   // physical row at logical position l
+    const int t = threadIdx.x, lane = t & 31;
+    const int rb = t & 7, cbk = t >> 3;
+    const int i0 = 8 * rb, j0 = 4 * cbk;
+    // RC_A(c, r) = element (i0 + r, j0 + c); padding rows / columns: identity
+#define RC_DECL(c, r) double RC_A(c, r);
+    RC_C4R8(RC_DECL)
+#undef RC_DECL
+#define RC_LOAD2(c, q)                                                                                   \
+    {                                                                                                    \
+        const int j = j0 + c, i = i0 + 2 * q;                                                            \
+        double2 v = make_double2((i == j) ? 1.0 : 0.0, (i + 1 == j) ? 1.0 : 0.0);                        \
+        if (j < d && i < d) {                                                                            \
+            v = *reinterpret_cast<const double2*>(W + (size_t)j * ld + i);                               \
+            if (i + 1 >= d) v.y = 0.0;                                                                   \
+        }                                                                                                \
+        RC_A(c, 2 * q) = v.x;                                                                            \
+        RC_A(c, 2 * q + 1) = v.y;                                                                        \
+    }
+    // (token pasting needs literal row numbers)
+#define RC_LOADC(c)                                                                                      \
+    {                                                                                                    \
+        const int j = j0 + c;                                                                            \
+        double2 v0 = make_double2((i0 == j) ? 1.0 : 0.0, (i0 + 1 == j) ? 1.0 : 0.0), v1 = make_double2((i0 + 2 == j) ? 1.0 : 0.0, (i0 + 3 == j) ? 1.0 : 0.0); \
+        double2 v2 = make_double2((i0 + 4 == j) ? 1.0 : 0.0, (i0 + 5 == j) ? 1.0 : 0.0), v3 = make_double2((i0 + 6 == j) ? 1.0 : 0.0, (i0 + 7 == j) ? 1.0 : 0.0); \
+        if (j < d) {                                                                                     \
+            const double* col = W + (size_t)j * ld + i0;                                                 \
+            if (i0 < d) { v0 = *reinterpret_cast<const double2*>(col); if (i0 + 1 >= d) v0.y = 0.0; }              \
+            if (i0 + 2 < d) { v1 = *reinterpret_cast<const double2*>(col + 2); if (i0 + 3 >= d) v1.y = 0.0; }      \
+            if (i0 + 4 < d) { v2 = *reinterpret_cast<const double2*>(col + 4); if (i0 + 5 >= d) v2.y = 0.0; }      \
+            if (i0 + 6 < d) { v3 = *reinterpret_cast<const double2*>(col + 6); if (i0 + 7 >= d) v3.y = 0.0; }      \
+        }                                                                                                \
+        RC_A(c, 0) = v0.x; RC_A(c, 1) = v0.y; RC_A(c, 2) = v1.x; RC_A(c, 3) = v1.y;                      \
+        RC_A(c, 4) = v2.x; RC_A(c, 5) = v2.y; RC_A(c, 6) = v3.x; RC_A(c, 7) = v3.y;                      \
+    }
+    RC_LOADC(0) RC_LOADC(1) RC_LOADC(2) RC_LOADC(3)
+#undef RC_LOADC
+#undef RC_LOAD2
+    if (t < N) { lof[t] = t; pof[t] = t; }
+    // one column of the tile -> 8 consecutive doubles of shared memory
+#define RC_STORE_COL(c, dst)                                                                             \
+    {                                                                                                    \
+        *reinterpret_cast<double2*>((dst)) = make_double2(RC_A(c, 0), RC_A(c, 1));                       \
+        *reinterpret_cast<double2*>((dst) + 2) = make_double2(RC_A(c, 2), RC_A(c, 3));                   \
+        *reinterpret_cast<double2*>((dst) + 4) = make_double2(RC_A(c, 4), RC_A(c, 5));                   \
+        *reinterpret_cast<double2*>((dst) + 6) = make_double2(RC_A(c, 6), RC_A(c, 7));                   \
+    }
+    if (cbk == 0) RC_STORE_COL(0, buf + i0)   // column 0 for the first step
+    rc_sync();
+    for (int k = 0; k < d; ++k) {
+        const double* colbuf = buf + (k & 1) * N;
+        // pivot: first maximum of |W(l, k)| over logical rows l >= k (a NaN never wins, a NaN at logical (k, k) keeps l = k);
+        // every warp finds it redundantly
+        // (|v| of a non-NaN double orders like its bit pattern: key = bits + 2, NaN -> 1, not a candidate -> 0; the maximum of
+        //  the 64-bit keys and then the smallest logical position among its holders take three warp reductions (redux.sync))
+        int p;
+        {
+            const int pk = pof[k];
+            const double vk = colbuf[pk];
+            p = pk;
+            if (vk == vk) {
+                unsigned long long key = 0ull;
+                int bl = 0x7fffffff;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = lane + 32 * h;
+                    const int l = lof[r];
+                    if (r < d && l >= k) {
+                        const double v = colbuf[r];
+                        const unsigned long long kv = (v == v) ? (unsigned long long)(__double_as_longlong(v) & 0x7fffffffffffffffll) + 2ull : 1ull;
+                        if (kv > key || (kv == key && l < bl)) { key = kv; bl = l; }
+                    }
+                }
+                const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+                const unsigned mhi = __reduce_max_sync(FULL, hi);
+                const unsigned mlo = __reduce_max_sync(FULL, (hi == mhi) ? lo : 0u);
+                const unsigned ml = __reduce_min_sync(FULL, (hi == mhi && lo == mlo) ? (unsigned)bl : 0x7fffffffu);
+                p = pof[ml];
+            }
+        }
+        const double pv = colbuf[p];
+        const double rinv = 1.0 / pv;
+        // the scaled pivot row, from the threads that hold physical row p (p is uniform: no divergence inside the switch)
+        if (rb == (p >> 3)) {
+            double r0, r1, r2, r3;
+            switch (p & 7) {
+#define RC_ROW(R) case R: r0 = RC_A(0, R); r1 = RC_A(1, R); r2 = RC_A(2, R); r3 = RC_A(3, R); break;
+                RC_ROW(0) RC_ROW(1) RC_ROW(2) RC_ROW(3) RC_ROW(4) RC_ROW(5) RC_ROW(6)
+                default: r0 = RC_A(0, 7); r1 = RC_A(1, 7); r2 = RC_A(2, 7); r3 = RC_A(3, 7); break;
+#undef RC_ROW
+            }
+            *reinterpret_cast<double2*>(rowbuf + j0) = make_double2(r0 * rinv, r1 * rinv);
+            *reinterpret_cast<double2*>(rowbuf + j0 + 2) = make_double2(r2 * rinv, r3 * rinv);
+        }
+        rc_sync();
+        if (t == 0) {   // logical rows k and lof[p] change places (read again only after the next barrier)
+            const int lp = lof[p], pk = pof[k];
+            pof[k] = p; pof[lp] = pk;
+            lof[p] = k; lof[pk] = lp;
+        }
+        // multipliers: column k; the pivot row gets pivot - 1 (its scaling folded into the update, see rc_inverse_inplace)
+        const double2 c01 = *reinterpret_cast<const double2*>(colbuf + i0), c23 = *reinterpret_cast<const double2*>(colbuf + i0 + 2);
+        const double2 c45 = *reinterpret_cast<const double2*>(colbuf + i0 + 4), c67 = *reinterpret_cast<const double2*>(colbuf + i0 + 6);
+        const int pr = p - i0;   // the pivot row's place in this tile (0..7) or outside
+        const double f0 = (pr == 0) ? pv - 1.0 : c01.x, f1 = (pr == 1) ? pv - 1.0 : c01.y, f2 = (pr == 2) ? pv - 1.0 : c23.x, f3 = (pr == 3) ? pv - 1.0 : c23.y;
+        const double f4 = (pr == 4) ? pv - 1.0 : c45.x, f5 = (pr == 5) ? pv - 1.0 : c45.y, f6 = (pr == 6) ? pv - 1.0 : c67.x, f7 = (pr == 7) ? pv - 1.0 : c67.y;
+        const double2 ra = *reinterpret_cast<const double2*>(rowbuf + j0), rb2 = *reinterpret_cast<const double2*>(rowbuf + j0 + 2);
+        const double rr0 = ra.x, rr1 = ra.y, rr2 = rb2.x, rr3 = rb2.y;
+#define RC_UPD(c, r) RC_A(c, r) = fma(-RC_F(r), rr##c, RC_A(c, r));
+        RC_C4R8(RC_UPD)
+#undef RC_UPD
+        if (cbk == (k >> 2)) {   // column k: 1 / pivot in the pivot row, -multiplier / pivot elsewhere (k is uniform)
+#define RC_FIX(c, r) RC_A(c, r) = (pr == r) ? rinv : -RC_F(r) * rinv;
+            switch (k & 3) {
+            case 0: RC_R8(RC_FIX, 0) break;
+            case 1: RC_R8(RC_FIX, 1) break;
+            case 2: RC_R8(RC_FIX, 2) break;
+            default: RC_R8(RC_FIX, 3) break;
+            }
+#undef RC_FIX
+        }
+        // column k + 1 for the next step (the other half of the double buffer: this step's is still being read)
+        if (k + 1 < d && cbk == ((k + 1) >> 2)) {
+            double* nb = buf + ((k + 1) & 1) * N + i0;
+            switch ((k + 1) & 3) {
+            case 0: RC_STORE_COL(0, nb) break;
+            case 1: RC_STORE_COL(1, nb) break;
+            case 2: RC_STORE_COL(2, nb) break;
+            default: RC_STORE_COL(3, nb) break;
+            }
+        }
+        rc_sync();
+    }
+    // A^-1(i, r) = tile value at (physical row pof[i], column lof[r]): physical row pr, column c goes to (lof[pr], pof[c])
+    {
+        int li[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) li[r] = (i0 + r < d) ? lof[i0 + r] : -1;
+#define RC_OUT(c, r) if (li[r] >= 0) col[li[r]] = RC_A(c, r);
+#define RC_OUTC(c)                                          \
+    if (j0 + c < d) {                                       \
+        double* col = W + (size_t)pof[j0 + c] * ld;         \
+        RC_R8(RC_OUT, c)                                    \
+    }
+        RC_OUTC(0) RC_OUTC(1) RC_OUTC(2) RC_OUTC(3)
+#undef RC_OUTC
+#undef RC_OUT
+    }
+    rc_sync();
+}
+#undef RC_STORE_COL
+#undef RC_F
+#undef RC_A
+#undef RC_C4R8
+#undef RC_R8
+
 // in-place lower Cholesky of the shared matrix (right-looking); the strict upper triangle keeps the input's entries — the
 // Eigen matrixLLT storage the reference multiplies with in full; returns nothing, L in the lower triangle
 __device__ void rc_cholesky_inplace(double* W, int d, int ld)
@@ -246,6 +423,14 @@ __device__ void rc_cholesky_inplace(double* W, int d, int ld)
     }
 }
 
+// n_dim > 32: the register-tile elimination; smaller matrices would mostly multiply padding there
+__device__ int rc_force_shared_gj = 0;   // MCMCB200_RMHMC_REGTILE=0 (tests: the two eliminations must agree bit for bit)
+__device__ __forceinline__ void rc_invert(double* W, int d, int ld, int* piv, double* buf, int* perm)
+{
+    if (d > 32 && !rc_force_shared_gj) rc_inverse_regtile(W, d, ld, buf, perm);
+    else rc_inverse_inplace(W, d, ld, piv, buf);
+}
+
 template <class T, class MC, int RNGM>
 __global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
 {
@@ -253,7 +438,8 @@ __global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_c
     __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
     __shared__ int piv[RC_MAXD];
     __shared__ double red[4];
-    __shared__ __align__(16) double rcbuf[2 * (RC_MAXD + 2)];
+    __shared__ __align__(16) double rcbuf[3 * RC_MAXD];   // >= 2 (RC_MAXD + 2)
+    __shared__ __align__(16) int rtperm[2 * RC_MAXD];
     __shared__ double sc_u, sc_lp;   // broadcast scalars (uniform, log-density)
     if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -358,7 +544,7 @@ __global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_c
     rc_sync();
     store_global(Gacc);
     double logdet_prev = logdet_chol(metric, xprev);
-    rc_inverse_inplace(W, d, ld, piv, rcbuf);
+    rc_invert(W, d, ld, piv, rcbuf, rtperm);
     for (int k = t; k < d * ld; k += RC_THREADS) Ainv0[k] = W[k];
     MC metric_prev = metric;   // the start-of-trajectory metric (Q17) of every draw until an accept replaces it
     target_at(xprev, true, false);
@@ -413,7 +599,7 @@ __global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_c
                 mw.prepare(wv, d);
                 mw.build(wv, d, W, ld);
                 rc_sync();
-                rc_inverse_inplace(W, d, ld, piv, rcbuf);
+                rc_invert(W, d, ld, piv, rcbuf, rtperm);
                 if (t < d) {
                     double acc = 0.0;
                     for (int j = 0; j < d; ++j) acc = fma(Ainv0[(size_t)j * ld + t] + W[(size_t)j * ld + t], heps * pv[j], acc);
@@ -432,7 +618,7 @@ __global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_c
                 store_global(Gnew);
                 logdet_new = logdet_chol(metric_new, xcur);
             }
-            rc_inverse_inplace(W, d, ld, piv, rcbuf);
+            rc_invert(W, d, ld, piv, rcbuf, rtperm);
             have_new = true;
             mntm_update(xcur, pv, W, metric_new, xcur, wv);
             if (t < d) pv[t] = pv[t] + wv[t];
@@ -486,6 +672,11 @@ template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
 {
     const int d = a.d, ld = (d + 2) & ~1, dp = (d + 1) & ~1;
     const size_t smem = ((size_t)d * ld + (size_t)16 * dp) * sizeof(double);
+    {
+        const char* e = std::getenv("MCMCB200_RMHMC_REGTILE");
+        const int v = (e && e[0] == '0') ? 1 : 0;
+        MCMCB200_CUDA_TRY(cudaMemcpyToSymbolAsync(rc_force_shared_gj, &v, sizeof(int), 0, cudaMemcpyHostToDevice, a.stream));
+    }
     auto launch = [&](auto kern) -> int {
         // static (tables, buffers: ~18 KB) + dynamic shared memory together exceed the 48 KB default long before the dynamic part alone does
         if (smem > 24 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

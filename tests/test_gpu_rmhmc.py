@@ -269,3 +269,20 @@ def test_c5_full_size(engine, monkeypatch):
     monkeypatch.delenv("MCMCB200_RMHMC_CTA")
     assert np.abs(sub["draws"] - r["draws"][1000:1024]).max() <= TOL and np.array_equal(sub["n_accept"], r["n_accept"][1000:1024])
     print("C5 full size: kernel %.1f ms for 6 draws (%.2f ms/draw), acceptance %.2f" % (r["kernel_ms"], r["kernel_ms"] / 6, acc))
+
+
+def test_register_tile_elimination_reproduces_the_shared_memory_one(engine, monkeypatch):
+    """n_dim > 32: the CTA kernel inverts its metrics with the matrix held in registers (8 x 4 tile per thread, implicit
+    partial pivoting, rc_inverse_regtile); MCMCB200_RMHMC_REGTILE=0 keeps the shared-memory Gauss-Jordan with physical row
+    exchanges.  Same pivots, same multipliers, same update formulas: identical bits, full and ragged n_dim, both metrics."""
+    rng = np.random.default_rng(77)
+    for d, metric_id in ((64, 2), (40, 2), (33, 1), (63, 2)):
+        x0 = _funnel_start(24, d, rng)
+        kw = dict(n_leap_steps=3, step_size=0.02, n_fp_steps=4, n_burnin=1, n_keep=6, want_logp=True, metric_id=metric_id,
+                  rng_mode=engine.api.RNG_PHILOX, seed=9)
+        a = engine.rmhmc(x0, "funnel", **kw)
+        monkeypatch.setenv("MCMCB200_RMHMC_REGTILE", "0")
+        b = engine.rmhmc(x0, "funnel", **kw)
+        monkeypatch.delenv("MCMCB200_RMHMC_REGTILE")
+        assert np.array_equal(a["draws"], b["draws"], equal_nan=True), (d, metric_id, np.nanmax(np.abs(a["draws"] - b["draws"])))
+        assert np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["logp"], b["logp"], equal_nan=True)
