@@ -431,17 +431,22 @@ __device__ __forceinline__ void rc_invert(double* W, int d, int ld, int* piv, do
     else rc_inverse_inplace(W, d, ld, piv, buf);
 }
 
+__device__ double2 rc_rng_tab_g[RNG_TAB_DOUBLE2];
+__global__ void rc_build_rng_tab() { build_rng_tables(rc_rng_tab_g); }   // same values from every launch: concurrent calls do not conflict
+
+// 128 registers: four CTAs (16 warps) per SM — the eliminations are latency chains that only more resident warps hide
 template <class T, class MC, int RNGM>
-__global__ void __launch_bounds__(RC_THREADS, 3) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
+__global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
 {
     extern __shared__ __align__(16) double smem[];
-    __shared__ double2 rng_tab[RNGM == RNG_PHILOX ? RNG_TAB_DOUBLE2 : 1];
+    // Box-Muller tables: read from global memory (built once per launch by rc_build_rng_tab; d normals per draw use them) —
+    // 16 KB of shared memory per CTA would cap the SM at three CTAs
+    const double2* const rng_tab = rc_rng_tab_g;
     __shared__ int piv[RC_MAXD];
     __shared__ double red[4];
     __shared__ __align__(16) double rcbuf[3 * RC_MAXD];   // >= 2 (RC_MAXD + 2)
     __shared__ __align__(16) int rtperm[2 * RC_MAXD];
     __shared__ double sc_u, sc_lp;   // broadcast scalars (uniform, log-density)
-    if (RNGM == RNG_PHILOX) build_rng_tables(rng_tab);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const long long chain = blockIdx.x;
     const int d = a.d;
@@ -677,6 +682,7 @@ template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
         const int v = (e && e[0] == '0') ? 1 : 0;
         MCMCB200_CUDA_TRY(cudaMemcpyToSymbolAsync(rc_force_shared_gj, &v, sizeof(int), 0, cudaMemcpyHostToDevice, a.stream));
     }
+    if (a.rng.mode == RNG_PHILOX) rc_build_rng_tab<<<1, 256, 0, a.stream>>>();
     auto launch = [&](auto kern) -> int {
         // static (tables, buffers: ~18 KB) + dynamic shared memory together exceed the 48 KB default long before the dynamic part alone does
         if (smem > 24 * 1024) MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
