@@ -82,7 +82,7 @@ def test_batched_rounds_on_the_reference_stream_tape(engine, oracle, monkeypatch
 
 
 def test_batched_is_the_default_for_many_chains_and_shards_consistently(engine):
-    """>= 1024 chains on a dense target take the batched path by default; a shard of the call (global chain ids through
+    """>= 512 chains on a dense target take the batched path by default; a shard of the call (global chain ids through
     chain_offset) reproduces the same chains bit for bit, whatever the other chains of its call are doing."""
     rng = np.random.default_rng(5)
     d, C = 64, 1100
@@ -101,3 +101,28 @@ def test_batched_is_the_default_for_many_chains_and_shards_consistently(engine):
     finally:
         del os.environ["MCMCB200_NUTS_BATCHED"]
     assert np.array_equal(part["draws"], r["draws"][1000:]) and np.array_equal(part["n_leapfrog"], r["n_leapfrog"][1000:])
+
+
+def test_deep_trees_use_the_global_tables_and_full_tiles(engine, monkeypatch):
+    """max_tree_depth = 12: the summary table (2299 entries) and the per-state leaf records no longer fit shared memory and live in
+    the chain's global area (the MEMO_SH = false build of the step kernel); n_dim = 128 = a full register tile (no bounds
+    predicates).  Tiny fixed step so that trees really get deep; the persistent kernel is the reference."""
+    rng = np.random.default_rng(17)
+    for d, depth, eps, C in ((128, 12, 0.004, 40), (256, 10, 0.05, 24), (10, 12, 0.002, 9)):
+        q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+        P = (q / np.logspace(0, 1, d)) @ q.T
+        P = (P + P.T) / 2
+        x0 = rng.normal(size=(C, d))
+        kw = dict(target_data=P.ravel(), n_burnin=0, n_keep=5, n_adapt_draws=0, step_size=eps, max_tree_depth=depth, rng_mode=engine.api.RNG_PHILOX, seed=3)
+        monkeypatch.setenv("MCMCB200_NUTS_BATCHED", "1")
+        r = engine.nuts(x0, "dense_gauss", **kw)
+        monkeypatch.setenv("MCMCB200_NUTS_BATCHED", "0")
+        monkeypatch.setenv("MCMCB200_NUTS_COOP", "0")
+        w = engine.nuts(x0, "dense_gauss", **kw)
+        monkeypatch.delenv("MCMCB200_NUTS_BATCHED")
+        monkeypatch.delenv("MCMCB200_NUTS_COOP")
+        assert r["kernel_launches"] > 50 and w["kernel_launches"] == 1
+        assert np.array_equal(r["n_leapfrog"], w["n_leapfrog"]) and np.array_equal(r["n_accept"], w["n_accept"]), (d, depth)
+        assert np.abs(r["draws"] - w["draws"]).max() <= TOL, (d, depth, np.abs(r["draws"] - w["draws"]).max())
+        if depth == 12 and d == 128:
+            assert r["n_leapfrog"].max() > 5 * 100   # deep trees did occur (a depth-9 doubling alone has 46 distinct states)
