@@ -933,7 +933,7 @@ static int rmhmc_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rn
         const bool user_metric = pr->target_id >= MCMCB200_USER_TARGET_BASE;
         if (user_metric ? !(user_target_has(USER_LAUNCH_RMHMC, pr->target_id) && pr->n_dim <= 64)
                         : !rmhmc_general_supported(pr->target_id, st->metric_id, pr->n_dim)) {
-            set_error("rmhmc: target %d has no registered metric %d for n_dim=%d (general kernel: n_dim <= 64)", pr->target_id, st->metric_id, pr->n_dim);
+            set_error("rmhmc: target %d has no registered metric %d for n_dim=%d (cube kernel: n_dim <= 64; FAST arithmetic with a contraction-form metric: n_dim <= 128)", pr->target_id, st->metric_id, pr->n_dim);
             return MCMCB200_ERR_UNSUPPORTED;
         }
         a.work_stride = rmhmc_general_work_doubles(pr->n_dim);

@@ -27,12 +27,15 @@
 #include "rmhmc_cta.h"
 #include <math_constants.h>
 #include <cstdlib>
+#include <type_traits>
 
 namespace mcmcb200
 {
 
 constexpr int RC_THREADS = 128;
-constexpr int RC_MAXD = 64;
+constexpr int RC_MAXD = 64;      // the tuned thread mappings (two threads per row / column half, register-tile elimination)
+constexpr int RC_MAXD_WIDE = 128;   // generic mappings (one thread per row): 64 < n_dim <= 128, one CTA per SM (the matrix is 133 KB)
+// WIDE is a template parameter of the kernel and its helpers; MCMCB200_RMHMC_WIDE=1 selects it at n_dim <= 64 too (tests: identical bits)
 
 __device__ __forceinline__ void rc_sync() { __syncthreads(); }
 
@@ -52,18 +55,25 @@ __device__ __forceinline__ double rc_block_sum(double v, double* red)
 struct FunnelSoftabsCta {
     FunnelSoftabsScalars<false> sc;
     __device__ __forceinline__ void prepare(const double* xs, int d) { sc.compute(xs, d); }
-    __device__ __forceinline__ void build(const double* xs, int d, double* G, int ld) const
+    __device__ __forceinline__ double entry(const double* xs, int i, int j) const
     {
+        if (i == 0 && j == 0) return sc.g11.v;
+        if (i == 0 || j == 0) return sc.w.v * xs[i + j];
+        return ((i == j) ? sc.fa.v : 0.0) + (sc.P.v * xs[i]) * xs[j];
+    }
+    template <bool WIDE> __device__ __forceinline__ void build(const double* xs, int d, double* G, int ld) const
+    {
+        if (WIDE) {   // one thread per row
+            const int i = threadIdx.x;
+            if (i < d)
+                for (int j = 0; j < d; ++j) G[(size_t)j * ld + i] = entry(xs, i, j);
+            return;
+        }
         const int i = threadIdx.x & 63;
         if (i < d)
-            for (int j = threadIdx.x >> 6; j < d; j += 2) {
-                double g;
-                if (i == 0 && j == 0) g = sc.g11.v;
-                else if (i == 0 || j == 0) g = sc.w.v * xs[i + j];
-                else g = ((i == j) ? sc.fa.v : 0.0) + (sc.P.v * xs[i]) * xs[j];
-                G[(size_t)j * ld + i] = g;
-            }
+            for (int j = threadIdx.x >> 6; j < d; j += 2) G[(size_t)j * ld + i] = entry(xs, i, j);
     }
+    template <bool WIDE>
     __device__ __forceinline__ void contract(const double* xs, int d, const double* Am, int ld, const double* u, const double* up, double* vs, double* red,
                                              double* c) const
     {
@@ -71,7 +81,15 @@ struct FunnelSoftabsCta {
         double* yr = vs;
         double* yc = vs + d;
         const int t = threadIdx.x, i = t & 63;
-        if (i < d) {
+        if (WIDE) {   // one thread per row: both products
+            if (t < d) {
+                double acc = 0.0, acc2 = 0.0;
+                for (int j = 1; j < d; ++j) acc = fma(Am[(size_t)j * ld + t], xs[j], acc);
+                for (int j = 1; j < d; ++j) acc2 = fma(Am[(size_t)t * ld + j], xs[j], acc2);
+                yr[t] = acc;
+                yc[t] = acc2;
+            }
+        } else if (i < d) {
             double acc = 0.0;
             if (t < 64) { for (int j = 1; j < d; ++j) acc = fma(Am[(size_t)j * ld + i], xs[j], acc); yr[i] = acc; }
             else { for (int j = 1; j < d; ++j) acc = fma(Am[(size_t)i * ld + j], xs[j], acc); yc[i] = acc; }
@@ -109,12 +127,19 @@ struct FunnelSoftabsCta {
 struct FunnelFisherCta {   // G = diag(1/9 + (d-1)/2, e^-v, ..., e^-v); dG/dv = diag(0, -e^-v, ...), everything else zero
     double ev;
     __device__ __forceinline__ void prepare(const double* xs, int) { ev = exp(-xs[0]); }
-    __device__ __forceinline__ void build(const double*, int d, double* G, int ld) const
+    template <bool WIDE> __device__ __forceinline__ void build(const double*, int d, double* G, int ld) const
     {
+        if (WIDE) {
+            const int i = threadIdx.x;
+            if (i < d)
+                for (int j = 0; j < d; ++j) G[(size_t)j * ld + i] = (i != j) ? 0.0 : ((i == 0) ? 1.0 / 9.0 + (double)(d - 1) / 2.0 : ev);
+            return;
+        }
         const int i = threadIdx.x & 63;
         if (i < d)
             for (int j = threadIdx.x >> 6; j < d; j += 2) G[(size_t)j * ld + i] = (i != j) ? 0.0 : ((i == 0) ? 1.0 / 9.0 + (double)(d - 1) / 2.0 : ev);
     }
+    template <bool WIDE>
     __device__ __forceinline__ void contract(const double*, int d, const double* Am, int ld, const double* u, const double* up, double*, double* red,
                                              double* c) const
     {
@@ -136,14 +161,16 @@ struct FunnelFisherCta {   // G = diag(1/9 + (d-1)/2, e^-v, ..., e^-v); dG/dv = 
 // update by giving it the multiplier pivot - 1 (W(k,j) - (pivot - 1) W(k,j) / pivot = W(k,j) / pivot).
 // piv: d ints; rc: 2 (RC_MAXD + 2) doubles (the scaled pivot row and the multiplier column), 16-byte aligned.
 // A zero / NaN pivot propagates NaN like the reference's LU does.
-__device__ void rc_inverse_inplace(double* W, int d, int ld, int* piv, double* rc)
+// WIDE (64 < n_dim <= 128): 64 row pairs x 2 column groups instead of 32 x 4; same operations per element.
+template <bool WIDE> __device__ void rc_inverse_inplace(double* W, int d, int ld, int* piv, double* rc)
 {
+    constexpr int NRP = WIDE ? 64 : 32, NCG = RC_THREADS / NRP, MAXD = WIDE ? RC_MAXD_WIDE : RC_MAXD;
     double* rowbuf = rc;
-    double* colbuf = rc + RC_MAXD + 2;
-    const int t = threadIdx.x, rp = t & 31, cg = t >> 5;
+    double* colbuf = rc + MAXD + 2;
+    const int t = threadIdx.x, rp = t % NRP, cg = t / NRP;
     const int i0 = 2 * rp;
     const bool rows_ok = i0 < d;
-    const int cb = ((d + 7) / 8) * 2;                 // columns per thread group (even)
+    const int cb = ((d + 2 * NCG - 1) / (2 * NCG)) * 2;   // columns per thread group (even)
     const int jb = cg * cb, je = (jb + cb < d) ? jb + cb : d;
     for (int k = 0; k < d; ++k) {
         // pivot: first maximum of |W(r, k)|, r >= k (warp 0; a NaN never wins, a NaN at (k,k) keeps r = k)
@@ -181,10 +208,16 @@ __device__ void rc_inverse_inplace(double* W, int d, int ld, int* piv, double* r
         }
         const double pv = W[(size_t)k * ld + k];
         const double rinv = 1.0 / pv;
-        if (t < d) rowbuf[t] = W[(size_t)t * ld + k] * rinv;                                  // scaled pivot row
-        else if (t >= 64 && t - 64 < d + 1) {
-            const int r = t - 64;
-            colbuf[r] = (r == k) ? pv - 1.0 : ((r < d) ? W[(size_t)k * ld + r] : 0.0);        // multipliers (see above); padding row: 0
+        if (WIDE) {
+            if (t < d) rowbuf[t] = W[(size_t)t * ld + k] * rinv;                              // scaled pivot row
+            for (int r = t; r < d + 1; r += RC_THREADS)
+                colbuf[r] = (r == k) ? pv - 1.0 : ((r < d) ? W[(size_t)k * ld + r] : 0.0);    // multipliers (see above); padding row: 0
+        } else {
+            if (t < d) rowbuf[t] = W[(size_t)t * ld + k] * rinv;                              // scaled pivot row
+            else if (t >= 64 && t - 64 < d + 1) {
+                const int r = t - 64;
+                colbuf[r] = (r == k) ? pv - 1.0 : ((r < d) ? W[(size_t)k * ld + r] : 0.0);    // multipliers (see above); padding row: 0
+            }
         }
         rc_sync();
         if (rows_ok) {
@@ -406,9 +439,10 @@ __device__ __noinline__ void rc_inverse_regtile(double* W, int d, int ld, double
 
 // in-place lower Cholesky of the shared matrix (right-looking); the strict upper triangle keeps the input's entries — the
 // Eigen matrixLLT storage the reference multiplies with in full; returns nothing, L in the lower triangle
-__device__ void rc_cholesky_inplace(double* W, int d, int ld)
+template <bool WIDE> __device__ void rc_cholesky_inplace(double* W, int d, int ld)
 {
-    const int t = threadIdx.x, i = t & 63, jpar = t >> 6;
+    constexpr bool wide = WIDE;   // one thread per row instead of two
+    const int t = threadIdx.x, i = wide ? t : (t & 63), jpar = t >> 6;
     for (int j = 0; j < d; ++j) {
         const double dj = sqrt(W[(size_t)j * ld + j]);
         rc_sync();
@@ -417,7 +451,8 @@ __device__ void rc_cholesky_inplace(double* W, int d, int ld)
         // trailing update of the lower triangle: W(i, k) -= L(i, j) L(k, j), k > j, i >= k
         if (i < d && i > j) {
             const double lij = W[(size_t)j * ld + i];
-            for (int k = j + 1 + ((jpar + j + 1) & 1); k <= i; k += 2) W[(size_t)k * ld + i] = fma(-lij, W[(size_t)j * ld + k], W[(size_t)k * ld + i]);
+            if (wide) for (int k = j + 1; k <= i; ++k) W[(size_t)k * ld + i] = fma(-lij, W[(size_t)j * ld + k], W[(size_t)k * ld + i]);
+            else for (int k = j + 1 + ((jpar + j + 1) & 1); k <= i; k += 2) W[(size_t)k * ld + i] = fma(-lij, W[(size_t)j * ld + k], W[(size_t)k * ld + i]);
         }
         rc_sync();
     }
@@ -425,26 +460,27 @@ __device__ void rc_cholesky_inplace(double* W, int d, int ld)
 
 // n_dim > 32: the register-tile elimination; smaller matrices would mostly multiply padding there
 __device__ int rc_force_shared_gj = 0;   // MCMCB200_RMHMC_REGTILE=0 (tests: the two eliminations must agree bit for bit)
-__device__ __forceinline__ void rc_invert(double* W, int d, int ld, int* piv, double* buf, int* perm)
+template <bool WIDE> __device__ __forceinline__ void rc_invert(double* W, int d, int ld, int* piv, double* buf, int* perm)
 {
-    if (d > 32 && !rc_force_shared_gj) rc_inverse_regtile(W, d, ld, buf, perm);
-    else rc_inverse_inplace(W, d, ld, piv, buf);
+    if (WIDE) rc_inverse_inplace<true>(W, d, ld, piv, buf);
+    else if (d > 32 && !rc_force_shared_gj) rc_inverse_regtile(W, d, ld, buf, perm);
+    else rc_inverse_inplace<false>(W, d, ld, piv, buf);
 }
 
 __device__ double2 rc_rng_tab_g[RNG_TAB_DOUBLE2];
 __global__ void rc_build_rng_tab() { build_rng_tables(rc_rng_tab_g); }   // same values from every launch: concurrent calls do not conflict
 
 // 128 registers: four CTAs (16 warps) per SM — the eliminations are latency chains that only more resident warps hide
-template <class T, class MC, int RNGM>
-__global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
+template <class T, class MC, int RNGM, bool WIDE>
+__global__ void __launch_bounds__(RC_THREADS, WIDE ? 1 : 4) rmhmc_cta_kernel(const __grid_constant__ RmhmcLaunch a)
 {
     extern __shared__ __align__(16) double smem[];
     // Box-Muller tables: read from global memory (built once per launch by rc_build_rng_tab; d normals per draw use them) —
     // 16 KB of shared memory per CTA would cap the SM at three CTAs
     const double2* const rng_tab = rc_rng_tab_g;
-    __shared__ int piv[RC_MAXD];
+    __shared__ int piv[RC_MAXD_WIDE];
     __shared__ double red[4];
-    __shared__ __align__(16) double rcbuf[3 * RC_MAXD];   // >= 2 (RC_MAXD + 2)
+    __shared__ __align__(16) double rcbuf[2 * (RC_MAXD_WIDE + 2)];   // >= 3 RC_MAXD (register-tile elimination)
     __shared__ __align__(16) int rtperm[2 * RC_MAXD];
     __shared__ double sc_u, sc_lp;   // broadcast scalars (uniform, log-density)
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
@@ -471,34 +507,64 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
     // warp 0: d normals of `draw` into dst (shared)
     auto normals_to = [&](long long draw, double* dst) {
         if (warp == 0) {
-            double z[2];
-            rng.template normals<2, false>(a.rng, draw, d, lane, rng_tab, z);
-            if (2 * lane < d) dst[2 * lane] = z[0];
-            if (2 * lane + 1 < d) dst[2 * lane + 1] = z[1];
+            if (!WIDE || d <= 64) {
+                double z[2];
+                rng.template normals<2, false>(a.rng, draw, d, lane, rng_tab, z);
+                if (2 * lane < d) dst[2 * lane] = z[0];
+                if (2 * lane + 1 < d) dst[2 * lane + 1] = z[1];
+            } else {
+                double z[4];
+                rng.template normals<4, false>(a.rng, draw, d, lane, rng_tab, z);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (elem_index(lane, k) < d) dst[elem_index(lane, k)] = z[k];
+            }
         }
     };
     // warp 0: log pi and/or gradient at the shared vector xin -> sc_lp / gv
     auto target_at = [&](const double* xin, bool want_value, bool want_grad) {
         if (warp == 0) {
-            double x[2], g[2];
-            x[0] = (2 * lane < d) ? xin[2 * lane] : 0.0;
-            x[1] = (2 * lane + 1 < d) ? xin[2 * lane + 1] : 0.0;
-            double v = 0.0;
-            if (want_value && want_grad) v = T::template eval<2, false, true, true, true>(a.tdata, wctx, x, g);
-            else if (want_value) v = T::template eval<2, false, true, false, true>(a.tdata, wctx, x, g);
-            else T::template eval<2, false, false, true, true>(a.tdata, wctx, x, g);
-            if (want_grad) {
-                if (2 * lane < d) gv[2 * lane] = g[0];
-                if (2 * lane + 1 < d) gv[2 * lane + 1] = g[1];
-            }
-            if (want_value && lane == 0) sc_lp = v;
+            auto run = [&](auto epl_tag) {
+                constexpr int E = decltype(epl_tag)::value;
+                double x[E], g[E];
+#pragma unroll
+                for (int k = 0; k < E; ++k) x[k] = (elem_index(lane, k) < d) ? xin[elem_index(lane, k)] : 0.0;
+                double v = 0.0;
+                if (want_value && want_grad) v = T::template eval<E, false, true, true, true>(a.tdata, wctx, x, g);
+                else if (want_value) v = T::template eval<E, false, true, false, true>(a.tdata, wctx, x, g);
+                else T::template eval<E, false, false, true, true>(a.tdata, wctx, x, g);
+                if (want_grad) {
+#pragma unroll
+                    for (int k = 0; k < E; ++k)
+                        if (elem_index(lane, k) < d) gv[elem_index(lane, k)] = g[k];
+                }
+                if (want_value && lane == 0) sc_lp = v;
+            };
+            if constexpr (!WIDE) run(std::integral_constant<int, 2>());
+            else if (d <= 64) run(std::integral_constant<int, 2>());
+            else run(std::integral_constant<int, 4>());
         }
         rc_sync();
     };
     // y = Am v (threads 0..63) and optionally y2 = Am^T v (threads 64..127)
+    constexpr bool wide = WIDE;   // generic thread mappings: one thread per row
     auto gemv2 = [&](const double* Am, const double* v, double* y, double* y2) {
         const int i = t & 63;
-        if (i < d) {
+        if (wide) {
+            if (t < d) {
+                double acc = 0.0, acc2 = 0.0;
+                int j = 0;
+                for (; j + 1 < d; j += 2) { acc = fma(Am[(size_t)j * ld + t], v[j], acc); acc2 = fma(Am[(size_t)(j + 1) * ld + t], v[j + 1], acc2); }
+                if (j < d) acc = fma(Am[(size_t)j * ld + t], v[j], acc);
+                y[t] = acc + acc2;
+                if (y2) {
+                    acc = 0.0; acc2 = 0.0; j = 0;
+                    for (; j + 1 < d; j += 2) { acc = fma(Am[(size_t)t * ld + j], v[j], acc); acc2 = fma(Am[(size_t)t * ld + j + 1], v[j + 1], acc2); }
+                    if (j < d) acc = fma(Am[(size_t)t * ld + j], v[j], acc);
+                    y2[t] = acc + acc2;
+                }
+            }
+        } else if (i < d) {
             double acc = 0.0;
             double acc2 = 0.0;
             int j = 0;
@@ -519,10 +585,10 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
     // positive definite, which the accept rule then treats like the reference does — for the metric `m` prepared at xm; W is
     // used as scratch and holds G again on return
     auto logdet_chol = [&](const MC& m, const double* xm) -> double {
-        rc_cholesky_inplace(W, d, ld);
+        rc_cholesky_inplace<WIDE>(W, d, ld);
         const double s = rc_block_sum(t < d ? 2.0 * log(W[(size_t)t * ld + t]) : 0.0, red);
         rc_sync();
-        m.build(xm, d, W, ld);
+        m.template build<WIDE>(xm, d, W, ld);
         rc_sync();
         return s;
     };
@@ -530,14 +596,29 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
     auto mntm_update = [&](const double* y, const double* q, const double* Am, const MC& m, const double* xm, double* out) {
         target_at(y, false, true);
         gemv2(Am, q, uv, upv);
-        m.contract(xm, d, Am, ld, uv, upv, scr, red, cv);
+        m.template contract<WIDE>(xm, d, Am, ld, uv, upv, scr, red, cv);
         if (t < d) out[t] = (eps * fma(0.5, cv[t], -gv[t])) * 0.5;
         rc_sync();
     };
     auto store_global = [&](double* G) {   // W (ld) -> global (d), before it is inverted in place
+        if (wide) {
+            if (t < d)
+                for (int j = 0; j < d; ++j) G[(size_t)j * d + t] = W[(size_t)j * ld + t];
+            return;
+        }
         const int i = t & 63;
         if (i < d)
             for (int j = t >> 6; j < d; j += 2) G[(size_t)j * d + i] = W[(size_t)j * ld + i];
+    };
+    auto load_global = [&](const double* G) {   // global (d) -> W (ld)
+        if (wide) {
+            if (t < d)
+                for (int j = 0; j < d; ++j) W[(size_t)j * ld + t] = G[(size_t)j * d + t];
+            return;
+        }
+        const int i = t & 63;
+        if (i < d)
+            for (int j = t >> 6; j < d; j += 2) W[(size_t)j * ld + i] = G[(size_t)j * d + i];
     };
 
     // ---- set-up: pre-loop normals (value unused), metric / inverse / energy at the initial point ----
@@ -545,11 +626,11 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
     if (t < d) xprev[t] = a.x0[(a.broadcast_x0 ? 0 : chain * d) + t];
     rc_sync();
     metric.prepare(xprev, d);
-    metric.build(xprev, d, W, ld);
+    metric.template build<WIDE>(xprev, d, W, ld);
     rc_sync();
     store_global(Gacc);
     double logdet_prev = logdet_chol(metric, xprev);
-    rc_invert(W, d, ld, piv, rcbuf, rtperm);
+    rc_invert<WIDE>(W, d, ld, piv, rcbuf, rtperm);
     for (int k = t; k < d * ld; k += RC_THREADS) Ainv0[k] = W[k];
     MC metric_prev = metric;   // the start-of-trajectory metric (Q17) of every draw until an accept replaces it
     target_at(xprev, true, false);
@@ -568,13 +649,9 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
             if (lane == 0) sc_u = u;
         }
         // p = chol(G_prev) z with the Eigen matrixLLT storage quirk when asked for (Q8); K0 = p.(G_prev^-1 p)/2
-        {
-            const int i = t & 63;
-            if (i < d)
-                for (int j = t >> 6; j < d; j += 2) W[(size_t)j * ld + i] = Gacc[(size_t)j * d + i];
-        }
+        load_global(Gacc);
         rc_sync();
-        rc_cholesky_inplace(W, d, ld);
+        rc_cholesky_inplace<WIDE>(W, d, ld);
         if (t < d) {
             double acc = 0.0;
             const int jmax = (a.chol_mode == MCMCB200_CHOL_EIGEN_LLT) ? d : t + 1;
@@ -602,9 +679,9 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
             for (int kk = 0; kk < a.n_fp; ++kk) {   // position step, fixed point: w = x + (eps/2)(G_prev^-1 + G(w)^-1) p
                 MC mw;
                 mw.prepare(wv, d);
-                mw.build(wv, d, W, ld);
+                mw.template build<WIDE>(wv, d, W, ld);
                 rc_sync();
-                rc_invert(W, d, ld, piv, rcbuf, rtperm);
+                rc_invert<WIDE>(W, d, ld, piv, rcbuf, rtperm);
                 if (t < d) {
                     double acc = 0.0;
                     for (int j = 0; j < d; ++j) acc = fma(Ainv0[(size_t)j * ld + t] + W[(size_t)j * ld + t], heps * pv[j], acc);
@@ -617,13 +694,13 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
             if (t < d) xcur[t] = wv[t];
             rc_sync();
             metric_new.prepare(xcur, d);
-            metric_new.build(xcur, d, W, ld);
+            metric_new.template build<WIDE>(xcur, d, W, ld);
             rc_sync();
             if (s + 1 == a.n_leap) {   // only the end point's metric can become the next draw's G_prev and enters the energy
                 store_global(Gnew);
                 logdet_new = logdet_chol(metric_new, xcur);
             }
-            rc_invert(W, d, ld, piv, rcbuf, rtperm);
+            rc_invert<WIDE>(W, d, ld, piv, rcbuf, rtperm);
             have_new = true;
             mntm_update(xcur, pv, W, metric_new, xcur, wv);
             if (t < d) pv[t] = pv[t] + wv[t];
@@ -631,9 +708,7 @@ __global__ void __launch_bounds__(RC_THREADS, 4) rmhmc_cta_kernel(const __grid_c
         }
         if (!have_new) {   // n_leap == 0: the "new" metric is the current one
             for (int k = t; k < d * ld; k += RC_THREADS) W[k] = Ainv0[k];
-            const int i = t & 63;
-            if (i < d)
-                for (int j = t >> 6; j < d; j += 2) Gnew[(size_t)j * d + i] = Gacc[(size_t)j * d + i];
+            for (int k = t; k < d * d; k += RC_THREADS) Gnew[k] = Gacc[k];
             rc_sync();
         }
         target_at(xcur, true, false);
@@ -669,7 +744,7 @@ long long rmhmc_cta_work_doubles(int d) { return 2ll * d * d + (long long)d * ((
 
 bool rmhmc_cta_applicable(int target_id, int metric_id, int d, bool strict, bool has_bounds)
 {
-    if (strict || has_bounds || d < 2 || d > RC_MAXD) return false;
+    if (strict || has_bounds || d < 2 || d > RC_MAXD_WIDE) return false;
     return target_id == MCMCB200_TARGET_FUNNEL && metric_id >= 0 && metric_id <= 2;
 }
 
@@ -681,6 +756,7 @@ template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
         const char* e = std::getenv("MCMCB200_RMHMC_REGTILE");
         const int v = (e && e[0] == '0') ? 1 : 0;
         MCMCB200_CUDA_TRY(cudaMemcpyToSymbolAsync(rc_force_shared_gj, &v, sizeof(int), 0, cudaMemcpyHostToDevice, a.stream));
+
     }
     if (a.rng.mode == RNG_PHILOX) rc_build_rng_tab<<<1, 256, 0, a.stream>>>();
     auto launch = [&](auto kern) -> int {
@@ -690,8 +766,10 @@ template <class T, class MC> static int launch_cta(const RmhmcLaunch& a)
         MCMCB200_CUDA_TRY(cudaGetLastError());
         return MCMCB200_OK;
     };
-    if (a.rng.mode == RNG_PHILOX) return launch(rmhmc_cta_kernel<T, MC, RNG_PHILOX>);
-    return launch(rmhmc_cta_kernel<T, MC, RNG_TAPE>);
+    const char* ew = std::getenv("MCMCB200_RMHMC_WIDE");
+    const bool wide = d > RC_MAXD || (ew && ew[0] == '1');
+    if (a.rng.mode == RNG_PHILOX) return wide ? launch(rmhmc_cta_kernel<T, MC, RNG_PHILOX, true>) : launch(rmhmc_cta_kernel<T, MC, RNG_PHILOX, false>);
+    return wide ? launch(rmhmc_cta_kernel<T, MC, RNG_TAPE, true>) : launch(rmhmc_cta_kernel<T, MC, RNG_TAPE, false>);
 }
 
 int launch_rmhmc_cta(const RmhmcLaunch& a)

@@ -193,8 +193,11 @@ def test_funnel_other_samplers_and_unsupported_combinations(engine, oracle):
             for c in range(C):
                 o = oracle.run_chain(smp, ol.TGT_FUNNEL, None, x0[c], st, seed=5, rng_mode=ol.RNG_PHILOX, chain_id=c, sum_mode=ol.SUM_WARP)
                 assert np.abs(r["draws"][c] - o["draws"]).max() <= TOL and r["n_accept"][c] == o["n_accept"], (smp, d, c)
-    with pytest.raises(engine.McmcB200Error) as ei:
-        engine.rmhmc(np.zeros((2, 65)), "funnel", n_burnin=1, n_keep=1)
+    with pytest.raises(engine.McmcB200Error) as ei:   # beyond the CTA kernel's generic mappings (n_dim <= 128)
+        engine.rmhmc(np.zeros((2, 129)), "funnel", n_burnin=1, n_keep=1)
+    assert ei.value.code == engine.api.ERR_UNSUPPORTED
+    with pytest.raises(engine.McmcB200Error) as ei:   # STRICT arithmetic runs on the cube kernel: n_dim <= 64
+        engine.rmhmc(np.zeros((2, 65)), "funnel", n_burnin=1, n_keep=1, arith=engine.api.ARITH_STRICT)
     assert ei.value.code == engine.api.ERR_UNSUPPORTED
     with pytest.raises(engine.McmcB200Error) as ei:
         engine.rmhmc(np.zeros((2, 8)), "funnel", n_burnin=1, n_keep=1, metric_id=7)
@@ -286,3 +289,41 @@ def test_register_tile_elimination_reproduces_the_shared_memory_one(engine, monk
         monkeypatch.delenv("MCMCB200_RMHMC_REGTILE")
         assert np.array_equal(a["draws"], b["draws"], equal_nan=True), (d, metric_id, np.nanmax(np.abs(a["draws"] - b["draws"])))
         assert np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["logp"], b["logp"], equal_nan=True)
+
+
+def test_generic_thread_mappings_and_n_dim_up_to_128(engine, oracle, monkeypatch):
+    """64 < n_dim <= 128: the CTA kernel switches from its tuned mappings (two threads per row, register-tile elimination) to
+    generic ones (one thread per row, 64 row pairs x 2 column groups in the elimination; the 133 KB matrix leaves one CTA per
+    SM).  (i) MCMCB200_RMHMC_WIDE=1 forces the generic mappings at n_dim <= 64, where they must reproduce the tuned ones bit for
+    bit — every element sees the same operations in the same order; (ii) n_dim = 96 against the oracle (Philox, FAST), both
+    funnel metrics; (iii) n_dim = 128 stays finite and accepts."""
+    rng = np.random.default_rng(123)
+    for d, metric_id in ((64, 2), (40, 1), (7, 2), (33, 2)):
+        x0 = _funnel_start(16, d, rng)
+        kw = dict(n_leap_steps=3, step_size=0.02, n_fp_steps=4, n_burnin=1, n_keep=5, want_logp=True, metric_id=metric_id,
+                  rng_mode=engine.api.RNG_PHILOX, seed=19)
+        a = engine.rmhmc(x0, "funnel", **kw)
+        monkeypatch.setenv("MCMCB200_RMHMC_WIDE", "1")
+        b = engine.rmhmc(x0, "funnel", **kw)
+        monkeypatch.delenv("MCMCB200_RMHMC_WIDE")
+        assert np.array_equal(a["draws"], b["draws"], equal_nan=True), (d, metric_id, np.nanmax(np.abs(a["draws"] - b["draws"])))
+        assert np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["logp"], b["logp"], equal_nan=True)
+    d, C = 96, 3
+    for metric_id in (2, 1):
+        x0 = _funnel_start(C, d, rng)
+        st = ol.Settings(n_burnin=1, n_keep=4, n_leap_steps=2, step_size=0.02, n_fp_steps=3, metric_id=metric_id)
+        r = engine.rmhmc(x0, "funnel", n_leap_steps=2, step_size=0.02, n_fp_steps=3, n_burnin=1, n_keep=4, metric_id=metric_id,
+                         rng_mode=engine.api.RNG_PHILOX, seed=77, chain_offset=5)
+        tracked = 0
+        for c in range(C):
+            o = oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, x0[c], st, seed=77, rng_mode=ol.RNG_PHILOX, chain_id=5 + c, sum_mode=ol.SUM_WARP,
+                                 want_margins=True)
+            pert = lambda c=c: oracle.run_chain(ol.RMHMC, ol.TGT_FUNNEL, None, np.nextafter(x0[c], np.inf), st, seed=77, rng_mode=ol.RNG_PHILOX,
+                                                chain_id=5 + c, sum_mode=ol.SUM_WARP)["draws"]
+            if assert_tracks_or_flips_at_threshold(r["draws"][c], o, 1, TOL, "n_dim=96 metric %d chain %d" % (metric_id, c), rerun_perturbed=pert):
+                assert r["n_accept"][c] == o["n_accept"]
+                tracked += 1
+        assert tracked >= C - 1, (metric_id, tracked)
+    x0 = _funnel_start(8, 128, rng)
+    r = engine.rmhmc(x0, "funnel", n_leap_steps=2, step_size=0.01, n_fp_steps=3, n_burnin=1, n_keep=4, metric_id=2, rng_mode=engine.api.RNG_PHILOX, seed=3)
+    assert np.isfinite(r["draws"]).all() and r["n_accept"].sum() > 0
