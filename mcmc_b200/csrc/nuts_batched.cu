@@ -75,7 +75,7 @@ __host__ __device__ inline int ls_memo_entries(int max_depth)
 // w1 = n_alpha (21 bits) | epoch << 21 (11 bits, 0 = empty)
 struct LsSummary { double alpha; unsigned w0, w1; };
 
-enum { PH_INIT0 = 0, PH_INIT_GRAD, PH_INIT_LF, PH_DRAW_BEGIN, PH_DBL_BEGIN, PH_DBL_G0, PH_WALK_INIT, PH_LEAF, PH_WALK, PH_DRAW_END, PH_DONE };
+enum { PH_INIT0 = 0, PH_INIT_GRAD, PH_INIT_LF, PH_DRAW_BEGIN, PH_DBL_BEGIN, PH_DBL_G0, PH_WALK_INIT, PH_LEAF, PH_WALK, PH_DRAW_END, PH_DONE, PH_DBL_END };
 
 // a chain's control block: everything the coroutine needs besides its vectors (which sit in the chain's work area)
 struct LsCtl {
@@ -121,6 +121,8 @@ struct LsArgs {
     double* work;            // per-chain areas
     long long work_stride;
     int* n_running;          // this group's running-chain counter
+    int* next_chain;         // persistent kernel: the next chain to hand to a free warp
+    int split_dbl_end;       // hand the closing work of a doubling to the next round (MCMCB200_NUTS_SPLIT=0 keeps it in the leaf's resume)
     long long chain_base;    // this launch covers chains [chain_base, chain_base + n_group) of the call
     long long n_group;
     const unsigned* jmask;   // [max_depth][m_max + 1]: for a doubling of depth D and state k, the levels j whose subtree T(j, k - j - 1) exists
@@ -310,18 +312,17 @@ __global__ void nuts_ls_init(LsCtl* ctl, long long n_chains, int* n_running, int
     for (int i = 0; i < LS_CTL_WORDS; ++i) w[i] = 0ull;   // ph = PH_INIT0
 }
 
-// One round of every chain's coroutine.
-// 128 registers, 4 CTAs per SM at n_dim <= 256 (measured: 96 registers / 5 CTAs spills and is 10 % slower, 168 / 3 is 12 % slower)
-template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bounds__(LS_WARPS * 32, EPL <= 8 ? 4 : 2) nuts_ls_step(const __grid_constant__ LsArgs a)
+// A chain's resume: from the arrival of the product it asked for to its next product request (or the end of its run).
+//   c / memo : control block and (MEMO_SH) summary table in shared memory;  memo_g: the table's home in global memory
+//   TX / TRh : where the next request's position / half-kicked momentum are staged (global rows, or shared memory in the
+//              persistent kernel);  xt, rt, yin: the pending position, half-kicked momentum and the product, already loaded
+//   PERSIST  : the control block and table stay on chip for the chain's whole run (no write-through, see nuts_pc_kernel)
+template <int EPL, int RNGM, bool MEMO_SH, bool FT, bool PERSIST>
+__device__ __forceinline__ void ls_resume(const LsArgs& a, const long long chain, const int lane, LsCtl& c, LsSummary* const memo,
+                                          LsSummary* const memo_g, double* const TX, double* const TRh, double (&xt)[EPL], double (&rt)[EPL],
+                                          const double (&yin)[EPL])
 {
-    __shared__ __align__(16) LsCtl ctl_sh[LS_WARPS];
-    __shared__ __align__(16) LsSummary memo_sh[MEMO_SH ? LS_WARPS * LS_TAB_SMEM : 1];
     const int* const lvl_off = a.lvl_off;   // kernel-parameter (constant) bank, indexed dynamically
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long chain = a.chain_base + (long long)blockIdx.x * LS_WARPS + warp;
-    if (chain >= a.chain_base + a.n_group) return;
-    LsCtl* const gctl = a.ctl + chain;
-    LsCtl& c = ctl_sh[warp];
     const int d = a.d;
     const int m_max = a.m_max;
     const int memo_n = a.memo_n;
@@ -332,42 +333,11 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
     double* const Wxn = W + 3 * d;
     double* const Wrp = W + 4 * d;
     double* const Wrn = W + 5 * d;
-    double* const TRh = W + 6 * d;
     double* const G0 = W + 7 * d;
     double* const Wst = W + 8 * d;   // state k (1-based): x at Wst + (k-1)*2d, r at + d
     double* const Us = Wst + (size_t)2 * d * m_max;
     double* const Ks = Us + m_max;
-    double* const TX = a.TX + chain * d;
-    const double* const TY = a.TY + chain * d;
-    // summary table: the chain's copy in global memory is its home; with max_tree_depth <= 10 the walk works on a shared-memory
-    // copy (loaded here; every update is written through), so that no look-up of the walk pays a global-memory latency
-    LsSummary* const memo_g = reinterpret_cast<LsSummary*>(Ks + m_max);
-    LsSummary* const memo = MEMO_SH ? memo_sh + warp * LS_TAB_SMEM : memo_g;
-    // everything the resume needs is requested at once — control block and summary table straight into shared memory
-    // (cp.async: no registers), the three vectors of the pending product into registers — so that one memory latency is exposed
-    {
-        const char* src = reinterpret_cast<const char*>(gctl);
-        char* dst = reinterpret_cast<char*>(&c);
-#pragma unroll
-        for (int q = 0; q < (LS_CTL_WORDS / 2 + 31) / 32; ++q)
-            if (lane + 32 * q < LS_CTL_WORDS / 2) ls_cp_async16(dst + 16 * (lane + 32 * q), src + 16 * (lane + 32 * q));
-        if (MEMO_SH) {
-            const char* ms = reinterpret_cast<const char*>(memo_g);
-            char* md = reinterpret_cast<char*>(memo);
-#pragma unroll
-            for (int q = 0; q < LS_TAB_SMEM / 32; ++q)
-                if (lane + 32 * q < memo_n) ls_cp_async16(md + 16 * (lane + 32 * q), ms + 16 * (lane + 32 * q));
-        }
-        asm volatile("cp.async.commit_group;\n" ::);
-    }
-    double xt[EPL], rt[EPL], gt[EPL];   // pending position / half-kicked momentum on entry; then the tip of the trajectory
-    double yin[EPL];                      // the product the chain asked for
-    ldv<EPL, FT>(TX, d, lane, xt);
-    ldv<EPL, FT>(TRh, d, lane, rt);
-    ldv<EPL, FT>(TY, d, lane, yin);
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    __syncwarp();
-    if (c.ph == PH_DONE) return;
+    double gt[EPL];
     const long long dbg_t0 = a.dbg ? clock64() : 0;
     long long dbg_t1 = 0, dbg_t2 = 0, dbg_t3 = 0;
     const int dbg_ph = c.ph, dbg_t = c.t, dbg_depth = c.depth;   // (dbg_ph also steers the draw-boundary split)
@@ -421,7 +391,10 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
             load_vec<EPL>(a.x0 + (a.broadcast_x0 ? 0 : chain * d), d, lane, x);
             stv<EPL>(Wprev, d, lane, x);
             stv<EPL>(TX, d, lane, x);
-            for (int i = lane; i < memo_n; i += 32) { memo_g[i].alpha = 0.0; memo_g[i].w0 = 0u; memo_g[i].w1 = 0u; }
+            {
+                LsSummary* const mz = PERSIST ? memo : memo_g;   // (the launched kernel reloads its working copy from the home every round)
+                for (int i = lane; i < memo_n; i += 32) { mz[i].alpha = 0.0; mz[i].w0 = 0u; mz[i].w1 = 0u; }
+            }
             ph = PH_INIT_GRAD;
             yielded = true;
             break;
@@ -497,7 +470,7 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
                 // just finished a state and walked the tree hands it to the next round (which costs this chain one idle
                 // GEMM row per draw) instead of stretching this launch for every other chain of the group
                 ph = PH_DRAW_END;
-                yielded = (dbg_ph == PH_LEAF);
+                yielded = (dbg_ph == PH_LEAF || dbg_ph == PH_DBL_END);
                 break;
             }
             const double zz = rng.uniform_at(a.rng, t, ucount++, ubase_cur);        // :233
@@ -507,7 +480,7 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
             computed = 0;
             // new restart point / direction: the summaries of the previous doubling are void
             if (++epoch > LS_EPOCH_MAX) {
-                for (int i = lane; i < memo_n; i += 32) { memo_g[i].w1 = 0u; if (MEMO_SH) memo[i].w1 = 0u; }   // home and working copy
+                for (int i = lane; i < memo_n; i += 32) { if (!PERSIST) memo_g[i].w1 = 0u; if (MEMO_SH) memo[i].w1 = 0u; }   // home and working copy
                 __syncwarp();
                 epoch = 1;
             }
@@ -673,7 +646,7 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
                     const unsigned nw0 = (unsigned)rn | ((unsigned)rfar << 21) | ((unsigned)rs << 29), nw1 = (unsigned)rna | (ep << 21);
                     if (MEMO_SH) {   // working copy in shared memory (a same-value store from every lane) + write-through to its home
                         ent->alpha = ralpha; ent->w0 = nw0; ent->w1 = nw1;
-                        if (lane == 0) *reinterpret_cast<double2*>(memo_g + (ent - memo)) = make_double2(ralpha, __hiloint2double((int)nw1, (int)nw0));
+                        if (!PERSIST && lane == 0) *reinterpret_cast<double2*>(memo_g + (ent - memo)) = make_double2(ralpha, __hiloint2double((int)nw1, (int)nw0));
                     } else {
                         if (lane == 0) { ent->alpha = ralpha; ent->w0 = nw0; ent->w1 = nw1; }
                         __syncwarp();
@@ -684,6 +657,15 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
             }
             if (a.dbg) dbg_t3 = clock64();
             if (yielded) break;
+            // The doubling's tree is complete.  Its closing work (far slot, theta' selection with one Philox block per level,
+            // the trajectory's U-turn test: four more vector loads) would make this resume the longest of its launch / CTA
+            // round; MCMCB200_NUTS_SPLIT=1 hands it to the next round (one idle product row per doubling, ~5 % more rounds).
+            // Measured on C4: 3 % slower in both the launched and the persistent variant, so it is off by default.
+            ph = PH_DBL_END;
+            if (a.split_dbl_end) { yielded = true; break; }
+        }
+        // fall through
+        case PH_DBL_END: {
             alpha = R_alpha;   // overwritten by every doubling (Q12)
             n_alpha = R_nalpha;
             const int ubase = ucount;   // the merges of this doubling drew uniforms ubase .. ubase + n_alpha - 2 (post-order)
@@ -793,6 +775,67 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
             atomicAdd(a.dbg + 17, (unsigned long long)(dbg_t3 - dbg_t2));
         }
     }
+}
+
+// One round of every chain's coroutine.
+// 128 registers, 4 CTAs per SM at n_dim <= 256 (measured: 96 registers / 5 CTAs spills and is 10 % slower, 168 / 3 is 12 % slower)
+template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bounds__(LS_WARPS * 32, EPL <= 8 ? 4 : 2) nuts_ls_step(const __grid_constant__ LsArgs a)
+{
+    __shared__ __align__(16) LsCtl ctl_sh[LS_WARPS];
+    __shared__ __align__(16) LsSummary memo_sh[MEMO_SH ? LS_WARPS * LS_TAB_SMEM : 1];
+    const int* const lvl_off = a.lvl_off;   // kernel-parameter (constant) bank, indexed dynamically
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long chain = a.chain_base + (long long)blockIdx.x * LS_WARPS + warp;
+    if (chain >= a.chain_base + a.n_group) return;
+    LsCtl* const gctl = a.ctl + chain;
+    LsCtl& c = ctl_sh[warp];
+    const int d = a.d;
+    const int m_max = a.m_max;
+    const int memo_n = a.memo_n;
+    double* const W = a.work + chain * a.work_stride;
+    double* const Wprev = W;
+    double* const Wm = W + d;
+    double* const Wxp = W + 2 * d;
+    double* const Wxn = W + 3 * d;
+    double* const Wrp = W + 4 * d;
+    double* const Wrn = W + 5 * d;
+    double* const TRh = W + 6 * d;
+    double* const G0 = W + 7 * d;
+    double* const Wst = W + 8 * d;   // state k (1-based): x at Wst + (k-1)*2d, r at + d
+    double* const Us = Wst + (size_t)2 * d * m_max;
+    double* const Ks = Us + m_max;
+    double* const TX = a.TX + chain * d;
+    const double* const TY = a.TY + chain * d;
+    // summary table: the chain's copy in global memory is its home; with max_tree_depth <= 10 the walk works on a shared-memory
+    // copy (loaded here; every update is written through), so that no look-up of the walk pays a global-memory latency
+    LsSummary* const memo_g = reinterpret_cast<LsSummary*>(Ks + m_max);
+    LsSummary* const memo = MEMO_SH ? memo_sh + warp * LS_TAB_SMEM : memo_g;
+    // everything the resume needs is requested at once — control block and summary table straight into shared memory
+    // (cp.async: no registers), the three vectors of the pending product into registers — so that one memory latency is exposed
+    {
+        const char* src = reinterpret_cast<const char*>(gctl);
+        char* dst = reinterpret_cast<char*>(&c);
+#pragma unroll
+        for (int q = 0; q < (LS_CTL_WORDS / 2 + 31) / 32; ++q)
+            if (lane + 32 * q < LS_CTL_WORDS / 2) ls_cp_async16(dst + 16 * (lane + 32 * q), src + 16 * (lane + 32 * q));
+        if (MEMO_SH) {
+            const char* ms = reinterpret_cast<const char*>(memo_g);
+            char* md = reinterpret_cast<char*>(memo);
+#pragma unroll
+            for (int q = 0; q < LS_TAB_SMEM / 32; ++q)
+                if (lane + 32 * q < memo_n) ls_cp_async16(md + 16 * (lane + 32 * q), ms + 16 * (lane + 32 * q));
+        }
+        asm volatile("cp.async.commit_group;\n" ::);
+    }
+    double xt[EPL], rt[EPL];             // pending position / half-kicked momentum on entry; then the tip of the trajectory
+    double yin[EPL];                      // the product the chain asked for
+    ldv<EPL, FT>(TX, d, lane, xt);
+    ldv<EPL, FT>(TRh, d, lane, rt);
+    ldv<EPL, FT>(TY, d, lane, yin);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncwarp();
+    if (c.ph == PH_DONE) return;
+    ls_resume<EPL, RNGM, MEMO_SH, FT, false>(a, chain, lane, c, memo, memo_g, TX, TRh, xt, rt, yin);
     __syncwarp();
     {
         double2* dst = reinterpret_cast<double2*>(gctl);
@@ -800,6 +843,149 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
 #pragma unroll
         for (int q = 0; q < (LS_CTL_WORDS / 2 + 31) / 32; ++q)
             if (lane + 32 * q < LS_CTL_WORDS / 2) dst[lane + 32 * q] = src[lane + 32 * q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// One CTA of 16 warps per SM, one chain per warp, for the whole run: the coroutine's control block, summary table and the
+// vectors of the pending leapfrog never leave shared memory, and the round's product is computed by the CTA itself for its
+// own 16 chains (mma.sync.m8n8k4.f64, the target's matrix streamed from L2 in 16-row panels by cp.async) — no launches, no
+// state reload, no trip through L2 for x / y, and chains only wait for the 15 others of their CTA.  A warp whose chain is
+// finished takes the next chain from a global counter, so the 1.73 residency waves of 4096 chains (128 registers per
+// thread: 16 chains per SM) cost no idle tail.  Same accumulation order over k as nuts_ls_gemm: identical bits.
+// Full tiles only (n_dim = 64, 128, 256), max_tree_depth <= 10.
+constexpr int PC_WARPS = 16;
+// NH sub-groups of PC_WARPS / NH warps each run their rounds independently (named barriers): while one sub-group's chains are
+// in their tree logic the other's product has the tensor pipe — a round's product and step phases overlap across sub-groups.
+template <int EPL, int NH> constexpr size_t pc_smem_bytes()
+{
+    constexpr int D = 32 * EPL, LDX = D + 4;
+    return (size_t)PC_WARPS * sizeof(LsCtl) + (size_t)PC_WARPS * LS_TAB_SMEM * sizeof(LsSummary) + (size_t)PC_WARPS * LDX * 8 + (size_t)2 * PC_WARPS * D * 8;
+}
+template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS * 32, 1) nuts_pc_kernel(const __grid_constant__ LsArgs a)
+{
+    constexpr int D = 32 * EPL, LDX = D + 4, NB = D / 8;
+    constexpr int GW = PC_WARPS / NH;                    // warps (= chains = MMA rows: 8 or 16) per sub-group
+    constexpr int MB = GW / 8;                           // 8-row MMA blocks per sub-group
+    constexpr int NBW = (NB >= GW) ? NB / GW : 1;        // 8-column output blocks per warp
+    extern __shared__ __align__(16) unsigned char pcsm[];
+    __shared__ int alive[PC_WARPS];
+    LsCtl* const ctl = reinterpret_cast<LsCtl*>(pcsm);
+    LsSummary* const memo_all = reinterpret_cast<LsSummary*>(pcsm + (size_t)PC_WARPS * sizeof(LsCtl));
+    double* const X = reinterpret_cast<double*>(memo_all + (size_t)PC_WARPS * LS_TAB_SMEM);   // [16][LDX] pending positions (the MMA's A operand)
+    double* const RH = X + PC_WARPS * LDX;                                                      // [16][D]   half-kicked momenta
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int grp = warp / GW, gw = warp % GW;
+    double* const Y = RH + PC_WARPS * D;                                                        // [16][D]   the products
+    const int g = lane >> 2, t4 = lane & 3;
+    LsCtl& c = ctl[warp];
+    LsSummary* const memo = memo_all + (size_t)warp * LS_TAB_SMEM;
+    double* const Xrow = X + warp * LDX;
+    double* const RHrow = RH + warp * D;
+    const double* const Yrow = Y + warp * D;
+    const double* const Xg = X + (size_t)grp * GW * LDX;
+    auto gbar = [&]() {
+        if (NH == 1) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + grp), "n"(GW * 32) : "memory");
+    };
+    long long chain = -1;
+    auto fetch = [&]() {
+        int cn = 0;
+        if (lane == 0) cn = atomicAdd(a.next_chain, 1);
+        cn = __shfl_sync(FULL, cn, 0);
+        if (cn < a.n_chains) {
+            chain = cn;
+            unsigned long long* w = reinterpret_cast<unsigned long long*>(&c);
+            for (int i = lane; i < LS_CTL_WORDS; i += 32) w[i] = 0ull;   // ph = PH_INIT0
+        } else {
+            chain = -1;
+        }
+        __syncwarp();
+    };
+    for (int i = lane; i < LDX; i += 32) Xrow[i] = 0.0;
+    fetch();
+    const bool pw_active = gw * NBW < NB;
+    long long pt_step = 0, pt_w1 = 0, pt_prod = 0, pt_w2 = 0, pt_n = 0;
+    for (;;) {
+        const long long pc0 = a.dbg ? clock64() : 0;
+        if (chain >= 0) {
+            double xt[EPL], rt[EPL], yin[EPL];
+#pragma unroll
+            for (int m = 0; m < EPL / 2; ++m) {
+                const double2 vx = *reinterpret_cast<const double2*>(Xrow + m * 64 + 2 * lane);
+                const double2 vr = *reinterpret_cast<const double2*>(RHrow + m * 64 + 2 * lane);
+                const double2 vy = *reinterpret_cast<const double2*>(Yrow + m * 64 + 2 * lane);
+                xt[2 * m] = vx.x; xt[2 * m + 1] = vx.y; rt[2 * m] = vr.x; rt[2 * m + 1] = vr.y; yin[2 * m] = vy.x; yin[2 * m + 1] = vy.y;
+            }
+            __syncwarp();
+            ls_resume<EPL, RNGM, true, true, true>(a, chain, lane, c, memo, nullptr, Xrow, RHrow, xt, rt, yin);
+            __syncwarp();
+            if (c.ph == PH_DONE) fetch();   // the new chain's PH_INIT0 runs in the next round (it needs no product)
+        }
+        if (lane == 0) alive[warp] = chain >= 0 ? 1 : 0;
+        const long long pc1 = a.dbg ? clock64() : 0;
+        gbar();   // every X row of the sub-group is staged, every Y row consumed
+        const long long pc2 = a.dbg ? clock64() : 0;
+        {
+            int n = 0;
+#pragma unroll
+            for (int w = 0; w < GW; ++w) n += alive[grp * GW + w];
+            if (n == 0) break;
+        }
+        // ---- Y[GW][D] = X[GW][D] * A[D][D] ----
+        // No shared-memory panels and no barriers inside the product: the B fragment of mma.m8n8k4 (lane (g, t) holds
+        // A[4 k4 + t][8 n + g]) is loaded straight from L2 — per instruction four 64-byte row segments, whole sectors — into
+        // registers, double-buffered four k4-steps ahead (the warp's registers are free during the product); every warp
+        // runs its own column slice at its own pace.  k ascends exactly as in nuts_ls_gemm: identical bits.
+        if (pw_active) {
+            constexpr int U = 4, NBATCH = D / 4 / U;   // k4-steps per register buffer (8: no faster)
+            double acc[MB][NBW][2];
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+#pragma unroll
+                for (int j = 0; j < NBW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            const double* const Bcol = a.tdata + (size_t)t4 * D + (size_t)gw * NBW * 8 + g;
+            double bA[U][NBW], bB[U][NBW];
+            auto loadb = [&](double (&b)[U][NBW], int batch) {
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+#pragma unroll
+                    for (int j = 0; j < NBW; ++j) b[u][j] = __ldg(Bcol + (size_t)(batch * U + u) * 4 * D + j * 8);
+            };
+            auto compute = [&](const double (&b)[U][NBW], int batch) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    double af[MB];
+#pragma unroll
+                    for (int i = 0; i < MB; ++i) af[i] = Xg[(i * 8 + g) * LDX + (batch * U + u) * 4 + t4];
+#pragma unroll
+                    for (int j = 0; j < NBW; ++j)
+#pragma unroll
+                        for (int i = 0; i < MB; ++i) sg_dmma(acc[i][j][0], acc[i][j][1], af[i], b[u][j]);
+                }
+            };
+            loadb(bA, 0);
+            for (int batch = 0; batch < NBATCH; batch += 2) {
+                loadb(bB, batch + 1);
+                compute(bA, batch);
+                if (batch + 2 < NBATCH) loadb(bA, batch + 2);
+                compute(bB, batch + 1);
+            }
+            double* const Yg = Y + (size_t)grp * GW * D;
+#pragma unroll
+            for (int i = 0; i < MB; ++i)
+#pragma unroll
+                for (int j = 0; j < NBW; ++j)
+                    *reinterpret_cast<double2*>(Yg + (i * 8 + g) * D + (gw * NBW + j) * 8 + 2 * t4) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+        const long long pc3 = a.dbg ? clock64() : 0;
+        gbar();
+        if (a.dbg) { pt_step += pc1 - pc0; pt_w1 += pc2 - pc1; pt_prod += pc3 - pc2; pt_w2 += clock64() - pc3; ++pt_n; }
+    }
+    if (a.dbg && lane == 0) {   // per warp: cycles in its resume, waiting for the sub-group, in its part of the product, waiting again
+        atomicAdd(a.dbg + 18, (unsigned long long)pt_step); atomicAdd(a.dbg + 19, (unsigned long long)pt_w1);
+        atomicAdd(a.dbg + 20, (unsigned long long)pt_prod); atomicAdd(a.dbg + 21, (unsigned long long)pt_w2);
+        atomicAdd(a.dbg + 22, (unsigned long long)pt_n);
     }
 }
 
@@ -837,7 +1023,7 @@ long long nuts_batched_work_doubles(long long n_chains, int d, int max_depth)
     const long long m = ls_m_max(max_depth);
     const long long jm = ((((long long)(max_depth + 1) * (m + 1) + 1) / 2 + 2) + 1) & ~1ll;        // jmask (unsigned), in doubles, even
     const long long rec = (ls_memo_entries(max_depth) > LS_TAB_SMEM) ? ((n_chains * m + 1) & ~1ll) + ((((n_chains * m + 1) / 2 + 2) + 1) & ~1ll) : 0;   // lalpha_g + ut_g
-    return 2ll * RNG_TAB_DOUBLE2 + 2 * n_chains * (long long)d + LS_MAX_GROUPS / 2 + 20 + n_chains * (long long)LS_CTL_WORDS + jm + rec + n_chains * ls_work_per_chain(d, max_depth);
+    return 2ll * RNG_TAB_DOUBLE2 + 2 * n_chains * (long long)d + LS_MAX_GROUPS / 2 + 24 + n_chains * (long long)LS_CTL_WORDS + jm + rec + n_chains * ls_work_per_chain(d, max_depth);
 }
 
 int launch_nuts_batched(const NutsLaunch& h, double* work, int* launches, long long* steps_out)
@@ -859,12 +1045,13 @@ int launch_nuts_batched(const NutsLaunch& h, double* work, int* launches, long l
     a.TX = p; p += C * d;
     a.TY = p; p += C * d;
     a.n_running = reinterpret_cast<int*>(p); p += LS_MAX_GROUPS / 2;
+    a.split_dbl_end = (std::getenv("MCMCB200_NUTS_SPLIT") && std::getenv("MCMCB200_NUTS_SPLIT")[0] == '1') ? 1 : 0;   // measured: 3 % slower
     a.dbg = nullptr;
     if (std::getenv("MCMCB200_DEBUG")) {
         a.dbg = reinterpret_cast<unsigned long long*>(p);
-        MCMCB200_CUDA_TRY(cudaMemsetAsync(p, 0, 20 * sizeof(double), h.stream));
+        MCMCB200_CUDA_TRY(cudaMemsetAsync(p, 0, 24 * sizeof(double), h.stream));
     }
-    p += 20;
+    p += 24;
     a.ctl = reinterpret_cast<LsCtl*>(p); p += C * LS_CTL_WORDS;
     const int m_max = ls_m_max(h.max_depth);
     a.m_max = m_max;
@@ -901,6 +1088,55 @@ int launch_nuts_batched(const NutsLaunch& h, double* work, int* launches, long l
         MCMCB200_CUDA_TRY(cudaStreamSynchronize(h.stream));   // jm is a local
     }
     a.work_stride = ls_work_per_chain(d, h.max_depth);
+    // Persistent variant (nuts_pc_kernel): full tiles up to n_dim = 256 with the summary table in shared memory — one launch for the
+    // whole run.  Measured on B200, C4: 2.68 s against 2.96 s for the launched rounds (512 chains: 1.45 s against 1.62 s);
+    // MCMCB200_NUTS_PERSIST=0 keeps the launched rounds (tests: the two produce identical bits).
+    const bool persist_off = std::getenv("MCMCB200_NUTS_PERSIST") && std::getenv("MCMCB200_NUTS_PERSIST")[0] == '0';
+    if (!persist_off && d == 32 * epl_for_dim(d) && epl_for_dim(d) <= 8 && a.memo_n <= LS_TAB_SMEM) {
+        cudaStream_t st = h.stream;
+        nuts_ls_tables<<<1, 256, 0, st>>>(const_cast<double2*>(a.tab));
+        a.next_chain = a.n_running + 1;
+        MCMCB200_CUDA_TRY(cudaMemsetAsync(a.n_running, 0, 2 * sizeof(int), st));
+        a.chain_base = 0; a.n_group = C;
+        int dev = 0, n_sm = 0;
+        MCMCB200_CUDA_TRY(cudaGetDevice(&dev));
+        MCMCB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        const long long want = (C + PC_WARPS - 1) / PC_WARPS;
+        const unsigned grid = (unsigned)(want < n_sm ? want : n_sm);
+        const bool philox = a.rng.mode == RNG_PHILOX;
+        auto go = [&](auto kern, size_t smem) -> int {
+            MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, PC_WARPS * 32, smem, st>>>(a);
+            MCMCB200_CUDA_TRY(cudaGetLastError());
+            return MCMCB200_OK;
+        };
+        int rc = MCMCB200_OK;
+        // one group of 16 chains per CTA: every B fragment loaded from L2 feeds two MMAs (two 8-row blocks).  Two independently
+        // running groups of 8 (MCMCB200_NUTS_PERSIST_NH=2) overlap product and tree logic but stream the matrix twice: 3.3 s
+        const bool halves = std::getenv("MCMCB200_NUTS_PERSIST_NH") && std::getenv("MCMCB200_NUTS_PERSIST_NH")[0] == '2';
+#define PC_GO(E) (halves ? (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 2>, pc_smem_bytes<E, 2>()) : go(nuts_pc_kernel<E, RNG_TAPE, 2>, pc_smem_bytes<E, 2>())) \
+                         : (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 1>, pc_smem_bytes<E, 1>()) : go(nuts_pc_kernel<E, RNG_TAPE, 1>, pc_smem_bytes<E, 1>())))
+        switch (epl_for_dim(d)) {
+        case 2: rc = PC_GO(2); break;
+        case 4: rc = PC_GO(4); break;
+        default: rc = PC_GO(8); break;
+        }
+#undef PC_GO
+        if (rc) return rc;
+        if (a.dbg) {
+            unsigned long long hd[24];
+            MCMCB200_CUDA_TRY(cudaMemcpy(hd, a.dbg, sizeof(hd), cudaMemcpyDeviceToHost));
+            if (hd[22]) fprintf(stderr, "nuts (persistent): per warp-round mean cycles: resume %.0f | wait for the group %.0f | product %.0f | wait %.0f  (%llu warp-rounds)\n",
+                                (double)hd[18] / hd[22], (double)hd[19] / hd[22], (double)hd[20] / hd[22], (double)hd[21] / hd[22], hd[22]);
+            for (int k = 0; k < 5; ++k)
+                if (hd[3 * k + 1]) fprintf(stderr, "  resume path %d: count %llu mean %.0f cycles\n", k, hd[3 * k + 1], (double)hd[3 * k] / (double)hd[3 * k + 1]);
+            if (hd[1]) fprintf(stderr, "  leaf->leaf segments: finish %.0f | U-turn %.0f | walk %.0f | rest %.0f\n", (double)hd[15] / hd[1], (double)hd[16] / hd[1], (double)hd[17] / hd[1],
+                               ((double)hd[0] - hd[15] - hd[16] - hd[17]) / hd[1]);
+        }
+        *launches = 2;
+        if (steps_out) *steps_out = 0;
+        return MCMCB200_OK;
+    }
     // Chain groups.  A group's rounds (GEMM, step, GEMM, step, ...) are a dependent sequence of short, latency-bound kernels;
     // different groups are independent, so each group runs on its own stream and the GPU overlaps one group's GEMM (fp64
     // tensor pipe) with other groups' step kernels (integer / memory pipes) and fills the SMs a 1024-chain kernel leaves idle.

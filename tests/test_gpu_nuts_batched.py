@@ -92,7 +92,7 @@ def test_batched_is_the_default_for_many_chains_and_shards_consistently(engine):
     x0 = rng.normal(size=(C, d))
     kw = dict(target_data=P.ravel(), n_burnin=10, n_keep=10, n_adapt_draws=10, rng_mode=engine.api.RNG_PHILOX, seed=8)
     r = engine.nuts(x0, "dense_gauss", **kw)
-    assert r["kernel_launches"] > 100
+    assert r["kernel_launches"] == 2   # n_dim = 64 is a full tile: the persistent kernel (tables + one launch)
     assert np.isfinite(r["draws"]).all() and (r["n_leapfrog"] > 0).all()
     import os
     os.environ["MCMCB200_NUTS_BATCHED"] = "1"
@@ -121,8 +121,55 @@ def test_deep_trees_use_the_global_tables_and_full_tiles(engine, monkeypatch):
         w = engine.nuts(x0, "dense_gauss", **kw)
         monkeypatch.delenv("MCMCB200_NUTS_BATCHED")
         monkeypatch.delenv("MCMCB200_NUTS_COOP")
-        assert r["kernel_launches"] > 50 and w["kernel_launches"] == 1
+        assert (r["kernel_launches"] > 50 or (depth <= 10 and r["kernel_launches"] == 2)) and w["kernel_launches"] == 1
         assert np.array_equal(r["n_leapfrog"], w["n_leapfrog"]) and np.array_equal(r["n_accept"], w["n_accept"]), (d, depth)
         assert np.abs(r["draws"] - w["draws"]).max() <= TOL, (d, depth, np.abs(r["draws"] - w["draws"]).max())
         if depth == 12 and d == 128:
             assert r["n_leapfrog"].max() > 5 * 100   # deep trees did occur (a depth-9 doubling alone has 46 distinct states)
+
+
+def test_persistent_variant_reproduces_the_rounds_bit_for_bit(engine, oracle, monkeypatch):
+    """Full tiles (n_dim = 64, 128, 256) with max_tree_depth <= 10 run as ONE persistent kernel — 16 chains per CTA, the coroutine
+    state and the pending vectors stay in shared memory, the CTA computes its own chains' products with the same DMMA
+    accumulation order, free warps take the next chain from a global counter.  MCMCB200_NUTS_PERSIST=0 keeps the launched
+    rounds.  Same operations in the same order: identical bits, whatever the chain-to-CTA assignment turns out to be; also
+    with two independently running groups of 8 chains per CTA (MCMCB200_NUTS_PERSIST_NH=2), and on the reference's stream."""
+    rng = np.random.default_rng(29)
+    for d, C, n_adapt, eps0 in ((64, 700, 20, 1.0), (256, 90, 0, 0.08), (128, 33, 10, 1.0)):
+        q, _ = np.linalg.qr(rng.normal(size=(d, d)))
+        P = (q / np.logspace(0, 2, d)) @ q.T
+        P = (P + P.T) / 2
+        x0 = rng.normal(size=(C, d))
+        kw = dict(target_data=P.ravel(), n_burnin=20, n_keep=20, n_adapt_draws=n_adapt, step_size=eps0, rng_mode=engine.api.RNG_PHILOX, seed=4,
+                  want_logp=True)
+        monkeypatch.setenv("MCMCB200_NUTS_BATCHED", "1")
+        monkeypatch.setenv("MCMCB200_NUTS_PERSIST", "0")
+        r = engine.nuts(x0, "dense_gauss", **kw)
+        monkeypatch.delenv("MCMCB200_NUTS_PERSIST")
+        for nh in ("1", "2"):
+            monkeypatch.setenv("MCMCB200_NUTS_PERSIST_NH", nh)
+            p = engine.nuts(x0, "dense_gauss", **kw)
+            assert r["kernel_launches"] > 100 and p["kernel_launches"] == 2
+            assert np.array_equal(r["draws"], p["draws"]), (d, nh, np.abs(r["draws"] - p["draws"]).max())
+            assert np.array_equal(r["n_accept"], p["n_accept"]) and np.array_equal(r["n_leapfrog"], p["n_leapfrog"])
+            assert np.array_equal(r["step_size"], p["step_size"]) and np.array_equal(r["logp"], p["logp"])
+        monkeypatch.delenv("MCMCB200_NUTS_PERSIST_NH")
+        monkeypatch.delenv("MCMCB200_NUTS_BATCHED")
+    # the reference's own stream (oracle-recorded tape) through the persistent kernel, linreg target
+    d, C = 64, 3
+    tid, tname, td = _dense(rng, d, True)
+    x0 = rng.normal(size=(C, d))
+    st = ol.Settings(n_burnin=3, n_keep=12, n_adapt_draws=0, step_size=0.08, max_tree_depth=8)
+    tapes, od, oa = [], [], []
+    for c in range(C):
+        o = oracle.run_chain(ol.NUTS, tid, td, x0[c], st, seed=60 + c, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_WARP, record_tape=2_000_000)
+        tapes.append(o["tape"]); od.append(o["draws"]); oa.append(o["n_accept"])
+    tape = np.zeros((C, max(len(t) for t in tapes) + 8))
+    for c in range(C):
+        tape[c, :len(tapes[c])] = tapes[c]
+    monkeypatch.setenv("MCMCB200_NUTS_BATCHED", "1")
+    r = engine.nuts(x0, tname, target_data=td, n_burnin=3, n_keep=12, n_adapt_draws=0, step_size=0.08, max_tree_depth=8,
+                    rng_mode=engine.api.RNG_USER_TAPE, tape=tape)
+    monkeypatch.delenv("MCMCB200_NUTS_BATCHED")
+    assert r["kernel_launches"] == 2
+    assert np.abs(r["draws"] - np.stack(od)).max() <= TOL and np.array_equal(r["n_accept"], np.array(oa))
