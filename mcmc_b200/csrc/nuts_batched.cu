@@ -944,13 +944,28 @@ template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS 
             for (int i = 0; i < MB; ++i)
 #pragma unroll
                 for (int j = 0; j < NBW; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-            const double* const Bcol = a.tdata + (size_t)t4 * D + (size_t)gw * NBW * 8 + g;
+            // With an even number of column blocks per warp, blocks are PAIRED on interleaved columns: block 2p holds the even,
+            // block 2p + 1 the odd columns of a 16-column group, so a lane's two B values are adjacent in memory — one 128-bit
+            // load per k4-step and pair instead of two 64-bit ones (the LSU pipe was 65 % busy), whole 128-byte lines per
+            // warp.  Which column an accumulator belongs to changes, not its arithmetic: the results are the same bits.
+            constexpr bool PAIRED = (NBW % 2 == 0);
+            const double* const Bcol = a.tdata + (size_t)t4 * D + (size_t)gw * NBW * 8 + (PAIRED ? 2 * g : g);
             double bA[U][NBW], bB[U][NBW];
             auto loadb = [&](double (&b)[U][NBW], int batch) {
 #pragma unroll
-                for (int u = 0; u < U; ++u)
+                for (int u = 0; u < U; ++u) {
+                    if constexpr (PAIRED) {
 #pragma unroll
-                    for (int j = 0; j < NBW; ++j) b[u][j] = __ldg(Bcol + (size_t)(batch * U + u) * 4 * D + j * 8);
+                        for (int pr = 0; pr < NBW / 2; ++pr) {
+                            const double2 v = __ldg(reinterpret_cast<const double2*>(Bcol + (size_t)(batch * U + u) * 4 * D + pr * 16));
+                            b[u][2 * pr] = v.x;
+                            b[u][2 * pr + 1] = v.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < NBW; ++j) b[u][j] = __ldg(Bcol + (size_t)(batch * U + u) * 4 * D + j * 8);
+                    }
+                }
             };
             auto compute = [&](const double (&b)[U][NBW], int batch) {
 #pragma unroll
@@ -973,10 +988,20 @@ template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS 
             }
             double* const Yg = Y + (size_t)grp * GW * D;
 #pragma unroll
-            for (int i = 0; i < MB; ++i)
+            for (int i = 0; i < MB; ++i) {
+                if constexpr (PAIRED) {
 #pragma unroll
-                for (int j = 0; j < NBW; ++j)
-                    *reinterpret_cast<double2*>(Yg + (i * 8 + g) * D + (gw * NBW + j) * 8 + 2 * t4) = make_double2(acc[i][j][0], acc[i][j][1]);
+                    for (int pr = 0; pr < NBW / 2; ++pr)
+#pragma unroll
+                        for (int cc = 0; cc < 2; ++cc)   // accumulator element cc of blocks 2 pr / 2 pr + 1 = columns 2 (2 t + cc), + 1 of the group
+                            *reinterpret_cast<double2*>(Yg + (i * 8 + g) * D + gw * NBW * 8 + pr * 16 + 2 * (2 * t4 + cc)) =
+                                make_double2(acc[i][2 * pr][cc], acc[i][2 * pr + 1][cc]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < NBW; ++j)
+                        *reinterpret_cast<double2*>(Yg + (i * 8 + g) * D + (gw * NBW + j) * 8 + 2 * t4) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            }
         }
         const long long pc3 = a.dbg ? clock64() : 0;
         gbar();
