@@ -158,6 +158,12 @@ template <int EPL, bool FT = false> __device__ __forceinline__ void ldv(const do
         }
     }
 }
+__device__ __forceinline__ long long ls_clock()   // ordered against barriers and memory operations (the intrinsic is not)
+{
+    long long v;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(v)::"memory");
+    return v;
+}
 __device__ __forceinline__ void ls_cp_async16(void* smem_dst, const void* gsrc)
 {
     const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
@@ -907,7 +913,7 @@ template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS 
     const bool pw_active = gw * NBW < NB;
     long long pt_step = 0, pt_w1 = 0, pt_prod = 0, pt_w2 = 0, pt_n = 0;
     for (;;) {
-        const long long pc0 = a.dbg ? clock64() : 0;
+        const long long pc0 = a.dbg ? ls_clock() : 0;
         if (chain >= 0) {
             double xt[EPL], rt[EPL], yin[EPL];
 #pragma unroll
@@ -923,9 +929,9 @@ template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS 
             if (c.ph == PH_DONE) fetch();   // the new chain's PH_INIT0 runs in the next round (it needs no product)
         }
         if (lane == 0) alive[warp] = chain >= 0 ? 1 : 0;
-        const long long pc1 = a.dbg ? clock64() : 0;
+        const long long pc1 = a.dbg ? ls_clock() : 0;
         gbar();   // every X row of the sub-group is staged, every Y row consumed
-        const long long pc2 = a.dbg ? clock64() : 0;
+        const long long pc2 = a.dbg ? ls_clock() : 0;
         {
             int n = 0;
 #pragma unroll
@@ -1003,9 +1009,9 @@ template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS 
                 }
             }
         }
-        const long long pc3 = a.dbg ? clock64() : 0;
+        const long long pc3 = a.dbg ? ls_clock() : 0;
         gbar();
-        if (a.dbg) { pt_step += pc1 - pc0; pt_w1 += pc2 - pc1; pt_prod += pc3 - pc2; pt_w2 += clock64() - pc3; ++pt_n; }
+        if (a.dbg) { pt_step += pc1 - pc0; pt_w1 += pc2 - pc1; pt_prod += pc3 - pc2; pt_w2 += ls_clock() - pc3; ++pt_n; }
     }
     if (a.dbg && lane == 0) {   // per warp: cycles in its resume, waiting for the sub-group, in its part of the product, waiting again
         atomicAdd(a.dbg + 18, (unsigned long long)pt_step); atomicAdd(a.dbg + 19, (unsigned long long)pt_w1);
