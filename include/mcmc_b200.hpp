@@ -56,7 +56,16 @@ namespace mcmc
 {
 
 using uint_t = unsigned int;
-using fp_t = double;  // MCMC_FPN_TYPE (include/misc/mcmc_options.hpp:80-99); the device path is fp64
+// MCMC_FPN_TYPE (include/misc/mcmc_options.hpp:80-99).  double (default): every buffer goes to the device as it is.
+// float: the reference's fp32 build — ColVec_t / Mat_t / Cube_t, the settings and target_data are fp32 at this boundary; they
+// are widened on the way in, the device computes in fp64 (at least the reference's precision: against a float build of the
+// reference the draws agree to fp32 rounding until the reference's own rounding decorrelates the chains) and draws_out is
+// narrowed on the way out.  Stated tolerance of the fp32 boundary: per-draw L-inf <= 2^-23 |x| against the fp64 build.
+#ifndef MCMC_FPN_TYPE
+#define MCMC_FPN_TYPE double
+#endif
+using fp_t = MCMC_FPN_TYPE;
+static_assert(sizeof(fp_t) == sizeof(double) || sizeof(fp_t) == sizeof(float), "MCMC_FPN_TYPE must be double or float");
 
 #if defined(MCMC_ENABLE_EIGEN_WRAPPERS)
 using ColVec_t = Eigen::Matrix<fp_t, Eigen::Dynamic, 1>;
@@ -280,17 +289,29 @@ inline const char* last_error()
 namespace b200_detail
 {
 
-inline void fill_problem(mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, const fp_t* x0, size_t d, size_t n_chains, registered_kernel k,
-                         void* target_data, const algo_settings_t& s, int rng_mode)
+// fp_t <-> device (double) conversions: overloads, so that the double build passes pointers through untouched
+inline const double* widen(const double* src, size_t, std::vector<double>&) { return src; }
+inline const double* widen(const float* src, size_t n, std::vector<double>& tmp)
+{
+    if (!src) return nullptr;
+    tmp.assign(src, src + n);
+    return tmp.data();
+}
+inline double* device_side(double* direct, size_t, std::vector<double>&) { return direct; }            // results land where they belong
+inline double* device_side(float*, size_t n, std::vector<double>& tmp) { tmp.resize(n); return tmp.data(); }   // ... or in a double scratch
+inline void narrow(double* dst, const double* src, size_t n) { if (dst != src && n) std::memcpy(dst, src, n * sizeof(double)); }
+inline void narrow(float* dst, const double* src, size_t n) { for (size_t i = 0; i < n; ++i) dst[i] = static_cast<float>(src[i]); }
+
+inline void fill_problem(mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, const double* x0, size_t d, size_t n_chains, registered_kernel k,
+                         const double* target_values, size_t target_n, const algo_settings_t& s, int rng_mode)
 {
     std::memset(&pr, 0, sizeof(pr));
     std::memset(&rng, 0, sizeof(rng));
-    const kernel_data* kd = static_cast<const kernel_data*>(target_data);
     pr.n_chains = static_cast<int64_t>(n_chains);
     pr.n_dim = static_cast<int32_t>(d);
     pr.target_id = k.target_id;
-    pr.target_data = kd ? kd->values : nullptr;
-    pr.target_data_len = kd ? static_cast<int64_t>(kd->n) : 0;
+    pr.target_data = target_values;
+    pr.target_data_len = static_cast<int64_t>(target_n);
     pr.initial_vals = x0;  // d x C column-major == [C][d] chain-major
     pr.initial_mem = MCMCB200_MEM_HOST;
     pr.device = s.b200.device;
@@ -303,13 +324,13 @@ inline void fill_problem(mcmcb200_problem_t& pr, mcmcb200_rng_t& rng, const fp_t
 // draws_out; many chains arrive in one page-locked staging buffer (the D2H then runs at the PCIe rate) and are copied —
 // plain memcpy, chains spread over host threads — into the Cube_t's matrices.
 struct pinned_buffer {
-    fp_t* p = nullptr;
+    double* p = nullptr;
     size_t n = 0;
     bool pinned = false;
-    std::vector<fp_t> fallback;
+    std::vector<double> fallback;
     explicit pinned_buffer(size_t count) : n(count)
     {
-        if (count * sizeof(fp_t) >= (size_t(1) << 24)) p = static_cast<fp_t*>(mcmcb200_host_alloc(count * sizeof(fp_t)));
+        if (count * sizeof(double) >= (size_t(1) << 24)) p = static_cast<double*>(mcmcb200_host_alloc(count * sizeof(double)));
         pinned = p != nullptr;
         if (!p) { fallback.resize(count); p = fallback.data(); }
     }
@@ -317,13 +338,13 @@ struct pinned_buffer {
     pinned_buffer(const pinned_buffer&) = delete;
     pinned_buffer& operator=(const pinned_buffer&) = delete;
 };
-inline void unpack(const fp_t* buf, size_t n_chains, size_t n_keep, size_t d, Cube_t& cube)
+inline void unpack(const double* buf, size_t n_chains, size_t n_keep, size_t d, Cube_t& cube)
 {
     cube.set_n_mat(n_chains);
     auto work = [&](size_t c_begin, size_t c_end) {
         for (size_t c = c_begin; c < c_end; ++c) {
             mresize(cube.mat(c), n_keep, d);   // allocation and first touch happen on the copying thread
-            if (n_keep > 0 && d > 0) std::memcpy(mdata(cube.mat(c)), buf + c * n_keep * d, n_keep * d * sizeof(fp_t));
+            if (n_keep > 0 && d > 0) narrow(mdata(cube.mat(c)), buf + c * n_keep * d, n_keep * d);
         }
     };
     size_t n_thr = 1;
@@ -339,7 +360,10 @@ inline void unpack(const fp_t* buf, size_t n_chains, size_t n_keep, size_t d, Cu
     for (auto& t : th) t.join();
 }
 
-inline const fp_t* precond_or_null(const Mat_t& m, size_t d) { return (msize(m) == d * d) ? cdata(m) : nullptr; }  // src/hmc.cpp:57
+inline const double* precond_or_null(const Mat_t& m, size_t d, std::vector<double>& tmp)   // src/hmc.cpp:57
+{
+    return (msize(m) == d * d) ? widen(cdata(m), d * d, tmp) : nullptr;
+}
 
 template <class RunFn>
 inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, void* target_data, algo_settings_t* sp, size_t n_keep,
@@ -355,16 +379,18 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
     }
     mcmcb200_problem_t pr;
     mcmcb200_rng_t rng;
-    fill_problem(pr, rng, x0, d, n_chains, k, target_data, s, rng_mode);
+    const kernel_data* kd = static_cast<const kernel_data*>(target_data);
+    std::vector<double> w_x0, w_td, w_lb, w_ub, w_single;   // used by the fp32 build only
+    fill_problem(pr, rng, widen(x0, d * n_chains, w_x0), d, n_chains, k, kd ? widen(kd->values, kd->n, w_td) : nullptr, kd ? kd->n : 0, s, rng_mode);
     if (s.vals_bound) {
         pr.vals_bound = 1;
-        pr.lower_bounds = cdata(s.lower_bounds);
-        pr.upper_bounds = cdata(s.upper_bounds);
+        pr.lower_bounds = widen(cdata(s.lower_bounds), d, w_lb);
+        pr.upper_bounds = widen(cdata(s.upper_bounds), d, w_ub);
     }
     // one chain: the result lands directly in draws_out; many chains: in a page-locked staging buffer
     if (single) mresize(*single, n_keep, d);
     pinned_buffer stage(cube ? n_chains * n_keep * d : 0);
-    fp_t* const buf = cube ? stage.p : mdata(*single);
+    double* const buf = cube ? stage.p : device_side(mdata(*single), n_keep * d, w_single);
     std::vector<int64_t> acc(n_chains, 0);
     mcmcb200_output_t out;
     std::memset(&out, 0, sizeof(out));
@@ -405,6 +431,7 @@ inline bool run(const fp_t* x0, size_t d, size_t n_chains, registered_kernel k, 
             }
     }
     if (cube) unpack(buf, n_chains, n_keep, d, *cube);
+    else narrow(mdata(*single), buf, n_keep * d);   // (fp64 build: buf IS draws_out)
     if (sp) {  // written back only if a settings object was passed (src/hmc.cpp:220-222)
         long double tot = 0;
         for (size_t c = 0; c < n_chains; ++c) tot += static_cast<long double>(acc[c]);
@@ -433,7 +460,8 @@ inline bool hmc_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kerne
                                 h.n_keep_draws = static_cast<int64_t>(st.hmc_settings.n_keep_draws);
                                 h.n_leap_steps = static_cast<int64_t>(static_cast<uint_t>(st.hmc_settings.n_leap_steps));  // Q22
                                 h.step_size = st.hmc_settings.step_size;
-                                h.precond_mat = b200_detail::precond_or_null(st.hmc_settings.precond_mat, d);
+                                std::vector<double> w_pm;
+                                h.precond_mat = b200_detail::precond_or_null(st.hmc_settings.precond_mat, d, w_pm);
                                 h.chol_mode = st.b200.chol_mode;
                                 h.arith = st.b200.arith;
                                 return mcmcb200_hmc_run(&pr, &rng, &h, &out);
@@ -476,7 +504,8 @@ inline bool mala_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kern
                                 m.n_burnin_draws = static_cast<int64_t>(st.mala_settings.n_burnin_draws);
                                 m.n_keep_draws = static_cast<int64_t>(st.mala_settings.n_keep_draws);
                                 m.step_size = st.mala_settings.step_size;
-                                m.precond_mat = b200_detail::precond_or_null(st.mala_settings.precond_mat, d);
+                                std::vector<double> w_pm;
+                                m.precond_mat = b200_detail::precond_or_null(st.mala_settings.precond_mat, d, w_pm);
                                 m.chol_mode = st.b200.chol_mode;
                                 m.arith = st.b200.arith;
                                 return mcmcb200_mala_run(&pr, &rng, &m, &out);
@@ -520,7 +549,8 @@ inline bool rwmh_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kern
                                 m.n_burnin_draws = static_cast<int64_t>(st.rwmh_settings.n_burnin_draws);
                                 m.n_keep_draws = static_cast<int64_t>(st.rwmh_settings.n_keep_draws);
                                 m.par_scale = st.rwmh_settings.par_scale;
-                                m.cov_mat = b200_detail::precond_or_null(st.rwmh_settings.cov_mat, d);
+                                std::vector<double> w_pm;
+                                m.cov_mat = b200_detail::precond_or_null(st.rwmh_settings.cov_mat, d, w_pm);
                                 m.chol_mode = st.b200.chol_mode;
                                 m.arith = st.b200.arith;
                                 return mcmcb200_rwmh_run(&pr, &rng, &m, &out);
@@ -564,11 +594,14 @@ inline bool de_impl(const fp_t* x0, size_t d, size_t n_pops, registered_kernel k
     }
     mcmcb200_problem_t pr;
     mcmcb200_rng_t rng;
-    b200_detail::fill_problem(pr, rng, x0, d, n_pops, k, target_data, s, s.b200.rng_mode);
+    const kernel_data* kd = static_cast<const kernel_data*>(target_data);
+    std::vector<double> w_x0, w_td, w_lb, w_ub, w_ilb, w_iub;   // used by the fp32 build only
+    b200_detail::fill_problem(pr, rng, b200_detail::widen(x0, d * n_pops, w_x0), d, n_pops, k, kd ? b200_detail::widen(kd->values, kd->n, w_td) : nullptr,
+                              kd ? kd->n : 0, s, s.b200.rng_mode);
     if (s.vals_bound) {
         pr.vals_bound = 1;
-        pr.lower_bounds = b200_detail::cdata(s.lower_bounds);
-        pr.upper_bounds = b200_detail::cdata(s.upper_bounds);
+        pr.lower_bounds = b200_detail::widen(b200_detail::cdata(s.lower_bounds), d, w_lb);
+        pr.upper_bounds = b200_detail::widen(b200_detail::cdata(s.upper_bounds), d, w_ub);
     }
     mcmcb200_de_settings_t st;
     mcmcb200_de_settings_default(&st);
@@ -579,10 +612,10 @@ inline bool de_impl(const fp_t* x0, size_t d, size_t n_pops, registered_kernel k
     st.arith = s.b200.arith;
     st.par_b = ds.par_b;
     st.par_gamma_jump = ds.par_gamma_jump;
-    st.initial_lb = (b200_detail::vsize(ds.initial_lb) == d) ? b200_detail::cdata(ds.initial_lb) : nullptr;   // src/de.cpp:70-71
-    st.initial_ub = (b200_detail::vsize(ds.initial_ub) == d) ? b200_detail::cdata(ds.initial_ub) : nullptr;
+    st.initial_lb = (b200_detail::vsize(ds.initial_lb) == d) ? b200_detail::widen(b200_detail::cdata(ds.initial_lb), d, w_ilb) : nullptr;   // src/de.cpp:70-71
+    st.initial_ub = (b200_detail::vsize(ds.initial_ub) == d) ? b200_detail::widen(b200_detail::cdata(ds.initial_ub), d, w_iub) : nullptr;
     const size_t n_keep = ds.n_keep_draws, n_pop = ds.n_pop;
-    std::vector<fp_t> buf(n_pops * n_keep * n_pop * d);
+    std::vector<double> buf(n_pops * n_keep * n_pop * d);
     std::vector<int64_t> acc(n_pops, 0);
     mcmcb200_output_t out;
     std::memset(&out, 0, sizeof(out));
@@ -595,10 +628,10 @@ inline bool de_impl(const fp_t* x0, size_t d, size_t n_pops, registered_kernel k
         for (size_t g = 0; g < n_keep; ++g) {
             Mat_t& m = cubes[p].mat(g);
             b200_detail::mresize(m, n_pop, d);
-            const fp_t* src = buf.data() + ((p * n_keep + g) * n_pop) * d;
+            const double* src = buf.data() + ((p * n_keep + g) * n_pop) * d;
             fp_t* dst = b200_detail::mdata(m);
             for (size_t j = 0; j < d; ++j)
-                for (size_t i = 0; i < n_pop; ++i) dst[j * n_pop + i] = src[i * d + j];
+                for (size_t i = 0; i < n_pop; ++i) dst[j * n_pop + i] = static_cast<fp_t>(src[i * d + j]);
         }
     }
     if (sp) s.de_settings.n_accept_draws = static_cast<size_t>(acc[0]);   // src/de.cpp:237-239 (population 0 in many-population calls)
@@ -649,7 +682,8 @@ inline bool nuts_impl(const fp_t* x0, size_t d, size_t n_chains, registered_kern
                                 n.gamma_val = st.nuts_settings.gamma_val;
                                 n.t0_val = st.nuts_settings.t0_val;
                                 n.kappa_val = st.nuts_settings.kappa_val;
-                                n.precond_mat = b200_detail::precond_or_null(st.nuts_settings.precond_mat, d);
+                                std::vector<double> w_pm;
+                                n.precond_mat = b200_detail::precond_or_null(st.nuts_settings.precond_mat, d, w_pm);
                                 n.chol_mode = st.b200.chol_mode;
                                 n.arith = st.b200.arith;
                                 return mcmcb200_nuts_run(&pr, &rng, &n, &out);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "cpp", "bin")
 
 
-def _build(src, out, std="c++14"):
+def _build(src, out, std="c++14", defines=()):
     from mcmc_b200 import api
 
     assert os.path.exists(api.LIB_PATH), "build the library first (python -c 'import __graft_entry__ as g; g.build()')"
@@ -20,7 +20,7 @@ def _build(src, out, std="c++14"):
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     libdir = os.path.dirname(api.LIB_PATH)
     cmd = [cxx, "-std=" + std, "-O2", "-Wall", "-I", os.path.join(ROOT, "include"), src, "-o", out, "-L", libdir, "-lmcmc_b200",
-           "-Wl,-rpath," + libdir]
+           "-Wl,-rpath," + libdir] + ["-D" + x for x in defines]
     r = subprocess.run(cmd, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
     return out
@@ -56,6 +56,9 @@ def test_header_and_examples_compile_and_link():
     _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
     _build(os.path.join(ROOT, "examples", "hmc_normal.cpp"), os.path.join(BIN, "hmc_normal"))
     _build(os.path.join(ROOT, "examples", "rmhmc_funnel.cpp"), os.path.join(BIN, "rmhmc_funnel"))
+    # the reference's fp32 build (MCMC_FPN_TYPE float): the same user source against fp_t compiles both ways, C++11 included
+    _build(os.path.join(ROOT, "tests", "cpp", "fp32_check.cpp"), os.path.join(BIN, "fp32_check_f32"), std="c++11", defines=("MCMC_FPN_TYPE=float",))
+    _build(os.path.join(ROOT, "tests", "cpp", "fp32_check.cpp"), os.path.join(BIN, "fp32_check_f64"), std="c++11")
 
 
 @pytest.mark.gpu
@@ -108,3 +111,32 @@ def test_funnel_example_runs(engine):
     assert r.returncode == 0, r.stderr
     acc = float(r.stdout.strip().split("acceptance rate")[1])
     assert 0.2 < acc < 0.9, r.stdout
+
+
+@pytest.mark.gpu
+def test_fp32_build_of_the_header_returns_the_fp64_draws_narrowed(engine):
+    """MCMC_FPN_TYPE float (include/misc/mcmc_options.hpp:80-99): ColVec_t / Mat_t / Cube_t, settings and target_data are fp32 at
+    the boundary, the device computes in fp64.  One user source, built with and without -DMCMC_FPN_TYPE=float: every fp32
+    draw is the fp64 draw rounded to float (the inputs are exactly representable), accept counts are identical."""
+    src = os.path.join(ROOT, "tests", "cpp", "fp32_check.cpp")
+    outs = {}
+    for tag, defs in (("f32", ("MCMC_FPN_TYPE=float",)), ("f64", ())):
+        exe = _build(src, os.path.join(BIN, "fp32_check_" + tag), std="c++11", defines=defs)
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        d = {}
+        for line in r.stdout.splitlines():
+            tok = line.split()
+            if tok[0] == "sizeof_fp_t":
+                d["sizeof"] = int(tok[1])
+            else:
+                d[tok[0]] = (int(tok[3]), np.array([float.fromhex(h) for h in tok[4:]]).reshape(int(tok[1]), int(tok[2])))
+        outs[tag] = d
+    assert outs["f32"]["sizeof"] == 4 and outs["f64"]["sizeof"] == 8
+    names = [k for k in outs["f64"] if k != "sizeof"]
+    assert len(names) == 6
+    for k in names:
+        a32, d32 = outs["f32"][k]
+        a64, d64 = outs["f64"][k]
+        assert a32 == a64, k
+        assert np.array_equal(d32, d64.astype(np.float32).astype(np.float64)), (k, np.abs(d32 - d64).max())
