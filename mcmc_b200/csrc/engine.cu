@@ -21,6 +21,7 @@
 #include "rmhmc_cta.h"
 #include "hmc_batched.h"
 #include "nuts_batched.h"
+#include "hmc_duo.h"
 
 namespace mcmcb200
 {
@@ -579,7 +580,9 @@ static int hmc_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng,
         if ((rc = launch_hmc_batched(a, static_cast<double*>(wp), &launches))) return rc;
     } else {
         MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
-        if ((rc = wide ? launch_hmc_wide(a) : launch_hmc(a))) return rc;
+        // few chains (strong-scaling shards): two warps per chain, variates of draw t + 1 generated under the trajectory of draw t
+        if (!wide && hmc_duo_supported(a)) { if ((rc = launch_hmc_duo(a))) return rc; }
+        else if ((rc = wide ? launch_hmc_wide(a) : launch_hmc(a))) return rc;
     }
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));
     if (out->n_leapfrog_out)

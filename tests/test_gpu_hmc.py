@@ -247,3 +247,30 @@ def test_wide_hmc_four_warps_per_chain(engine, oracle, d):
                    seed=56, chain_offset=9)
     od, oa, _ = _oracle_chains(oracle, ol.HMC, ol.TGT_ISO_GAUSS, None, x0, st, 56, ol.RNG_PHILOX, ol.SUM_WARP, chain_offset=9)
     assert np.abs(r["draws"] - od).max() <= TOL and np.array_equal(r["n_accept"], oa)   # precision matrix I == the iso-Gaussian
+
+
+@pytest.mark.parametrize("tname", ["iso_gauss", "diag_gauss"])
+def test_two_warps_per_chain_kernel_reproduces_the_production_kernel(engine, oracle, monkeypatch, tname):
+    """Few chains (strong-scaling shards): hmc_duo.cu runs a chain on TWO warps — one generates draw t + 1's Philox / Box-Muller
+    variates while the other runs draw t's trajectory (src/hmc.cpp:155-205) — coupled through shared memory and one named
+    barrier per draw.  Same variates, same arithmetic: bit-identical to the one-warp-per-chain production kernel, and within
+    1e-10 of the oracle; MCMCB200_HMC_DUO=0/1 forces the choice (default: n_leap != 10 and <= 2048 chains, where it is faster)."""
+    rng = np.random.default_rng(8)
+    for d, L, C in ((128, 10, 300), (64, 7, 37), (256, 3, 50), (128, 0, 9)):
+        w = np.exp(rng.uniform(-0.5, 0.5, size=d)) if tname == "diag_gauss" else None
+        x0 = rng.normal(size=(C, d))
+        kw = dict(target_data=w, n_leap_steps=L, step_size=0.11, n_burnin=7, n_keep=25, rng_mode=engine.api.RNG_PHILOX, seed=31, chain_offset=3,
+                  want_logp=True)
+        monkeypatch.setenv("MCMCB200_HMC_DUO", "0")
+        a = engine.hmc(x0, tname, **kw)
+        monkeypatch.setenv("MCMCB200_HMC_DUO", "1")
+        b = engine.hmc(x0, tname, **kw)
+        monkeypatch.delenv("MCMCB200_HMC_DUO")
+        c = engine.hmc(x0, tname, **kw)   # default choice
+        assert np.array_equal(a["draws"], b["draws"]) and np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["logp"], b["logp"]), (d, L)
+        assert np.array_equal(b["draws"], c["draws"])
+        st = ol.Settings(n_burnin=7, n_keep=25, n_leap_steps=L, step_size=0.11)
+        tid = ol.TGT_DIAG_GAUSS if tname == "diag_gauss" else ol.TGT_ISO_GAUSS
+        for ch in (0, C - 1):
+            o = oracle.run_chain(ol.HMC, tid, w, x0[ch], st, seed=31, rng_mode=ol.RNG_PHILOX, chain_id=3 + ch, sum_mode=ol.SUM_WARP)
+            assert np.abs(b["draws"][ch] - o["draws"]).max() <= TOL and b["n_accept"][ch] == o["n_accept"]
