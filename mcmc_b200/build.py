@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmcmc_b200.so")
 
 CU_SOURCES = ["engine.cu", "dispatch.cu", "hmc_wide.cu", "mala_wide.cu", "rmhmc.cu", "util_kernels.cu", "summary.cu", "rmhmc_general.cu",
-              "hmc_batched.cu", "gather.cu", "transpose.cu", "rmhmc_cta.cu", "nuts_batched.cu", "hmc_duo.cu"]
+              "hmc_batched.cu", "gather.cu", "transpose.cu", "rmhmc_cta.cu", "nuts_batched.cu", "hmc_duo.cu", "hmc_half.cu"]
 # compiled once per registered target (-DMCMCB200_TARGET_SLICE=k), so the big template fan-out builds in parallel
 SLICED_SOURCES = ["nuts.cu", "hmc.cu", "mala.cu", "rwmh.cu", "de.cu"]
 # translation units that take longest (dense targets in the NUTS kernel: ~9 min each) start first

@@ -22,6 +22,7 @@
 #include "hmc_batched.h"
 #include "nuts_batched.h"
 #include "hmc_duo.h"
+#include "hmc_half.h"
 
 namespace mcmcb200
 {
@@ -581,7 +582,8 @@ static int hmc_run_impl(const mcmcb200_problem_t* pr, const mcmcb200_rng_t* rng,
     } else {
         MCMCB200_CUDA_TRY(cudaEventRecord(s.ev0, s.stream));
         // few chains (strong-scaling shards): two warps per chain, variates of draw t + 1 generated under the trajectory of draw t
-        if (!wide && hmc_duo_supported(a)) { if ((rc = launch_hmc_duo(a))) return rc; }
+        if (!wide && hmc_half_supported(a)) { if ((rc = launch_hmc_half(a))) return rc; }   // n_dim <= 32: two chains per warp
+        else if (!wide && hmc_duo_supported(a)) { if ((rc = launch_hmc_duo(a))) return rc; }
         else if ((rc = wide ? launch_hmc_wide(a) : launch_hmc(a))) return rc;
     }
     MCMCB200_CUDA_TRY(cudaEventRecord(s.ev1, s.stream));

@@ -274,3 +274,29 @@ def test_two_warps_per_chain_kernel_reproduces_the_production_kernel(engine, ora
         for ch in (0, C - 1):
             o = oracle.run_chain(ol.HMC, tid, w, x0[ch], st, seed=31, rng_mode=ol.RNG_PHILOX, chain_id=3 + ch, sum_mode=ol.SUM_WARP)
             assert np.abs(b["draws"][ch] - o["draws"]).max() <= TOL and b["n_accept"][ch] == o["n_accept"]
+
+
+@pytest.mark.parametrize("tname", ["iso_gauss", "diag_gauss"])
+def test_two_chains_per_warp_kernel_for_small_n_dim(engine, oracle, monkeypatch, tname):
+    """n_dim <= 32 (BASELINE config 5's sweep point d = 32): hmc_half.cu puts two chains on one warp, 16 lanes each — same
+    per-lane arithmetic, Philox counters and spare-bit uniform per half, 16-lane reductions.  Bit-identical to the
+    warp-per-chain kernel (whose idle upper lanes only ever contributed zeros), odd chain counts and ragged n_dim included,
+    and within 1e-10 of the oracle."""
+    rng = np.random.default_rng(18)
+    for d, L, C in ((32, 10, 301), (31, 4, 64), (17, 7, 9), (2, 3, 5), (1, 2, 4), (8, 0, 6)):
+        w = np.exp(rng.uniform(-0.5, 0.5, size=d)) if tname == "diag_gauss" else None
+        x0 = rng.normal(size=(C, d))
+        kw = dict(target_data=w, n_leap_steps=L, step_size=0.13, n_burnin=5, n_keep=30, rng_mode=engine.api.RNG_PHILOX, seed=77, chain_offset=2,
+                  want_logp=True)
+        monkeypatch.setenv("MCMCB200_HMC_HALF", "0")
+        a = engine.hmc(x0, tname, **kw)
+        monkeypatch.setenv("MCMCB200_HMC_HALF", "1")
+        b = engine.hmc(x0, tname, **kw)
+        monkeypatch.delenv("MCMCB200_HMC_HALF")
+        assert np.array_equal(a["draws"], b["draws"]), (d, L, C, np.abs(a["draws"] - b["draws"]).max())
+        assert np.array_equal(a["n_accept"], b["n_accept"]) and np.array_equal(a["logp"], b["logp"])
+        st = ol.Settings(n_burnin=5, n_keep=30, n_leap_steps=L, step_size=0.13)
+        tid = ol.TGT_DIAG_GAUSS if tname == "diag_gauss" else ol.TGT_ISO_GAUSS
+        for ch in (0, C - 1):
+            o = oracle.run_chain(ol.HMC, tid, w, x0[ch], st, seed=77, rng_mode=ol.RNG_PHILOX, chain_id=2 + ch, sum_mode=ol.SUM_WARP)
+            assert np.abs(b["draws"][ch] - o["draws"]).max() <= TOL and b["n_accept"][ch] == o["n_accept"]
