@@ -860,29 +860,29 @@ template <int EPL, int RNGM, bool MEMO_SH, bool FT> __global__ void __launch_bou
 // finished takes the next chain from a global counter, so the 1.73 residency waves of 4096 chains (128 registers per
 // thread: 16 chains per SM) cost no idle tail.  Same accumulation order over k as nuts_ls_gemm: identical bits.
 // Full tiles only (n_dim = 64, 128, 256), max_tree_depth <= 10.
-constexpr int PC_WARPS = 16;
+constexpr int PC_WARPS = 16;   // chains per CTA of the full-size variant; small calls use 8 (template parameter NW)
 // NH sub-groups of PC_WARPS / NH warps each run their rounds independently (named barriers): while one sub-group's chains are
 // in their tree logic the other's product has the tensor pipe — a round's product and step phases overlap across sub-groups.
-template <int EPL, int NH> constexpr size_t pc_smem_bytes()
+template <int EPL, int NH, int NW = PC_WARPS> constexpr size_t pc_smem_bytes()
 {
     constexpr int D = 32 * EPL, LDX = D + 4;
-    return (size_t)PC_WARPS * sizeof(LsCtl) + (size_t)PC_WARPS * LS_TAB_SMEM * sizeof(LsSummary) + (size_t)PC_WARPS * LDX * 8 + (size_t)2 * PC_WARPS * D * 8;
+    return (size_t)NW * sizeof(LsCtl) + (size_t)NW * LS_TAB_SMEM * sizeof(LsSummary) + (size_t)NW * LDX * 8 + (size_t)2 * NW * D * 8;
 }
-template <int EPL, int RNGM, int NH> __global__ void __launch_bounds__(PC_WARPS * 32, 1) nuts_pc_kernel(const __grid_constant__ LsArgs a)
+template <int EPL, int RNGM, int NH, int NW = PC_WARPS> __global__ void __launch_bounds__(NW * 32, 1) nuts_pc_kernel(const __grid_constant__ LsArgs a)
 {
     constexpr int D = 32 * EPL, LDX = D + 4, NB = D / 8;
-    constexpr int GW = PC_WARPS / NH;                    // warps (= chains = MMA rows: 8 or 16) per sub-group
+    constexpr int GW = NW / NH;                    // warps (= chains = MMA rows: 8 or 16) per sub-group
     constexpr int MB = GW / 8;                           // 8-row MMA blocks per sub-group
     constexpr int NBW = (NB >= GW) ? NB / GW : 1;        // 8-column output blocks per warp
     extern __shared__ __align__(16) unsigned char pcsm[];
-    __shared__ int alive[PC_WARPS];
+    __shared__ int alive[NW];
     LsCtl* const ctl = reinterpret_cast<LsCtl*>(pcsm);
-    LsSummary* const memo_all = reinterpret_cast<LsSummary*>(pcsm + (size_t)PC_WARPS * sizeof(LsCtl));
-    double* const X = reinterpret_cast<double*>(memo_all + (size_t)PC_WARPS * LS_TAB_SMEM);   // [16][LDX] pending positions (the MMA's A operand)
-    double* const RH = X + PC_WARPS * LDX;                                                      // [16][D]   half-kicked momenta
+    LsSummary* const memo_all = reinterpret_cast<LsSummary*>(pcsm + (size_t)NW * sizeof(LsCtl));
+    double* const X = reinterpret_cast<double*>(memo_all + (size_t)NW * LS_TAB_SMEM);   // [16][LDX] pending positions (the MMA's A operand)
+    double* const RH = X + NW * LDX;                                                      // [16][D]   half-kicked momenta
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int grp = warp / GW, gw = warp % GW;
-    double* const Y = RH + PC_WARPS * D;                                                        // [16][D]   the products
+    double* const Y = RH + NW * D;                                                        // [16][D]   the products
     const int g = lane >> 2, t4 = lane & 3;
     LsCtl& c = ctl[warp];
     LsSummary* const memo = memo_all + (size_t)warp * LS_TAB_SMEM;
@@ -1132,12 +1132,20 @@ int launch_nuts_batched(const NutsLaunch& h, double* work, int* launches, long l
         int dev = 0, n_sm = 0;
         MCMCB200_CUDA_TRY(cudaGetDevice(&dev));
         MCMCB200_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        const long long want = (C + PC_WARPS - 1) / PC_WARPS;
-        const unsigned grid = (unsigned)(want < n_sm ? want : n_sm);
+        // Few chains (a strong-scaling shard: C4 over 8 GPUs = 512 chains): 16 chains per CTA would leave most SMs empty and a
+        // CTA's round costs the product of ALL its rows plus its slowest chain — 8 chains per CTA use twice the SMs and halve
+        // the product per round (512 chains: 1.45 s -> see DESIGN §4.13).  From 8 x #SMs chains on, 16 per CTA (every B fragment
+        // then feeds two MMAs).
+        bool small = C <= 8ll * n_sm;
+        if (const char* e = std::getenv("MCMCB200_NUTS_PERSIST_NW")) small = (e[0] == '8');
+        const int nw = small ? 8 : PC_WARPS;
+        const long long want = (C + nw - 1) / nw;
+        const long long slots = small ? 2ll * n_sm : n_sm;   // (two 8-chain CTAs fit one SM)
+        const unsigned grid = (unsigned)(want < slots ? want : slots);
         const bool philox = a.rng.mode == RNG_PHILOX;
         auto go = [&](auto kern, size_t smem) -> int {
             MCMCB200_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            kern<<<grid, PC_WARPS * 32, smem, st>>>(a);
+            kern<<<grid, nw * 32, smem, st>>>(a);
             MCMCB200_CUDA_TRY(cudaGetLastError());
             return MCMCB200_OK;
         };
@@ -1145,8 +1153,9 @@ int launch_nuts_batched(const NutsLaunch& h, double* work, int* launches, long l
         // one group of 16 chains per CTA: every B fragment loaded from L2 feeds two MMAs (two 8-row blocks).  Two independently
         // running groups of 8 (MCMCB200_NUTS_PERSIST_NH=2) overlap product and tree logic but stream the matrix twice: 3.3 s
         const bool halves = std::getenv("MCMCB200_NUTS_PERSIST_NH") && std::getenv("MCMCB200_NUTS_PERSIST_NH")[0] == '2';
-#define PC_GO(E) (halves ? (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 2>, pc_smem_bytes<E, 2>()) : go(nuts_pc_kernel<E, RNG_TAPE, 2>, pc_smem_bytes<E, 2>())) \
-                         : (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 1>, pc_smem_bytes<E, 1>()) : go(nuts_pc_kernel<E, RNG_TAPE, 1>, pc_smem_bytes<E, 1>())))
+#define PC_GO(E) (small  ? (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 1, 8>, pc_smem_bytes<E, 1, 8>()) : go(nuts_pc_kernel<E, RNG_TAPE, 1, 8>, pc_smem_bytes<E, 1, 8>())) \
+                 : halves ? (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 2>, pc_smem_bytes<E, 2>()) : go(nuts_pc_kernel<E, RNG_TAPE, 2>, pc_smem_bytes<E, 2>())) \
+                          : (philox ? go(nuts_pc_kernel<E, RNG_PHILOX, 1>, pc_smem_bytes<E, 1>()) : go(nuts_pc_kernel<E, RNG_TAPE, 1>, pc_smem_bytes<E, 1>())))
         switch (epl_for_dim(d)) {
         case 2: rc = PC_GO(2); break;
         case 4: rc = PC_GO(4); break;

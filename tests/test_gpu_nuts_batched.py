@@ -146,14 +146,17 @@ def test_persistent_variant_reproduces_the_rounds_bit_for_bit(engine, oracle, mo
         monkeypatch.setenv("MCMCB200_NUTS_PERSIST", "0")
         r = engine.nuts(x0, "dense_gauss", **kw)
         monkeypatch.delenv("MCMCB200_NUTS_PERSIST")
-        for nh in ("1", "2"):
+        # chains per CTA (8: the default below 8 x #SMs chains, 16: above) x independently running sub-groups per CTA
+        for nw, nh in (("8", "1"), ("16", "1"), ("16", "2")):
+            monkeypatch.setenv("MCMCB200_NUTS_PERSIST_NW", nw)
             monkeypatch.setenv("MCMCB200_NUTS_PERSIST_NH", nh)
             p = engine.nuts(x0, "dense_gauss", **kw)
             assert r["kernel_launches"] > 100 and p["kernel_launches"] == 2
-            assert np.array_equal(r["draws"], p["draws"]), (d, nh, np.abs(r["draws"] - p["draws"]).max())
+            assert np.array_equal(r["draws"], p["draws"]), (d, nw, nh, np.abs(r["draws"] - p["draws"]).max())
             assert np.array_equal(r["n_accept"], p["n_accept"]) and np.array_equal(r["n_leapfrog"], p["n_leapfrog"])
             assert np.array_equal(r["step_size"], p["step_size"]) and np.array_equal(r["logp"], p["logp"])
         monkeypatch.delenv("MCMCB200_NUTS_PERSIST_NH")
+        monkeypatch.delenv("MCMCB200_NUTS_PERSIST_NW")
         monkeypatch.delenv("MCMCB200_NUTS_BATCHED")
     # the reference's own stream (oracle-recorded tape) through the persistent kernel, linreg target
     d, C = 64, 3
