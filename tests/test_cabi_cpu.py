@@ -119,3 +119,48 @@ def test_user_target_library_registers_without_a_gpu():
     assert tid >= 64
     assert api.load().mcmcb200_target_data_len(tid, 2) == 1 and api.load().mcmcb200_target_data_len(tid, 3) == -1
     assert api.metric_lookup("funnel_softabs") == (api.TARGET_FUNNEL, 2)
+
+
+def test_argument_validation_precedes_the_device(api):
+    """Every run call validates its arguments before it touches the device, so a malformed call gets the specific error
+    (code + text in mcmcb200_last_error) with or without a GPU — never a CUDA error, never a silent clamp.  Mirrors the
+    reference's habit of refusing before sampling (src/de.cpp:83-91 bounds/size checks; include/misc/mcmc_structs.hpp
+    defaults)."""
+    import mcmc_b200
+
+    x0 = np.zeros((2, 4))
+
+    def err(fn, *a, **k):
+        with pytest.raises(mcmc_b200.McmcB200Error) as e:
+            fn(*a, **k)
+        return e.value.code, str(e.value)
+
+    # unknown target id / a target whose data blob is too short / n_dim invalid for the target
+    code, msg = err(mcmc_b200.hmc, x0, 4242, n_burnin=1, n_keep=1)
+    assert code == api.ERR_UNKNOWN_TARGET and "4242" in msg
+    code, msg = err(mcmc_b200.hmc, x0, "diag_gauss", target_data=np.ones(3), n_burnin=1, n_keep=1)
+    assert code == api.ERR_INVALID_ARG and "needs 4 doubles" in msg
+    code, msg = err(mcmc_b200.hmc, np.zeros((2, 3)), "normal_model", target_data=np.ones(3), n_burnin=1, n_keep=1)
+    assert code == api.ERR_UNKNOWN_TARGET   # the normal model has exactly two parameters
+    # draw counts and trajectory lengths out of range
+    code, msg = err(mcmc_b200.hmc, x0, "iso_gauss", n_burnin=-1, n_keep=1)
+    assert code == api.ERR_INVALID_ARG and "draw counts" in msg
+    code, msg = err(mcmc_b200.hmc, x0, "iso_gauss", n_leap_steps=-3, n_burnin=1, n_keep=1)
+    assert code == api.ERR_INVALID_ARG and "n_leap_steps" in msg
+    code, msg = err(mcmc_b200.rmhmc, np.zeros((2, 2)), "normal_model", target_data=np.ones(3), n_leap_steps=2**31, n_burnin=1, n_keep=1)
+    assert code == api.ERR_INVALID_ARG and "n_leap_steps" in msg
+    code, msg = err(mcmc_b200.nuts, x0, "iso_gauss", max_tree_depth=21, n_burnin=1, n_keep=1)
+    assert code == api.ERR_INVALID_ARG and "max_tree_depth" in msg
+    # n_dim beyond what the sampler/target combination supports is refused, not truncated
+    code, msg = err(mcmc_b200.hmc, np.zeros((2, 4096)), "iso_gauss", n_burnin=1, n_keep=1)
+    assert code == api.ERR_UNSUPPORTED and "n_dim=4096" in msg
+    # mcmc::de needs two other members for a proposal (src/de.cpp:166-178) and has no log-density output
+    code, msg = err(mcmc_b200.de, x0, "iso_gauss", n_pop=2, n_burnin=1, n_keep=1)
+    assert code == api.ERR_INVALID_ARG and "n_pop" in msg
+    code, msg = err(mcmc_b200.de, x0, "iso_gauss", n_pop=8, n_burnin=1, n_keep=1, want_logp=True)
+    assert code == api.ERR_UNSUPPORTED and "logp_out" in msg
+    # null pointers through the raw C ABI
+    lib = api.load()
+    assert lib.mcmcb200_hmc_run(None, None, None, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_nuts_run(None, None, None, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_de_run(None, None, None, None) == api.ERR_INVALID_ARG
