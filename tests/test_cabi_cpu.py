@@ -164,3 +164,17 @@ def test_argument_validation_precedes_the_device(api):
     assert lib.mcmcb200_hmc_run(None, None, None, None) == api.ERR_INVALID_ARG
     assert lib.mcmcb200_nuts_run(None, None, None, None) == api.ERR_INVALID_ARG
     assert lib.mcmcb200_de_run(None, None, None, None) == api.ERR_INVALID_ARG
+
+
+def test_integration_note_names_every_entry_point(api):
+    """INTEGRATION.md §1 maps every exported C entry point to the reference interface it replaces (or marks it new)."""
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for sym in api.EXPORTED_SYMBOLS:
+        stem = sym
+        if sym.endswith("_settings_default"):
+            stem = "mcmcb200_*_settings_default"
+        elif sym.startswith("mcmcb200_comm_"):
+            stem = "mcmcb200_comm_*"
+        elif sym == "mcmcb200_host_free":
+            stem = "mcmcb200_host_alloc / _free"
+        assert stem in txt, sym
