@@ -161,14 +161,35 @@ struct Ctx {
     bool bounded;             // algo_settings_t::vals_bound
     std::vector<int> btype;   // determine_bounds_type: 1 none, 2 lower, 3 upper, 4 both
     vec lb, ub;
+    // The reference forms its diagonal operators as FULL d x d matrices and multiplies by them: inv_jacobian_adjust
+    // (src/hmc.cpp:114-122, src/nuts.cpp:121-129, src/rmhmc.cpp:122-130, src/mala.cpp:111-119) and, with no precond_mat,
+    // the identity mass matrix (inv_precond_matrix = eye: src/hmc.cpp:57-59,171,160,184; src/nuts.cpp:64-66,148,204;
+    // nuts.ipp:51,66,84,140).  The products equal the element-wise ones — until an element of the multiplied vector is
+    // non-finite, when the exact zeros of every OTHER row turn it into NaN there (0 * inf).  That is observable only for a
+    // bounded chain whose trajectory diverged (inv_transform maps non-finite coordinates back to finite ones, so such a
+    // proposal can be accepted).  Literal-reference mode only (oracle_cfg_t::dense_jacobian): the comparator modes and the
+    // device kernels keep the element-wise products.
+    bool dense_jac = false;
 };
+
+// rows of (J_dense * w) that the off-diagonal zeros of J turn into NaN: row i if any OTHER element of w is non-finite
+static void dense_jacobian_poison(const Ctx& c, const double* w, double* out)
+{
+    if (!c.dense_jac || !c.bounded) return;
+    int n_bad = 0;
+    for (int j = 0; j < c.d; ++j) n_bad += std::isfinite(w[j]) ? 0 : 1;
+    if (n_bad == 0) return;
+    for (int i = 0; i < c.d; ++i)
+        if (n_bad - (std::isfinite(w[i]) ? 0 : 1) > 0) out[i] = std::numeric_limits<double>::quiet_NaN();
+}
 
 const double EPS_DBL = std::numeric_limits<double>::epsilon();   // mcmc::eps_dbl (mcmc_options.hpp:103)
 
 // include/misc/determine_bounds_type.hpp:27-57
-void setup_bounds(Ctx& c, int vals_bound, const double* lower, const double* upper)
+void setup_bounds(Ctx& c, int vals_bound, const double* lower, const double* upper, int dense_jacobian = 0)
 {
     c.bounded = vals_bound != 0;
+    c.dense_jac = c.bounded && dense_jacobian != 0;
     c.btype.assign(c.d, 1);
     if (!c.bounded) return;
     c.lb.assign(lower, lower + c.d);
@@ -410,8 +431,13 @@ void momentum_from_normals(const Ctx& c, const double* z, double* p)
 // K = p.(M^-1 p)/2   (src/hmc.cpp:160,184)
 double kinetic(const Ctx& c, const double* p)
 {
-    if (c.identity) return otgt::dot(p, p, c.d, c.sum_mode) / 2.0;
+    if (c.identity && !c.dense_jac) return otgt::dot(p, p, c.d, c.sum_mode) / 2.0;
     vec t(c.d);
+    if (c.identity) {                             // eye * p as a dense product (src/hmc.cpp:160,184)
+        for (int i = 0; i < c.d; ++i) t[i] = p[i];
+        dense_jacobian_poison(c, p, t.data());
+        return otgt::dot(p, t.data(), c.d, c.sum_mode) / 2.0;
+    }
     gemv_plain(c.Minv, c.d, p, t.data());
     return otgt::dot(p, t.data(), c.d, c.sum_mode) / 2.0;
 }
@@ -425,8 +451,10 @@ void leapfrog(const Ctx& c, double eps, double* x, double* p)
     box_grad(c, x, g.data(), J.data());
     if (c.bounded) for (int i = 0; i < d; ++i) p[i] = p[i] + (J[i] * (eps * g[i])) / 2.0;   // (step*J)*grad/2: J diagonal
     else for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
+    dense_jacobian_poison(c, g.data(), p);
     if (c.identity) {
         for (int i = 0; i < d; ++i) x[i] = x[i] + eps * p[i];
+        dense_jacobian_poison(c, p, x);           // (eps * eye) * p as a dense product (src/hmc.cpp:171)
     } else {
         gemv_scaled(c.Minv, d, eps, p, t.data());
         for (int i = 0; i < d; ++i) x[i] = x[i] + t[i];
@@ -434,6 +462,7 @@ void leapfrog(const Ctx& c, double eps, double* x, double* p)
     box_grad(c, x, g.data(), J.data());
     if (c.bounded) for (int i = 0; i < d; ++i) p[i] = p[i] + (J[i] * (eps * g[i])) / 2.0;
     else for (int i = 0; i < d; ++i) p[i] = p[i] + (eps * g[i]) / 2.0;
+    dense_jacobian_poison(c, g.data(), p);
 }
 
 void setup_precond(Ctx& c, const double* precond, int chol_mode)
@@ -485,6 +514,7 @@ struct oracle_cfg_t {
     double* tape_out; long tape_out_cap;  // optional: every variate consumed, in order
     int vals_bound; const double* lower; const double* upper;   // algo_settings_t::vals_bound / lower_bounds / upper_bounds
     int metric_id;           // rmhmc: metric registered with the target (0 = default)
+    int dense_jacobian;      // 1: literal src/*.cpp semantics of the dense inv_jacobian_adjust product for non-finite gradients (Ctx::dense_jac)
 };
 
 struct oracle_res_t {
@@ -509,7 +539,7 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
-    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper, cfg->dense_jacobian);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -561,6 +591,7 @@ static void mala_mean(const Ctx& c, double eps, const double* v, double* out, do
         // grad (j increasing), /2, added to v.  M = I: (J_ii * 1) * e2 on the diagonal, exact zeros elsewhere.
         if (c.identity) {
             for (int i = 0; i < d; ++i) out[i] = v[i] + ((J[i] * e2) * g[i]) / 2.0;
+            dense_jacobian_poison(c, g.data(), out);
         } else {
             for (int i = 0; i < d; ++i) t[i] = 0.0;
             for (int j = 0; j < d; ++j)
@@ -592,7 +623,7 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
-    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper, cfg->dense_jacobian);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -789,7 +820,7 @@ static int run_nuts(const oracle_cfg_t* cfg, const double* x0, double* draws, do
 {
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     setup_precond(c, cfg->precond, cfg->chol_mode);
-    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper, cfg->dense_jacobian);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;
@@ -926,8 +957,9 @@ static void rm_mntm_update(const Ctx& c, double eps, const double* y, const doub
         const double dp = otgt::dot(tq.data(), Aq.data(), d, c.sum_mode);
         g[i] = -g[i] + 0.5 * (tr - dp);
     }
-    if (c.bounded) for (int i = 0; i < d; ++i) out[i] = (J[i] * (eps * g[i])) / 2.0;   // step*J*grad/2 (src/rmhmc.cpp:125)
+    if (c.bounded) for (int i = 0; i < d; ++i) out[i] = (J[i] * (eps * g[i])) / 2.0;   // step*J*grad/2 (src/rmhmc.cpp:130)
     else for (int i = 0; i < d; ++i) out[i] = (eps * g[i]) / 2.0;
+    dense_jacobian_poison(c, g.data(), out);
 }
 
 static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, double* logp_out, oracle_res_t* res)
@@ -935,7 +967,7 @@ static int run_rmhmc(const oracle_cfg_t* cfg, const double* x0, double* draws, d
     Ctx c; c.target_id = cfg->target_id; c.tdata = cfg->tdata; c.d = cfg->d; c.sum_mode = cfg->sum_mode;
     c.identity = true;   // precond_mat is never read (Q18)
     c.metric_id = cfg->metric_id;
-    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper);
+    setup_bounds(c, cfg->vals_bound, cfg->lower, cfg->upper, cfg->dense_jacobian);
     Rng rng; init_rng(rng, cfg);
     const int d = c.d;
     const long n_total = cfg->n_burnin + cfg->n_keep;

@@ -57,6 +57,7 @@ class _OracleCfg(ctypes.Structure):
         ("chain_id", ctypes.c_long), ("sum_mode", ctypes.c_int), ("mala_exact_dmvnorm", ctypes.c_int),
         ("tape_out", ctypes.c_void_p), ("tape_out_cap", ctypes.c_long),
         ("vals_bound", ctypes.c_int), ("lower", ctypes.c_void_p), ("upper", ctypes.c_void_p), ("metric_id", ctypes.c_int),
+        ("dense_jacobian", ctypes.c_int),
     ]
 
 
@@ -213,7 +214,7 @@ class Oracle:
         self.lib.oracle_target.restype = ctypes.c_double
 
     def run_chain(self, sampler, target_id, tdata, x0, st, seed=0, rng_mode=RNG_MT, tape=None, chain_id=0,
-                  sum_mode=SUM_SEQ, chol_mode=1, mala_exact=0, record_tape=0, want_logp=False, want_margins=False):
+                  sum_mode=SUM_SEQ, chol_mode=1, mala_exact=0, record_tape=0, want_logp=False, want_margins=False, dense_jacobian=0):
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         d = x0.size
         tdata = np.ascontiguousarray(tdata if tdata is not None else [0.0], dtype=np.float64)
@@ -227,7 +228,7 @@ class Oracle:
                          st["target_accept_rate"], st["gamma_val"], st["t0_val"], st["kappa_val"],
                          st["max_tree_depth"], rng_mode, ctypes.c_ulong(seed), _ptr(tape_a),
                          0 if tape_a is None else tape_a.size, chain_id, sum_mode, mala_exact, _ptr(rec),
-                         record_tape, vb, lo, hi, st["metric_id"])
+                         record_tape, vb, lo, hi, st["metric_id"], int(dense_jacobian))
         draws = np.zeros((st["n_keep"], d))
         logp = np.zeros(st["n_keep"]) if want_logp else None
         res = _OracleRes()

@@ -287,3 +287,82 @@ def test_de_golden_cases(oracle, golden):
         o = oracle.run_de(c["target"], c["tdata"], c["x0"], st, seed=c["seed"])
         assert np.array_equal(o["draws"], want), c["name"]
         assert o["n_accept"] == c["n_accept"], c["name"]
+
+
+def _swept_cases(n_cases=72):
+    """A seeded sweep over the settings space (dimension, trajectory length, step size, draw counts, target family,
+    identity / dense mass, open / half-open / closed boxes): the oracle is pinned to the unmodified reference well away
+    from the hand-picked cases above."""
+    rng = np.random.default_rng(20261017)
+    cases = []
+    for k in range(n_cases):
+        sampler = [ol.HMC, ol.MALA, ol.NUTS, ol.RWMH][k % 4]
+        d = int(rng.integers(1, 41))
+        fam = int(rng.integers(0, 4))
+        if fam == 0:
+            tid, tdata = ol.TGT_ISO_GAUSS, None
+        elif fam == 1:
+            tid, tdata = ol.TGT_DIAG_GAUSS, np.exp(rng.uniform(-1, 1, d))
+        else:
+            a = rng.normal(size=(d, d))
+            P = a @ a.T / d + (0.5 + rng.uniform()) * np.eye(d)
+            P = (P + P.T) / 2
+            if fam == 2:
+                tid, tdata = ol.TGT_DENSE_GAUSS, P.ravel()
+            else:
+                tid, tdata = ol.TGT_LINREG, np.concatenate([P.ravel(), rng.normal(size=d)])
+        kw = dict(n_burnin=int(rng.integers(0, 8)), n_keep=int(rng.integers(1, 40)))
+        eps = float(np.exp(rng.uniform(np.log(0.02), np.log(0.6))) / d ** 0.25)
+        if sampler == ol.HMC:
+            kw.update(n_leap_steps=int(rng.integers(1, 13)), step_size=eps)
+        elif sampler == ol.NUTS:
+            adapt = int(rng.integers(0, 2)) * kw["n_burnin"]
+            kw.update(step_size=eps, n_adapt_draws=adapt, max_tree_depth=int(rng.integers(1, 8)))
+        else:
+            kw.update(step_size=eps)
+        x0 = rng.normal(size=d)
+        box = int(rng.integers(0, 3))
+        dense_m = rng.uniform() < 0.35 and not (sampler == ol.MALA and box)   # bounded MALA: M = I is the form restated
+        if dense_m:
+            m = rng.normal(size=(d, d))
+            M = m @ m.T / d + np.eye(d)
+            kw["precond"] = (M + M.T) / 2
+        if box:
+            lo = np.where(rng.uniform(size=d) < 0.5, x0 - rng.uniform(0.2, 3.0, d), -np.inf)
+            hi = np.where(rng.uniform(size=d) < 0.5, x0 + rng.uniform(0.2, 3.0, d), np.inf)
+            if box == 2:
+                hi = np.full(d, np.inf)
+            kw.update(lower_bounds=lo, upper_bounds=hi)
+        cases.append(("sweep %d: sampler %d family %d d=%d box=%d denseM=%d" % (k, sampler, fam, d, box, int(dense_m)), sampler, tid, tdata, x0,
+                      ol.Settings(**kw), 1000 + k))
+    return cases
+
+
+def test_oracle_bit_equal_to_live_reference_on_a_seeded_sweep(oracle, reference):
+    """Bit-equal draw for draw over 240 seeded settings, including the chains the sweep drives unstable.  Those pin one more
+    piece of reference semantics (oracle.cpp Ctx::dense_jac): the reference multiplies by its diagonal operators — the
+    inverse-Jacobian matrix and the identity mass matrix — as FULL d x d matrices (src/hmc.cpp:57-59,122,160,171,184), so one
+    non-finite momentum / gradient element turns every other row into NaN (0 * inf); in a bounded chain inv_transform maps
+    those back to finite coordinates and the proposal can be accepted (accept test on a NaN energy: std::min(0.01, NaN) =
+    0.01, src/hmc.cpp:188).  Without dense_jacobian=1 the restatement keeps the element-wise products and differs exactly
+    there (the second half of this test shows it is ONLY there)."""
+    n_moved = n_finite = n_elementwise_differs = 0
+    for name, sampler, tid, tdata, x0, st, seed in _swept_cases(240):
+        ref, acc = reference.run_chain(sampler, tid, tdata, x0, st, seed)
+        kw = dict(seed=seed, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1)
+        o = oracle.run_chain(sampler, tid, tdata, x0, st, dense_jacobian=1, **kw)
+        assert np.array_equal(o["draws"], ref, equal_nan=True), name
+        assert o["n_accept"] == acc, name
+        fin = bool(np.isfinite(ref).all())
+        n_finite += int(fin)
+        n_moved += int(fin and acc > 0)
+        e = oracle.run_chain(sampler, tid, tdata, x0, st, **kw)   # element-wise products (what the device kernels do)
+        same = np.array_equal(e["draws"], ref, equal_nan=True) and e["n_accept"] == acc
+        if not same:
+            assert st["lower_bounds"] is not None, name           # only bounded chains ...
+            t = int(np.argmax([not np.array_equal(e["draws"][k], ref[k], equal_nan=True) for k in range(len(ref))]))
+            at_bound = np.isclose(ref[t], st["lower_bounds"], rtol=0, atol=1e-12) | np.isclose(ref[t], st["upper_bounds"], rtol=0, atol=1e-12)
+            assert at_bound.any() or not np.isfinite(ref[t]).all(), name   # ... whose trajectory left the finite range
+            n_elementwise_differs += 1
+    assert n_finite >= 200 and n_moved >= 170, (n_finite, n_moved)   # the sweep is not a collection of stuck or diverged chains
+    assert 1 <= n_elementwise_differs <= 12, n_elementwise_differs
