@@ -366,3 +366,36 @@ def test_oracle_bit_equal_to_live_reference_on_a_seeded_sweep(oracle, reference)
             n_elementwise_differs += 1
     assert n_finite >= 200 and n_moved >= 170, (n_finite, n_moved)   # the sweep is not a collection of stuck or diverged chains
     assert 1 <= n_elementwise_differs <= 12, n_elementwise_differs
+
+
+def test_rmhmc_oracle_bit_equal_to_live_reference_on_a_seeded_sweep(oracle, reference):
+    """mcmc::rmhmc over 120 seeded settings (Normal model with its Fisher metric; Neal's funnel d = 2..12 with both registered
+    metrics; trajectory lengths 1-5, 1-6 fixed-point steps, steps 0.01-0.4, a third of the cases with box constraints)."""
+    rng = np.random.default_rng(777)
+    xs = 2 + 2 * np.sin(np.arange(100.0))
+    nm = [100.0, float(xs.mean()), float(((xs - xs.mean()) ** 2).sum())]
+    n_moved = n_finite = 0
+    for k in range(120):
+        if k % 3 == 0:
+            tid, tdata, x0, mid = ol.TGT_NORMAL_MODEL, nm, rng.uniform(1.5, 4, 2), 0
+        else:
+            d = int(rng.integers(2, 13))
+            tid, tdata, mid = ol.TGT_FUNNEL, None, 1 + k % 2
+            x0 = np.concatenate([[rng.uniform(-0.5, 0.5)], 0.6 * rng.normal(size=d - 1)])
+        kw = dict(n_burnin=int(rng.integers(0, 4)), n_keep=int(rng.integers(1, 25)), n_leap_steps=int(rng.integers(1, 6)),
+                  step_size=float(np.exp(rng.uniform(np.log(0.01), np.log(0.4)))), n_fp_steps=int(rng.integers(1, 7)), metric_id=mid)
+        if rng.uniform() < 0.3:
+            dd = len(x0)
+            lo = np.where(rng.uniform(size=dd) < 0.5, x0 - rng.uniform(0.2, 3, dd), -np.inf)
+            hi = np.where(rng.uniform(size=dd) < 0.5, x0 + rng.uniform(0.2, 3, dd), np.inf)
+            if tid == ol.TGT_NORMAL_MODEL:
+                lo[1] = max(lo[1], 0.0) if np.isfinite(lo[1]) else 0.0   # sigma > 0
+            kw.update(lower_bounds=lo, upper_bounds=hi)
+        st = ol.Settings(**kw)
+        ref, acc = reference.run_chain(ol.RMHMC, tid, tdata, x0, st, 5000 + k)
+        o = oracle.run_chain(ol.RMHMC, tid, tdata, x0, st, seed=5000 + k, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1, dense_jacobian=1)
+        assert np.array_equal(o["draws"], ref, equal_nan=True), (k, kw)
+        assert o["n_accept"] == acc, (k, kw)
+        n_finite += int(np.isfinite(ref).all())
+        n_moved += int(acc > 0)
+    assert n_finite >= 100 and n_moved >= 90, (n_finite, n_moved)
