@@ -399,3 +399,39 @@ def test_rmhmc_oracle_bit_equal_to_live_reference_on_a_seeded_sweep(oracle, refe
         n_finite += int(np.isfinite(ref).all())
         n_moved += int(acc > 0)
     assert n_finite >= 100 and n_moved >= 90, (n_finite, n_moved)
+
+
+def test_de_oracle_bit_equal_to_live_reference_on_a_seeded_sweep(oracle, reference):
+    """mcmc::de over 150 seeded settings (n_dim 1-16, four target families, populations of 3-29 members, jumps on / off,
+    par_b 1e-5..1e-1, par_gamma_jump 0.5-2.5, default / explicit initial box / box constraints): src/de.cpp:30-271."""
+    rng = np.random.default_rng(4242)
+    n_moved = 0
+    for k in range(150):
+        d, fam = int(rng.integers(1, 17)), int(rng.integers(0, 4))
+        if fam == 0:
+            tid, tdata = ol.TGT_ISO_GAUSS, None
+        elif fam == 1:
+            tid, tdata = ol.TGT_DIAG_GAUSS, np.exp(rng.uniform(-1, 1, d))
+        elif fam == 2:
+            a = rng.normal(size=(d, d))
+            P = a @ a.T / d + np.eye(d)
+            tid, tdata = ol.TGT_DENSE_GAUSS, ((P + P.T) / 2).ravel()
+        else:
+            d = max(d, 2)
+            tid, tdata = ol.TGT_FUNNEL, None
+        x0 = rng.normal(size=d)
+        kw = dict(n_pop=int(rng.integers(3, 30)), n_burnin=int(rng.integers(0, 10)), n_keep=int(rng.integers(1, 20)), jumps=bool(rng.integers(0, 2)),
+                  par_b=float(10 ** rng.uniform(-5, -1)), par_gamma_jump=float(rng.uniform(0.5, 2.5)))
+        m = int(rng.integers(0, 3))
+        if m == 1:
+            kw.update(initial_lb=x0 - rng.uniform(0.1, 2, d), initial_ub=x0 + rng.uniform(0.1, 2, d))
+        if m == 2:
+            kw.update(lower_bounds=np.where(rng.uniform(size=d) < 0.5, x0 - rng.uniform(0.6, 3, d), -np.inf),
+                      upper_bounds=np.where(rng.uniform(size=d) < 0.5, x0 + rng.uniform(0.6, 3, d), np.inf))
+        st = ol.DeSettings(**kw)
+        ref, acc = reference.run_de(tid, tdata, x0, st, 9000 + k)
+        o = oracle.run_de(tid, tdata, x0, st, seed=9000 + k)
+        assert np.array_equal(o["draws"], ref, equal_nan=True), (k, kw)
+        assert o["n_accept"] == acc, (k, kw)
+        n_moved += int(acc > 0)
+    assert n_moved >= 140
