@@ -164,7 +164,7 @@ struct Ctx {
     // The reference forms its diagonal operators as FULL d x d matrices and multiplies by them: inv_jacobian_adjust
     // (src/hmc.cpp:114-122, src/nuts.cpp:121-129, src/rmhmc.cpp:122-130, src/mala.cpp:111-119) and, with no precond_mat,
     // the identity mass matrix (inv_precond_matrix = eye: src/hmc.cpp:57-59,171,160,184; src/nuts.cpp:64-66,148,204;
-    // nuts.ipp:51,66,84,140).  The products equal the element-wise ones — until an element of the multiplied vector is
+    // nuts.ipp:51,66,84,140; bounded MALA: J * M, chol(J) * sqrtM and the proposal covariance, src/mala.cpp:111-119,155-157).  The products equal the element-wise ones — until an element of the multiplied vector is
     // non-finite, when the exact zeros of every OTHER row turn it into NaN there (0 * inf).  That is observable only for a
     // bounded chain whose trajectory diverged (inv_transform maps non-finite coordinates back to finite ones, so such a
     // proposal can be accepted).  Literal-reference mode only (oracle_cfg_t::dense_jacobian): the comparator modes and the
@@ -578,6 +578,15 @@ static int run_hmc(const oracle_cfg_t* cfg, const double* x0, double* draws, dou
     return 0;
 }
 
+// diag(J) as a full d x d matrix times B, the way the reference forms it (inv_jacobian_adjust returns a Mat_t): with a
+// non-finite J_ii the zeros of B (or of J's own off-diagonal) produce NaN entries — literal mode only (Ctx::dense_jac)
+static void dense_diag_times(const double* J, const vec& B, int d, vec& C)
+{
+    vec Jd(size_t(d) * d, 0.0);
+    for (int i = 0; i < d; ++i) Jd[size_t(i) * d + i] = J[i];
+    matmul(Jd, B, d, C);
+}
+
 // ------------------------------------------------------------------ MALA (src/mala.cpp:30-208, mala.ipp:30-70, dmvnorm.hpp:28-54)
 static void mala_mean(const Ctx& c, double eps, const double* v, double* out, double* J_out = nullptr)
 {
@@ -586,6 +595,16 @@ static void mala_mean(const Ctx& c, double eps, const double* v, double* out, do
     vec g(d), t(d), J(d);
     box_grad(c, v, g.data(), J.data());
     const double e2 = eps * eps;
+    if (c.bounded && c.dense_jac) {
+        // literal: J as a full matrix, (J * M) * e2 as a matrix, times grad (run_mala materialises M = eye for this mode)
+        vec JM;
+        dense_diag_times(J.data(), c.M, d, JM);
+        for (double& a : JM) a *= e2;
+        gemv_plain(JM, d, g.data(), t.data());
+        for (int i = 0; i < d; ++i) out[i] = v[i] + t[i] / 2.0;
+        if (J_out) for (int i = 0; i < d; ++i) J_out[i] = J[i];
+        return;
+    }
     if (c.bounded) {
         // ((e2*J) * M) -> matrix product then "*= e2" (ScaledMat * Matrix in the stand-in): entries (J_ii * M_ij) * e2; times
         // grad (j increasing), /2, added to v.  M = I: (J_ii * 1) * e2 on the diagonal, exact zeros elsewhere.
@@ -629,6 +648,12 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     const long n_total = cfg->n_burnin + cfg->n_keep;
     const double eps = cfg->step_size;
     const double e2 = eps * eps;
+    if (c.dense_jac && c.identity) {   // literal mode: precond_matrix = eye as a full matrix (src/mala.cpp:57-58), chol(eye) = eye
+        c.M.assign(size_t(d) * d, 0.0);
+        for (int i = 0; i < d; ++i) c.M[size_t(i) * d + i] = 1.0;
+        c.S = c.M; c.Minv = c.M;
+        c.identity = false;
+    }
 
     // Sigma = eps^2 M (materialised like ScaledMat -> Mat_t) and, for the cancelled form, its inverse
     vec Sigma(size_t(d) * d, 0.0), SigInv;
@@ -644,7 +669,16 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
     for (long it = 0; it < n_total; ++it) {
         rng.normals(it, d, z.data());                 // :150
         mala_mean(c, eps, prev.data(), mean_prev.data(), Jprev.data());
-        if (c.bounded && c.identity)   // :155-157: mean + ((eps*chol(J)) * sqrtM) * z, chol of the diagonal J = sqrt(J_ii), sqrtM = I
+        if (c.bounded && c.dense_jac) {   // literal :155-157: chol of the FULL matrix J, ((eps * L) * sqrtM) as a matrix, times z
+            vec Jd(size_t(d) * d, 0.0), L, P;
+            for (int i = 0; i < d; ++i) Jd[size_t(i) * d + i] = Jprev[i];
+            mat_chol(Jd, d, cfg->chol_mode, L);
+            matmul(L, c.S, d, P);
+            for (double& a : P) a *= eps;
+            gemv_plain(P, d, z.data(), t.data());
+            for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + t[i];
+        }
+        else if (c.bounded && c.identity)   // :155-157: mean + ((eps*chol(J)) * sqrtM) * z, chol of the diagonal J = sqrt(J_ii), sqrtM = I
             for (int i = 0; i < d; ++i) cur[i] = mean_prev[i] + (std::sqrt(Jprev[i]) * eps) * z[i];
         else if (c.bounded) {          // dense sqrtM: entries (sqrt(J_ii) * S_ij) * eps, times z (j increasing)
             for (int i = 0; i < d; ++i) t[i] = 0.0;
@@ -665,7 +699,8 @@ static int run_mala(const oracle_cfg_t* cfg, const double* x0, double* draws, do
                 //  LLT log-det of its lower triangle can be NaN — in BOTH densities — and then min(0.01, NaN) accepts; only the
                 //  literal evaluation reproduces that.  The device path refuses this combination.)
                 vec Sg(size_t(d) * d, 0.0);
-                if (c.identity) for (int i = 0; i < d; ++i) Sg[size_t(i) * d + i] = Jprop[i] * e2;
+                if (c.dense_jac) { dense_diag_times(Jprop.data(), c.M, d, Sg); for (double& a : Sg) a *= e2; }
+                else if (c.identity) for (int i = 0; i < d; ++i) Sg[size_t(i) * d + i] = Jprop[i] * e2;
                 else   // (J(prop) * M) * e2: NOT symmetric; LLT reads its lower triangle, the QR solve the whole matrix — as the reference does
                     for (int j = 0; j < d; ++j)
                         for (int i = 0; i < d; ++i) Sg[size_t(j) * d + i] = (Jprop[i] * c.M[size_t(j) * d + i]) * e2;

@@ -435,3 +435,59 @@ def test_de_oracle_bit_equal_to_live_reference_on_a_seeded_sweep(oracle, referen
         assert o["n_accept"] == acc, (k, kw)
         n_moved += int(acc > 0)
     assert n_moved >= 140
+
+
+def _harsh_cases(n_cases):
+    """Like _swept_cases but aimed at the edges: step sizes up to 3 (most trajectories overflow), trajectories up to 29 steps,
+    initial points up to 5 sigma out, boxes as tight as 0.05, and a dense mass matrix also for bounded MALA (the combination
+    the device path refuses, §4.6)."""
+    rng = np.random.default_rng(99)
+    out = []
+    for k in range(n_cases):
+        sampler = [ol.HMC, ol.MALA, ol.NUTS, ol.RWMH][k % 4]
+        d, fam = int(rng.integers(1, 25)), int(rng.integers(0, 4))
+        if fam == 0:
+            tid, tdata = ol.TGT_ISO_GAUSS, None
+        elif fam == 1:
+            tid, tdata = ol.TGT_DIAG_GAUSS, np.exp(rng.uniform(-2, 2, d))
+        else:
+            a = rng.normal(size=(d, d))
+            P = a @ a.T / d + (0.2 + rng.uniform()) * np.eye(d)
+            P = (P + P.T) / 2
+            tid, tdata = (ol.TGT_DENSE_GAUSS, P.ravel()) if fam == 2 else (ol.TGT_LINREG, np.concatenate([P.ravel(), rng.normal(size=d)]))
+        kw = dict(n_burnin=int(rng.integers(0, 8)), n_keep=int(rng.integers(1, 30)))
+        eps = float(np.exp(rng.uniform(np.log(0.02), np.log(3.0))))
+        if sampler == ol.HMC:
+            kw.update(n_leap_steps=int(rng.integers(1, 30)), step_size=eps)
+        elif sampler == ol.NUTS:
+            kw.update(step_size=eps, n_adapt_draws=int(rng.integers(0, 2)) * kw["n_burnin"], max_tree_depth=int(rng.integers(1, 9)))
+        else:
+            kw.update(step_size=eps)
+        x0 = rng.normal(size=d) * rng.choice([0.3, 1, 5])
+        box = int(rng.integers(0, 3))
+        if rng.uniform() < 0.35:
+            m = rng.normal(size=(d, d))
+            M = m @ m.T / d + np.eye(d)
+            kw["precond"] = (M + M.T) / 2
+        if box:
+            lo = np.where(rng.uniform(size=d) < 0.5, x0 - rng.uniform(0.05, 3, d), -np.inf)
+            hi = np.where(rng.uniform(size=d) < 0.5, x0 + rng.uniform(0.05, 3, d), np.inf)
+            if box == 2:
+                hi = np.full(d, np.inf)
+            kw.update(lower_bounds=lo, upper_bounds=hi)
+        out.append((k, sampler, tid, tdata, x0, ol.Settings(**kw), 20000 + k))
+    return out
+
+
+def test_oracle_bit_equal_to_live_reference_at_the_edges(oracle, reference):
+    """1200 seeded settings of which about a tenth overflow: the literal mode of the restatement (dense_jacobian=1: the
+    reference's diagonal operators as full matrices — inv_jacobian_adjust, eye as mass matrix, chol(J) and (J M) eps^2 in
+    bounded MALA, src/mala.cpp:111-119,155-157, mala.ipp:55-56) reproduces the unmodified reference bit for bit, NaN for NaN."""
+    n_nonfinite = 0
+    for k, sampler, tid, tdata, x0, st, seed in _harsh_cases(1200):
+        ref, acc = reference.run_chain(sampler, tid, tdata, x0, st, seed)
+        o = oracle.run_chain(sampler, tid, tdata, x0, st, seed=seed, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1, mala_exact=1, dense_jacobian=1)
+        assert np.array_equal(o["draws"], ref, equal_nan=True), (k, sampler, dict(st))
+        assert o["n_accept"] == acc, (k, sampler, dict(st))
+        n_nonfinite += int(not np.isfinite(ref).all())
+    assert 60 <= n_nonfinite <= 400, n_nonfinite
