@@ -178,3 +178,31 @@ def test_integration_note_names_every_entry_point(api):
         elif sym == "mcmcb200_host_free":
             stem = "mcmcb200_host_alloc / _free"
         assert stem in txt, sym
+
+
+def test_hot_kernels_keep_their_register_budget():
+    """Static guard (cuobjdump on the objects build() leaves behind, no GPU): the kernels whose occupancy the measured numbers
+    rest on keep their register budget and do not spill — the headline HMC kernel 72 registers / 0 stack (7 warps per
+    sub-partition), the persistent NUTS kernel with 16 chains per CTA 128 registers (§4.13), the RM-HMC CTA kernel
+    128 registers (4 CTAs per SM, §4.4), two-chains-per-warp HMC 64."""
+    import subprocess
+    import sys
+
+    build = os.path.join(ROOT, "mcmc_b200", "build")
+    if not os.path.isdir(build) or not os.path.exists(os.path.join(build, "hmc.cu.t0.o")):
+        pytest.skip("no build objects here (the library was built elsewhere)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "resource_usage.py")], capture_output=True, text=True, check=True).stdout
+    rows = {}
+    for line in out.splitlines()[1:]:
+        f = line.split(None, 5)
+        rows[f[5].strip()] = tuple(int(v) for v in f[1:5])   # regs, stack, shared, local
+
+    regs, stack, _, local = rows["hmc_pipe_kernel<IsoGauss, 4, 10, 1, false>"]
+    assert regs <= 72 and stack == 0 and local == 0
+    for k, v in rows.items():
+        if k.startswith("nuts_pc_kernel<8,") and k.endswith(", 16>"):
+            assert v[0] <= 128 and v[3] == 0, (k, v)
+        if k.startswith("rmhmc_cta_kernel<Funnel, FunnelSoftabsCta") and k.endswith("false>"):
+            assert v[0] <= 128 and v[3] == 0, (k, v)
+        if k.startswith("hmc_half_kernel<"):
+            assert v[0] <= 64 and v[1] == 0, (k, v)
