@@ -508,3 +508,79 @@ def test_comparator_modes_track_the_reference_over_the_seeded_sweep(oracle, refe
         assert err <= 1e-10, (name, err)
         worst, n = max(worst, err), n + 1
     assert n >= 225
+
+
+def test_rmhmc_oracle_bit_equal_to_live_reference_at_the_edges(oracle, reference):
+    """mcmc::rmhmc, 300 seeded settings aimed at the edges (steps up to 2, 0-7 fixed-point iterations, up to 8 leapfrog steps,
+    funnel d up to 16 started up to 3 sigma out, tight boxes): about a quarter of the chains go non-finite — the reference's
+    fixed-point iterations diverge and it accepts NaN energies (src/rmhmc.cpp:199-272) — and the restatement follows bit for bit."""
+    rng = np.random.default_rng(31337)
+    xs = 2 + 2 * np.sin(np.arange(100.0))
+    nm = [100.0, float(xs.mean()), float(((xs - xs.mean()) ** 2).sum())]
+    n_nonfinite = 0
+    for k in range(300):
+        if k % 3 == 0:
+            tid, tdata, x0, mid = ol.TGT_NORMAL_MODEL, nm, rng.uniform(0.5, 6, 2), 0
+        else:
+            d = int(rng.integers(2, 17))
+            tid, tdata, mid = ol.TGT_FUNNEL, None, 1 + k % 2
+            x0 = np.concatenate([[rng.uniform(-2, 2)], rng.choice([0.3, 1, 3]) * rng.normal(size=d - 1)])
+        kw = dict(n_burnin=int(rng.integers(0, 4)), n_keep=int(rng.integers(1, 25)), n_leap_steps=int(rng.integers(1, 9)),
+                  step_size=float(np.exp(rng.uniform(np.log(0.01), np.log(2.0)))), n_fp_steps=int(rng.integers(0, 8)), metric_id=mid)
+        if rng.uniform() < 0.4:
+            dd = len(x0)
+            lo = np.where(rng.uniform(size=dd) < 0.5, x0 - rng.uniform(0.05, 3, dd), -np.inf)
+            hi = np.where(rng.uniform(size=dd) < 0.5, x0 + rng.uniform(0.05, 3, dd), np.inf)
+            if tid == ol.TGT_NORMAL_MODEL:
+                lo[1] = max(lo[1], 0.0) if np.isfinite(lo[1]) else 0.0
+            kw.update(lower_bounds=lo, upper_bounds=hi)
+        st = ol.Settings(**kw)
+        ref, acc = reference.run_chain(ol.RMHMC, tid, tdata, x0, st, 70000 + k)
+        o = oracle.run_chain(ol.RMHMC, tid, tdata, x0, st, seed=70000 + k, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1, dense_jacobian=1)
+        assert np.array_equal(o["draws"], ref, equal_nan=True), (k, kw)
+        assert o["n_accept"] == acc, (k, kw)
+        n_nonfinite += int(not np.isfinite(ref).all())
+    assert 30 <= n_nonfinite <= 150, n_nonfinite
+
+
+def test_nuts_oracle_bit_equal_to_live_reference_on_long_adaptive_runs(oracle, reference):
+    """mcmc::nuts, 100 seeded settings with up to 150 adaptive + 60 kept draws, trees up to depth 10, n_dim up to 60, five
+    target families (condition numbers up to ~1e2 for the diagonal family), random dual-averaging constants, dense mass and box
+    constraints in a third of the cases each — about half a million leapfrog steps (include/mcmc/nuts.ipp:30-241,
+    src/nuts.cpp:160-332), draw for draw bit-equal."""
+    rng = np.random.default_rng(5150)
+    n_leapfrog = 0
+    for k in range(100):
+        d, fam = int(rng.integers(1, 61)), int(rng.integers(0, 5))
+        if fam == 0:
+            tid, tdata = ol.TGT_ISO_GAUSS, None
+        elif fam == 1:
+            tid, tdata = ol.TGT_DIAG_GAUSS, np.exp(rng.uniform(-2.5, 2.5, d))
+        elif fam in (2, 3):
+            a = rng.normal(size=(d, d))
+            P = a @ a.T / d + (0.05 + rng.uniform()) * np.eye(d)
+            P = (P + P.T) / 2
+            tid, tdata = (ol.TGT_DENSE_GAUSS, P.ravel()) if fam == 2 else (ol.TGT_LINREG, np.concatenate([P.ravel(), rng.normal(size=d)]))
+        else:
+            d = max(2, min(d, 12))
+            tid, tdata = ol.TGT_FUNNEL, None
+        nb = int(rng.integers(0, 150))
+        kw = dict(n_burnin=nb, n_keep=int(rng.integers(1, 60)), n_adapt_draws=int(rng.choice([0, nb, nb // 2, nb + 20])),
+                  step_size=float(np.exp(rng.uniform(np.log(0.005), np.log(1.0)))), max_tree_depth=int(rng.integers(1, 11)),
+                  target_accept_rate=float(rng.uniform(0.4, 0.9)), gamma_val=float(rng.uniform(0.02, 0.2)), t0_val=float(rng.uniform(5, 20)),
+                  kappa_val=float(rng.uniform(0.6, 0.9)))
+        x0 = rng.normal(size=d)
+        if rng.uniform() < 0.3:
+            m = rng.normal(size=(d, d))
+            M = m @ m.T / d + np.eye(d)
+            kw["precond"] = (M + M.T) / 2
+        if rng.uniform() < 0.3:
+            kw.update(lower_bounds=np.where(rng.uniform(size=d) < 0.5, x0 - rng.uniform(0.2, 3, d), -np.inf),
+                      upper_bounds=np.where(rng.uniform(size=d) < 0.5, x0 + rng.uniform(0.2, 3, d), np.inf))
+        st = ol.Settings(**kw)
+        ref, acc = reference.run_chain(ol.NUTS, tid, tdata, x0, st, 81000 + k)
+        o = oracle.run_chain(ol.NUTS, tid, tdata, x0, st, seed=81000 + k, rng_mode=ol.RNG_MT, sum_mode=ol.SUM_SEQ, chol_mode=1, dense_jacobian=1)
+        assert np.array_equal(o["draws"], ref, equal_nan=True), (k, kw)
+        assert o["n_accept"] == acc, (k, kw)
+        n_leapfrog += o["n_leapfrog"]
+    assert n_leapfrog >= 200_000, n_leapfrog
