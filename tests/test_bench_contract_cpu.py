@@ -33,3 +33,21 @@ def test_reference_arm_prints_one_line_with_the_contract_keys():
 
 def test_reference_arm_other_ranks_exit_without_work():
     assert _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}) == []
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback: on a box without a CUDA device the product arm exits non-zero and prints no result line."""
+    import ctypes
+
+    try:
+        have_gpu = ctypes.CDLL("libcuda.so.1").cuInit(0) == 0
+    except OSError:
+        have_gpu = False
+    if have_gpu:
+        import pytest
+
+        pytest.skip("a CUDA device is visible")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                       timeout=600, cwd=ROOT)
+    assert r.returncode != 0
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]
