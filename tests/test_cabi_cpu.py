@@ -206,3 +206,41 @@ def test_hot_kernels_keep_their_register_budget():
             assert v[0] <= 128 and v[3] == 0, (k, v)
         if k.startswith("hmc_half_kernel<"):
             assert v[0] <= 64 and v[1] == 0, (k, v)
+
+
+def test_host_side_preconditioner_algebra(api):
+    """csrc/host_linalg.cpp (no GPU): the one-time inverse and Cholesky factor of precond_mat / cov_mat that every dense-mass run
+    uploads (BMO_MATOPS_INV / BMO_MATOPS_CHOL_LOWER, src/hmc.cpp:58-59).  Against numpy; chol_mode 1 keeps precond_mat's strict
+    upper triangle like Eigen's matrixLLT(), chol_mode 0 zeroes it; not-positive-definite / singular input is reported,
+    not factorised."""
+    lib = ctypes.CDLL(api.LIB_PATH)
+    inv_fn = getattr(lib, "_ZN8mcmcb20021host_inverse_colmajorEPKdiPd")
+    chol_fn = getattr(lib, "_ZN8mcmcb20022host_cholesky_colmajorEPKdiiPd")
+    inv_fn.restype = chol_fn.restype = ctypes.c_bool
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(5)
+    for n in (1, 2, 7, 33, 128):
+        a = rng.normal(size=(n, n))
+        M = a @ a.T / n + np.eye(n)
+        M = (M + M.T) / 2
+        Mc = np.asfortranarray(M)                        # column-major bytes, as the C ABI takes precond_mat
+        out = np.zeros((n, n), order="F")
+        assert inv_fn(Mc.ctypes.data_as(dp), n, out.ctypes.data_as(dp))
+        assert np.abs(out @ M - np.eye(n)).max() <= 1e-12 * np.linalg.cond(M)
+        for mode in (0, 1):
+            L = np.zeros((n, n), order="F")
+            assert chol_fn(Mc.ctypes.data_as(dp), n, mode, L.ctypes.data_as(dp))
+            low = np.tril(L)
+            assert np.abs(low @ low.T - M).max() <= 1e-13 * np.abs(M).max() * n
+            assert np.abs(low - np.linalg.cholesky(M)).max() <= 1e-12
+            upper = L[np.triu_indices(n, 1)]
+            assert np.array_equal(upper, M[np.triu_indices(n, 1)] if mode == 1 else np.zeros_like(upper))
+    # a general (non-symmetric) matrix needs the row exchanges
+    G = np.asfortranarray(np.array([[0.0, 2.0, 1.0], [1.0, 0.0, 3.0], [4.0, 1.0, 0.0]]))
+    out = np.zeros((3, 3), order="F")
+    assert inv_fn(G.ctypes.data_as(dp), 3, out.ctypes.data_as(dp)) and np.abs(out @ G - np.eye(3)).max() <= 1e-14
+    bad = np.asfortranarray(np.array([[1.0, 2.0], [2.0, 1.0]]))           # indefinite
+    sing = np.asfortranarray(np.array([[1.0, 2.0], [2.0, 4.0]]))          # singular
+    tmp = np.zeros((2, 2), order="F")
+    assert not chol_fn(bad.ctypes.data_as(dp), 2, 1, tmp.ctypes.data_as(dp))
+    assert not inv_fn(sing.ctypes.data_as(dp), 2, tmp.ctypes.data_as(dp))
