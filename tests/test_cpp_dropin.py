@@ -61,6 +61,23 @@ def test_header_and_examples_compile_and_link():
     _build(os.path.join(ROOT, "tests", "cpp", "fp32_check.cpp"), os.path.join(BIN, "fp32_check_f64"), std="c++11")
 
 
+def test_host_preconditioner_algebra_is_bit_identical_to_the_reference_operations():
+    """tests/cpp/host_linalg_check.cpp: the inverse and the Cholesky factor the library computes on the host for precond_mat / cov_mat
+    equal, bit for bit, A.inverse() and A.llt().matrixLLT() of the (stand-in) Eigen the reference is built against — 96 matrices, n up to 128."""
+    from mcmc_b200 import api
+
+    os.makedirs(BIN, exist_ok=True)
+    exe = os.path.join(BIN, "host_linalg_check")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    libdir = os.path.dirname(api.LIB_PATH)
+    r = subprocess.run([cxx, "-std=c++14", "-O2", "-ffp-contract=off", "-Wall", "-I", os.path.join(ROOT, "oracle", "standin"),
+                        os.path.join(ROOT, "tests", "cpp", "host_linalg_check.cpp"), "-o", exe, "-L", libdir, "-lmcmc_b200", "-Wl,-rpath," + libdir],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "inverse_differs 0 cholesky_differs 0" in r.stdout, (r.stdout, r.stderr)
+
+
 @pytest.mark.gpu
 def test_dropin_program_reproduces_reference_goldens(engine):
     exe = _build(os.path.join(ROOT, "tests", "cpp", "dropin_check.cpp"), os.path.join(BIN, "dropin_check"), std="c++17")
