@@ -68,3 +68,20 @@ def test_sharded_runs_assemble_to_single_process_result():
         assert np.allclose(m, want.reshape(-1, D).mean(axis=0), rtol=1e-13, atol=1e-15)
         assert np.allclose(v, want.reshape(-1, D).var(axis=0, ddof=1), rtol=1e-12)
         assert np.allclose(rh, np.sqrt(((T - 1) / T * W + Bn) / W), rtol=1e-12)
+
+
+def test_chain_shard_is_a_contiguous_balanced_partition():
+    """mcmc_b200.dist.chain_shard for every (n_chains, world_size) a node can see: the shards tile [0, n_chains) in rank order,
+    sizes differ by at most one, remainders go to the lowest ranks — so chain_offset (the global chain id the Philox counter and
+    the MT seed are derived from) is the same whatever the number of ranks."""
+    from mcmc_b200.dist import chain_shard
+
+    for world in (1, 2, 3, 4, 7, 8, 16):
+        for n in list(range(0, 40)) + [511, 512, 513, 2048, 4096, 16384, 16385]:
+            nxt, sizes = 0, []
+            for r in range(world):
+                first, count = chain_shard(n, r, world)
+                assert first == nxt and count >= 0
+                nxt += count
+                sizes.append(count)
+            assert nxt == n and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)
