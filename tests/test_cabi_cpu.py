@@ -244,3 +244,32 @@ def test_host_side_preconditioner_algebra(api):
     tmp = np.zeros((2, 2), order="F")
     assert not chol_fn(bad.ctypes.data_as(dp), 2, 1, tmp.ctypes.data_as(dp))
     assert not inv_fn(sing.ctypes.data_as(dp), 2, tmp.ctypes.data_as(dp))
+
+
+def test_null_and_degenerate_arguments_never_crash(api):
+    """Every entry point that can be reached without a device answers null pointers and degenerate sizes with an error code
+    (and a message), never a crash — what a binding in another language relies on."""
+    c = ctypes
+    lib = api.load()
+    lib.mcmcb200_last_error.restype = c.c_char_p
+    lib.mcmcb200_target_data_len.restype = c.c_int64
+    buf = np.zeros(16)
+    p = buf.ctypes.data_as(c.c_void_p)
+    assert lib.mcmcb200_target_lookup(None) == -1 and lib.mcmcb200_target_lookup(b"") == -1
+    assert [lib.mcmcb200_target_data_len(2, -5), lib.mcmcb200_target_data_len(-1, 5), lib.mcmcb200_target_data_len(2, 0)] == [-1, -1, -1]
+    assert lib.mcmcb200_metric_lookup(None, None, None) != 0 and b"unknown metric" in lib.mcmcb200_last_error()
+    assert lib.mcmcb200_register_target(None, None) < 0
+    assert lib.mcmcb200_mt19937_tape(c.c_uint64(1), c.c_int64(0), c.c_int64(0), 4, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_mt19937_tape(c.c_uint64(1), c.c_int64(0), c.c_int64(0), 4, p) == 0          # nothing to generate is not an error
+    assert lib.mcmcb200_mt19937_tape(c.c_uint64(1), c.c_int64(-1), c.c_int64(1), 4, p) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_de_tape(c.c_uint64(1), c.c_int64(2), 4, c.c_int64(1), c.c_double(1e-4), p) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_philox_stream(c.c_uint64(1), c.c_int64(0), c.c_int64(0), 4, 3, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_target_eval(0, None, c.c_int64(0), 4, None, c.c_int64(0), None, None, 0) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_comm_unique_id(None, c.c_size_t(0)) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_comm_init(None, c.c_size_t(0), 2, 0, 0, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_comm_destroy(None) == 0
+    assert lib.mcmcb200_allgather_draws(None, None, None, c.c_int64(1), 4, None, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_fp64_peak(0, None) == api.ERR_INVALID_ARG
+    assert lib.mcmcb200_summarize_draws(None, 0, c.c_int64(1), c.c_int64(1), 4, -1, None, None) == api.ERR_INVALID_ARG
+    lib.mcmcb200_host_free(None)
+    lib.mcmcb200_release_workspace()
