@@ -1,6 +1,6 @@
 // TEST ONLY (CPU).  The product's one-time host algebra on precond_mat / cov_mat (mcmc_b200/csrc/host_linalg.cpp) against the
 // operations the reference performs on the same matrix — BMO_MATOPS_INV = A.inverse(), BMO_MATOPS_CHOL_LOWER = A.llt().matrixLLT()
-// (include/BaseMatrixOps/include/core/inverse.hpp, cholesky.hpp:37; src/hmc.cpp:58-59) — evaluated through the stand-in Eigen the
+// (include/BaseMatrixOps/include/core/inv.hpp:34, cholesky.hpp:37; src/hmc.cpp:58-59) — evaluated through the stand-in Eigen the
 // reference is compiled against in oracle/_ref.  Bit for bit: with the same inverse and factor on the device, a dense-mass chain in
 // STRICT arithmetic starts from the same operands as the reference's.
 #include <Eigen/Dense>
